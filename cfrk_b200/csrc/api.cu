@@ -1,0 +1,256 @@
+// api.cu -- the C ABI of libcfrk_b200.so (include/cfrk_b200.h) over the kernels.
+//
+// cfrk_count_dense_host is the operator that replaces the reference's kmer_main
+// (src/kmer_main.cu:20-128): same inputs and output, but
+//   * device buffers are cached per host thread instead of 5 cudaMalloc + 5 cudaFree per call
+//     (src/kmer_main.cu:59-63,120-124),
+//   * rows leave the device through a two-slot ring so that the device->host copy of slice i
+//     overlaps the kernel of slice i+1 (the reference does one synchronous cudaMemcpy of the
+//     whole Freq, src/kmer_main.cu:116),
+//   * errors are returned, not printed.
+#include "../../include/cfrk_b200.h"
+#include "kernels.h"
+#include "kmer_device.cuh"
+#include "internal.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+namespace {
+
+thread_local std::string t_err;
+
+int fail(int code, const char* what)
+{
+    t_err = what;
+    return code;
+}
+int fail_cuda(cudaError_t e, const char* where)
+{
+    t_err = std::string(where) + ": " + cudaGetErrorString(e);
+    return CFRK_ECUDA;
+}
+#define CU(call)                                            \
+    do {                                                    \
+        cudaError_t e_ = (call);                            \
+        if (e_ != cudaSuccess) return fail_cuda(e_, #call); \
+    } while (0)
+
+constexpr size_t kRingSlotBytes = (size_t)256 << 20;  // rows per kernel launch of the host path
+
+// Per host thread: kmer_main is called concurrently from several pthreads in the reference
+// driver (src/main.cu:279-289), each needs its own streams and scratch.
+struct HostCtx {
+    int device = -1;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaEvent_t done[2] = {nullptr, nullptr}, drained[2] = {nullptr, nullptr};
+    void* d_bases = nullptr;  size_t cap_bases = 0;
+    int64_t* d_start = nullptr; int32_t* d_length = nullptr; size_t cap_reads = 0;
+    int32_t* d_ring[2] = {nullptr, nullptr}; size_t cap_ring = 0;
+
+    void release()
+    {
+        if (device < 0) return;
+        cudaSetDevice(device);
+        cudaFree(d_bases); cudaFree(d_start); cudaFree(d_length);
+        cudaFree(d_ring[0]); cudaFree(d_ring[1]);
+        for (int i = 0; i < 2; i++) {
+            if (done[i]) cudaEventDestroy(done[i]);
+            if (drained[i]) cudaEventDestroy(drained[i]);
+        }
+        if (compute) cudaStreamDestroy(compute);
+        if (copy) cudaStreamDestroy(copy);
+        *this = HostCtx();
+    }
+    ~HostCtx() { /* process teardown: the CUDA context may already be gone; leak on purpose */ }
+};
+thread_local HostCtx t_ctx;
+
+int ensure_ctx(int device)
+{
+    HostCtx& c = t_ctx;
+    if (c.device == device) { CU(cudaSetDevice(device)); return CFRK_OK; }
+    c.release();
+    CU(cudaSetDevice(device));
+    CU(cudaStreamCreateWithFlags(&c.compute, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        CU(cudaEventCreateWithFlags(&c.done[i], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&c.drained[i], cudaEventDisableTiming));
+    }
+    c.device = device;
+    return CFRK_OK;
+}
+
+template <class T>
+int grow(T*& p, size_t& cap, size_t need)
+{
+    if (need <= cap) return CFRK_OK;
+    if (p) { cudaFree(p); p = nullptr; cap = 0; }
+    size_t want = need + need / 4 + 256;
+    cudaError_t e = cudaMalloc(reinterpret_cast<void**>(&p), want);
+    if (e != cudaSuccess) { t_err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return CFRK_ENOMEM; }
+    cap = want;
+    return CFRK_OK;
+}
+
+int check_common(int fmt, int k, int kmax, int mode)
+{
+    if (fmt != CFRK_FMT_CODES && fmt != CFRK_FMT_ASCII) return fail(CFRK_EINVAL, "fmt must be CFRK_FMT_CODES or CFRK_FMT_ASCII");
+    if (k < 1 || k > kmax) return fail(CFRK_EINVAL, "k out of range for this entry point");
+    if (mode != CFRK_MODE_COMPAT && mode != CFRK_MODE_EXACT) return fail(CFRK_EINVAL, "mode must be CFRK_MODE_COMPAT or CFRK_MODE_EXACT");
+    return CFRK_OK;
+}
+
+}  // namespace
+
+namespace cfrk {
+void set_last_error(const std::string& msg) { t_err = msg; }
+}
+
+extern "C" {
+
+const char* cfrk_version(void) { return "cfrk_b200 0.1 (sm_100a)"; }
+const char* cfrk_last_error(void) { return t_err.c_str(); }
+uint64_t cfrk_launch_count(void) { return cfrk::launch_count(); }
+
+int cfrk_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int cfrk_dense_reads_per_tile(int k) { return cfrk::dense_reads_per_tile(k); }
+
+int cfrk_count_dense_device(const void* d_bases, int fmt, const int64_t* d_start, const int32_t* d_length,
+                            int64_t nN, int64_t nS, int64_t read_begin, int64_t read_end, int k, int mode,
+                            int64_t chunk_size, int64_t first_read_index, int32_t* d_freq, void* stream)
+{
+    int rc = check_common(fmt, k, CFRK_DENSE_MAX_K, mode);
+    if (rc) return rc;
+    if (nS < 0 || nN < 0 || read_begin < 0 || read_end > nS || read_begin > read_end)
+        return fail(CFRK_EINVAL, "bad read range");
+    if (chunk_size < 0 || first_read_index < 0) return fail(CFRK_EINVAL, "negative chunk_size / first_read_index");
+    if (read_begin == read_end) return CFRK_OK;
+    if (!d_bases || !d_start || !d_length || !d_freq) return fail(CFRK_EINVAL, "null device pointer");
+    if ((reinterpret_cast<uintptr_t>(d_bases) & 15) || (reinterpret_cast<uintptr_t>(d_freq) & 15))
+        return fail(CFRK_EINVAL, "d_bases and d_freq must be 16-byte aligned");
+    if (read_begin % cfrk::dense_reads_per_tile(k))
+        return fail(CFRK_EINVAL, "read_begin must be a multiple of cfrk_dense_reads_per_tile(k)");
+    cudaError_t e = cfrk::launch_dense(d_bases, fmt, d_start, d_length, nS, read_begin, read_end, k, mode,
+                                       chunk_size, first_read_index, d_freq, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(e, "dense_count_kernel launch");
+    return CFRK_OK;
+}
+
+int cfrk_count_dense_host(const void* bases, int fmt, const int64_t* start, const int32_t* length,
+                          int64_t nN, int64_t nS, int k, int mode, int device, int32_t* freq_out)
+{
+    int rc = check_common(fmt, k, CFRK_DENSE_MAX_K, mode);
+    if (rc) return rc;
+    if (nS < 0 || nN < 0) return fail(CFRK_EINVAL, "negative size");
+    if (nS == 0) return CFRK_OK;
+    if (!bases || !start || !length || !freq_out) return fail(CFRK_EINVAL, "null pointer");
+    if (cfrk_device_count() <= device || device < 0)
+        return fail(CFRK_ECUDA, "no such CUDA device (this library has no CPU fallback)");
+    rc = ensure_ctx(device);
+    if (rc) return rc;
+    HostCtx& c = t_ctx;
+
+    const size_t fourk = (size_t)1 << (2 * k);
+    const size_t row_bytes = fourk * 4;
+    const int rpt = cfrk::dense_reads_per_tile(k);
+    int64_t slice = (int64_t)std::max<size_t>(1, kRingSlotBytes / row_bytes);
+    slice = std::max<int64_t>(rpt, slice / rpt * rpt);
+    if (slice > nS) slice = (nS + rpt - 1) / rpt * rpt;
+    const int64_t nslices = (nS + slice - 1) / slice;
+
+    if ((rc = grow(c.d_bases, c.cap_bases, (size_t)nN + CFRK_PAD))) return rc;
+    {
+        size_t need = (size_t)nS;
+        if (need > c.cap_reads) {
+            cudaFree(c.d_start); cudaFree(c.d_length); c.d_start = nullptr; c.d_length = nullptr; c.cap_reads = 0;
+            size_t want = need + need / 4 + 64;
+            if (cudaMalloc(reinterpret_cast<void**>(&c.d_start), want * 8) != cudaSuccess ||
+                cudaMalloc(reinterpret_cast<void**>(&c.d_length), want * 4) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(CFRK_ENOMEM, "cudaMalloc(start/length)");
+            }
+            c.cap_reads = want;
+        }
+    }
+    {
+        size_t need = (size_t)std::min<int64_t>(slice, nS) * row_bytes;
+        if (need > c.cap_ring) {
+            cudaFree(c.d_ring[0]); cudaFree(c.d_ring[1]); c.d_ring[0] = c.d_ring[1] = nullptr; c.cap_ring = 0;
+            const int slots = nslices > 1 ? 2 : 1;
+            for (int i = 0; i < slots; i++)
+                if (cudaMalloc(reinterpret_cast<void**>(&c.d_ring[i]), need) != cudaSuccess) {
+                    cudaGetLastError();
+                    return fail(CFRK_ENOMEM, "cudaMalloc(row ring)");
+                }
+            c.cap_ring = need;
+        } else if (nslices > 1 && !c.d_ring[1]) {
+            if (cudaMalloc(reinterpret_cast<void**>(&c.d_ring[1]), c.cap_ring) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(CFRK_ENOMEM, "cudaMalloc(row ring)");
+            }
+        }
+    }
+
+    CU(cudaMemcpyAsync(c.d_bases, bases, (size_t)nN, cudaMemcpyHostToDevice, c.compute));
+    // the kernel loads whole 16-byte blocks: define the tail
+    CU(cudaMemsetAsync(static_cast<char*>(c.d_bases) + nN, 0xFF, CFRK_PAD, c.compute));
+    CU(cudaMemcpyAsync(c.d_start, start, (size_t)nS * 8, cudaMemcpyHostToDevice, c.compute));
+    CU(cudaMemcpyAsync(c.d_length, length, (size_t)nS * 4, cudaMemcpyHostToDevice, c.compute));
+
+    for (int64_t s = 0; s < nslices; s++) {
+        const int slot = (int)(s & 1);
+        const int64_t r0 = s * slice, r1 = std::min(nS, r0 + slice);
+        if (s >= 2) CU(cudaStreamWaitEvent(c.compute, c.drained[slot], 0));
+        cudaError_t e = cfrk::launch_dense(c.d_bases, fmt, c.d_start, c.d_length, nS, r0, r1, k, mode,
+                                           0, 0, c.d_ring[slot], c.compute);
+        if (e != cudaSuccess) return fail_cuda(e, "dense_count_kernel launch");
+        CU(cudaEventRecord(c.done[slot], c.compute));
+        CU(cudaStreamWaitEvent(c.copy, c.done[slot], 0));
+        CU(cudaMemcpyAsync(freq_out + (size_t)r0 * fourk, c.d_ring[slot], (size_t)(r1 - r0) * row_bytes,
+                           cudaMemcpyDeviceToHost, c.copy));
+        CU(cudaEventRecord(c.drained[slot], c.copy));
+    }
+    CU(cudaStreamSynchronize(c.copy));
+    CU(cudaStreamSynchronize(c.compute));
+    return CFRK_OK;
+}
+
+int cfrk_encode_2bit_device(const void* d_bases, int fmt, int64_t n, uint32_t* d_codes, uint16_t* d_valid,
+                            void* stream)
+{
+    if (fmt != CFRK_FMT_CODES && fmt != CFRK_FMT_ASCII) return fail(CFRK_EINVAL, "bad fmt");
+    if (n < 0) return fail(CFRK_EINVAL, "negative size");
+    if (n == 0) return CFRK_OK;
+    if (!d_bases || !d_codes || !d_valid) return fail(CFRK_EINVAL, "null device pointer");
+    if (reinterpret_cast<uintptr_t>(d_bases) & 15) return fail(CFRK_EINVAL, "d_bases must be 16-byte aligned");
+    cudaError_t e = cfrk::launch_encode_2bit(d_bases, fmt, n, d_codes, d_valid, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(e, "encode_2bit_kernel launch");
+    return CFRK_OK;
+}
+
+int cfrk_global_hist_device(const void* d_bases, int fmt, const int64_t* d_start, const int32_t* d_length,
+                            int64_t nN, int64_t nS, int k, uint32_t* d_hist, void* stream)
+{
+    int rc = check_common(fmt, k, CFRK_HIST_MAX_K, CFRK_MODE_EXACT);
+    if (rc) return rc;
+    if (nS < 0 || nN < 0) return fail(CFRK_EINVAL, "negative size");
+    if (nS == 0) return CFRK_OK;
+    if (!d_bases || !d_start || !d_length || !d_hist) return fail(CFRK_EINVAL, "null device pointer");
+    if (reinterpret_cast<uintptr_t>(d_bases) & 15) return fail(CFRK_EINVAL, "d_bases must be 16-byte aligned");
+    cudaError_t e = cfrk::launch_global_hist(d_bases, fmt, d_start, d_length, nS, k, d_hist,
+                                             static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(e, "global_hist_kernel launch");
+    return CFRK_OK;
+}
+
+}  // extern "C"

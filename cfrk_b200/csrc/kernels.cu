@@ -1,0 +1,331 @@
+// kernels.cu -- sm_100a kernels of the CFRK hot path and their launchers.
+//
+//   dense_count_kernel   per-read dense int32 rows, k <= 8   (replaces SetMatrix x2 + ComputeIndex +
+//                        ComputeFreqNew, reference src/kmer_kernel.cu:6-90, src/kmer_main.cu:107-111)
+//   global_hist_kernel   whole-dataset histogram, k <= 15    (no reference counterpart; config C5)
+//   encode_2bit_kernel   bases -> packed 2-bit + validity    (replaces src/fastaIO.h:123-139)
+//
+// Compile: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo
+#include "kernels.h"
+#include "kmer_device.cuh"
+
+#include <atomic>
+
+namespace cfrk {
+
+static std::atomic<uint64_t> g_launches{0};
+uint64_t launch_count() { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------
+// Tile geometry.  A tile is TILE_BINS consecutive int32 of the output, i.e. a contiguous
+// TILE_BINS*4-byte span of HBM that one CTA builds in shared memory and ships with one TMA
+// bulk store:  k <= 6: RPT whole rows (reads) per tile;  k = 7, 8: one row = SUB tiles.
+template <int K, int TILE_BINS_T>
+struct Geo {
+    static constexpr int BINS = 1 << (2 * K);
+    static constexpr int SUB = BINS > TILE_BINS_T ? BINS / TILE_BINS_T : 1;
+    static constexpr int RPT_RAW = BINS >= TILE_BINS_T ? 1 : TILE_BINS_T / BINS;
+    static constexpr int RPT = RPT_RAW > kMaxGroupReads ? kMaxGroupReads : RPT_RAW;
+    static constexpr int TILE_BINS = SUB > 1 ? TILE_BINS_T : RPT * BINS;
+    static constexpr int TILE_BYTES = TILE_BINS * 4;
+    static constexpr int TABLE_READS = RPT + 1;  // + halo read (compat spill)
+    // shared memory: NBUF tile buffers, then the read table
+    static constexpr int table_bytes() { return TABLE_READS * 16 + (TABLE_READS + 1) * 4 + 16; }
+};
+
+template <int K, int TILE_BINS_T>
+struct DenseSink {
+    using G = Geo<K, TILE_BINS_T>;
+    uint32_t* hist;   // current tile buffer
+    int sub;          // which TILE_BINS-slice of the row (k >= 7)
+    bool has_last;    // tile holds bin 4^k-1 of its rows
+    int qb, period;   // table-local reads qb, qb+period, ... open a reference chunk (period 0: none)
+    __device__ __forceinline__ void kmer(int q, uint32_t idx)
+    {
+        if (G::SUB > 1) {
+            if ((int)(idx / G::TILE_BINS) != sub) return;
+            idx &= G::TILE_BINS - 1;
+        }
+        atomicAdd(&hist[q * G::BINS * (G::SUB > 1 ? 0 : 1) + idx], 1u);
+    }
+    // the reference adds at Freq[4^k*i + (-1)]: last bin of read i-1 (src/kmer_kernel.cu:84-87);
+    // q == 0 belongs to the previous tile (counted there through its halo read); for the first
+    // read of a reference chunk (a separate kmer_main call) it is the lost Freq[-1] store.
+    __device__ __forceinline__ void invalid(int q, int n)
+    {
+        if (period > 0 && q >= qb && (q - qb) % period == 0) return;
+        if (q >= 1 && has_last)
+            atomicAdd(&hist[(G::SUB > 1 ? 0 : (q - 1) * G::BINS) + (G::SUB > 1 ? G::TILE_BINS : G::BINS) - 1], (uint32_t)n);
+    }
+};
+
+struct DenseArgs {
+    const uint8_t* bases;
+    const int64_t* start;
+    const int32_t* length;
+    int64_t nS;          // reads in the batch (halo / spill scope)
+    int64_t read_begin;  // rows [read_begin, read_end) are produced by this launch
+    int64_t read_end;
+    uint32_t* out;       // row read_begin at out[0]
+    int mode;
+    int64_t num_tiles;
+    int64_t chunk_size;   // compat: reads with (index_base + i) % chunk_size == 0 start a reference
+    int64_t index_base;   //         chunk (their spill is dropped); 0 = only read 0 does
+};
+
+template <int K, int FMT, int TILE_BINS_T, int NTHREADS, int NBUF>
+__global__ void __launch_bounds__(NTHREADS) dense_count_kernel(const DenseArgs a)
+{
+    using G = Geo<K, TILE_BINS_T>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint32_t* bufs = reinterpret_cast<uint32_t*>(smem);
+    unsigned char* tp = smem + (size_t)NBUF * G::TILE_BYTES;
+    ReadTable tb;
+    tb.start = reinterpret_cast<int64_t*>(tp);
+    tb.tend = reinterpret_cast<int32_t*>(tp + G::TABLE_READS * 8);
+    tb.extra = reinterpret_cast<int32_t*>(tp + G::TABLE_READS * 12);
+    tb.cum = reinterpret_cast<uint32_t*>(tp + G::TABLE_READS * 16);
+
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x, ++it) {
+        const int64_t group = tile / G::SUB;
+        const int sub = (int)(tile - group * G::SUB);
+        const int64_t r0 = a.read_begin + group * G::RPT;
+        const int nrows = (int)min((int64_t)G::RPT, a.read_end - r0);
+        const bool has_last = (sub == G::SUB - 1);
+        // table-local reads qb, qb+period, ... open a reference chunk: their spill is dropped
+        int qb = 0, period = 0;
+        if (a.chunk_size > 0) {
+            const int64_t phase = (a.index_base + r0) % a.chunk_size;
+            const int64_t first = phase == 0 ? 0 : a.chunk_size - phase;
+            if (first <= G::TABLE_READS) {
+                qb = (int)first;
+                period = (int)min(a.chunk_size, (int64_t)(4 * kMaxGroupReads));
+            }
+        } else if (r0 == 0) {
+            period = 4 * kMaxGroupReads;  // only read 0
+        }
+        const bool next_opens_chunk = period > 0 && nrows >= qb && (nrows - qb) % period == 0;
+        const bool halo = a.mode == MODE_COMPAT && has_last && (r0 + nrows < a.nS) && !next_opens_chunk;
+        const int nreads = nrows + (halo ? 1 : 0);
+        uint32_t* hist = bufs + (size_t)(it % NBUF) * G::TILE_BINS;
+
+        // the TMA store that last used this buffer (NBUF tiles ago) must have read it out
+        if (threadIdx.x == 0) bulk_wait_read<NBUF - 1>();
+        fill_read_table<K>(tb, a.start, a.length, r0, nreads, a.mode);
+        __syncthreads();
+
+        {   // zero the tile (replaces SetMatrix(d_Freq, 0), src/kmer_main.cu:108) ...
+            uint4* h4 = reinterpret_cast<uint4*>(hist);
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll 4
+            for (int i = threadIdx.x; i < G::TILE_BYTES / 16; i += NTHREADS) h4[i] = z;
+            // ... while warp 0 turns block counts into item offsets
+            if (threadIdx.x < 32) scan_read_table(tb, nreads);
+        }
+        __syncthreads();
+
+        DenseSink<K, TILE_BINS_T> sink{hist, sub, has_last, qb, period};
+        for_each_window<K, FMT, G::TABLE_READS>(a.bases, tb, nreads, nrows, a.mode, sink);
+
+        fence_async_proxy_shared();  // make the shared-memory counts visible to the TMA engine
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const int64_t row0 = (r0 - a.read_begin);
+            uint32_t* dst = a.out + row0 * G::BINS + (int64_t)sub * G::TILE_BINS;
+            const uint32_t bytes = G::SUB > 1 ? (uint32_t)G::TILE_BYTES : (uint32_t)nrows * G::BINS * 4u;
+            bulk_store_tile(dst, hist, bytes);
+        }
+    }
+    if (threadIdx.x == 0) bulk_wait_all();
+}
+
+// ------------------------------------------------------------------------------------------
+constexpr int kTileBins = 4096;  // 16 KiB tiles
+constexpr int kDenseThreads = 256;
+constexpr int kDenseBufs = 2;
+
+template <int K, int FMT>
+static cudaError_t launch_dense_k(const DenseArgs& a0, cudaStream_t st)
+{
+    using G = Geo<K, kTileBins>;
+    auto kern = dense_count_kernel<K, FMT, kTileBins, kDenseThreads, kDenseBufs>;
+    const int smem = kDenseBufs * G::TILE_BYTES + G::table_bytes();
+    static thread_local int configured_dev = -1;
+    static thread_local int ctas_per_sm = 0, num_sms = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (configured_dev != dev) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kDenseThreads, smem);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        configured_dev = dev;
+    }
+    DenseArgs a = a0;
+    const int64_t groups = (a.read_end - a.read_begin + G::RPT - 1) / G::RPT;
+    a.num_tiles = groups * G::SUB;
+    if (a.num_tiles <= 0) return cudaSuccess;
+    const int64_t resident = (int64_t)num_sms * ctas_per_sm;  // persistent: one wave
+    const unsigned grid = (unsigned)(a.num_tiles < resident ? a.num_tiles : resident);
+    kern<<<grid, kDenseThreads, smem, st>>>(a);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+template <int FMT>
+static cudaError_t launch_dense_fmt(int k, const DenseArgs& a, cudaStream_t st)
+{
+    switch (k) {
+    case 1: return launch_dense_k<1, FMT>(a, st);
+    case 2: return launch_dense_k<2, FMT>(a, st);
+    case 3: return launch_dense_k<3, FMT>(a, st);
+    case 4: return launch_dense_k<4, FMT>(a, st);
+    case 5: return launch_dense_k<5, FMT>(a, st);
+    case 6: return launch_dense_k<6, FMT>(a, st);
+    case 7: return launch_dense_k<7, FMT>(a, st);
+    case 8: return launch_dense_k<8, FMT>(a, st);
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+int dense_reads_per_tile(int k)
+{
+    switch (k) {
+    case 1: return Geo<1, kTileBins>::RPT;
+    case 2: return Geo<2, kTileBins>::RPT;
+    case 3: return Geo<3, kTileBins>::RPT;
+    case 4: return Geo<4, kTileBins>::RPT;
+    case 5: return Geo<5, kTileBins>::RPT;
+    default: return 1;
+    }
+}
+
+cudaError_t launch_dense(const void* bases, int fmt, const int64_t* start, const int32_t* length,
+                         int64_t nS, int64_t read_begin, int64_t read_end, int k, int mode,
+                         int64_t chunk_size, int64_t index_base, int32_t* out, cudaStream_t st)
+{
+    DenseArgs a;
+    a.bases = static_cast<const uint8_t*>(bases);
+    a.start = start; a.length = length; a.nS = nS;
+    a.read_begin = read_begin; a.read_end = read_end;
+    a.out = reinterpret_cast<uint32_t*>(out);
+    a.mode = mode; a.num_tiles = 0;
+    a.chunk_size = chunk_size; a.index_base = index_base;
+    return fmt == FMT_ASCII ? launch_dense_fmt<FMT_ASCII>(k, a, st) : launch_dense_fmt<FMT_CODES>(k, a, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// Whole-dataset histogram: same item loop, sink = one red.global per valid window.
+struct HistSink {
+    uint32_t* hist;
+    __device__ __forceinline__ void kmer(int, uint32_t idx) { atomicAdd(&hist[idx], 1u); }
+    __device__ __forceinline__ void invalid(int, int) {}
+};
+
+constexpr int kHistGroup = 128;  // reads per work group
+constexpr int kHistThreads = 256;
+
+template <int K, int FMT>
+__global__ void __launch_bounds__(kHistThreads) global_hist_kernel(const uint8_t* __restrict__ bases,
+                                                                 const int64_t* __restrict__ start,
+                                                                 const int32_t* __restrict__ length,
+                                                                 int64_t nS, uint32_t* hist)
+{
+    __shared__ int64_t s_start[kHistGroup];
+    __shared__ int32_t s_tend[kHistGroup], s_extra[kHistGroup];
+    __shared__ uint32_t s_cum[kHistGroup + 1];
+    ReadTable tb{s_start, s_tend, s_extra, s_cum};
+    HistSink sink{hist};
+    const int64_t groups = (nS + kHistGroup - 1) / kHistGroup;
+    for (int64_t g = blockIdx.x; g < groups; g += gridDim.x) {
+        const int64_t r0 = g * kHistGroup;
+        const int n = (int)min((int64_t)kHistGroup, nS - r0);
+        __syncthreads();  // previous group's item loop is done with the table
+        fill_read_table<K>(tb, start, length, r0, n, MODE_EXACT);
+        __syncthreads();
+        if (threadIdx.x < 32) scan_read_table(tb, n);
+        __syncthreads();
+        for_each_window<K, FMT, kHistGroup>(bases, tb, n, n, MODE_EXACT, sink);
+    }
+}
+
+template <int K, int FMT>
+static cudaError_t launch_hist_k(const void* bases, const int64_t* start, const int32_t* length,
+                                 int64_t nS, uint32_t* hist, cudaStream_t st)
+{
+    auto kern = global_hist_kernel<K, FMT>;
+    int dev = 0, num_sms = 0, per_sm = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (e != cudaSuccess) return e;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kHistThreads, 0);
+    if (e != cudaSuccess) return e;
+    const int64_t groups = (nS + kHistGroup - 1) / kHistGroup;
+    if (groups <= 0) return cudaSuccess;
+    const int64_t resident = (int64_t)num_sms * (per_sm < 1 ? 1 : per_sm);
+    const unsigned grid = (unsigned)(groups < resident ? groups : resident);
+    kern<<<grid, kHistThreads, 0, st>>>(static_cast<const uint8_t*>(bases), start, length, nS, hist);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+template <int FMT>
+static cudaError_t launch_hist_fmt(int k, const void* b, const int64_t* s, const int32_t* l, int64_t nS,
+                                   uint32_t* h, cudaStream_t st)
+{
+    switch (k) {
+#define CASE(KK) case KK: return launch_hist_k<KK, FMT>(b, s, l, nS, h, st);
+    CASE(1) CASE(2) CASE(3) CASE(4) CASE(5) CASE(6) CASE(7) CASE(8) CASE(9) CASE(10)
+    CASE(11) CASE(12) CASE(13) CASE(14) CASE(15)
+#undef CASE
+    default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_global_hist(const void* bases, int fmt, const int64_t* start, const int32_t* length,
+                               int64_t nS, int k, uint32_t* hist, cudaStream_t st)
+{
+    return fmt == FMT_ASCII ? launch_hist_fmt<FMT_ASCII>(k, bases, start, length, nS, hist, st)
+                            : launch_hist_fmt<FMT_CODES>(k, bases, start, length, nS, hist, st);
+}
+
+// ------------------------------------------------------------------------------------------
+// bases -> packed 2-bit words + validity masks; one 16-byte block per thread.
+template <int FMT>
+__global__ void __launch_bounds__(256) encode_2bit_kernel(const uint8_t* __restrict__ bases, int64_t nblocks,
+                                                          int64_t n, uint32_t* __restrict__ codes,
+                                                          uint16_t* __restrict__ valid)
+{
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nblocks;
+         b += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t c, v;
+        encode16<FMT>(ld_block(bases + b * 16), c, v);
+        const int64_t rem = n - b * 16;  // bytes of this block inside the buffer
+        if (rem < 16) v &= ~from_pos((int)rem);
+        codes[b] = c;
+        valid[b] = (uint16_t)v;
+    }
+}
+
+cudaError_t launch_encode_2bit(const void* bases, int fmt, int64_t n, uint32_t* codes, uint16_t* valid,
+                               cudaStream_t st)
+{
+    const int64_t nblocks = (n + 15) / 16;
+    if (nblocks <= 0) return cudaSuccess;
+    int64_t grid = (nblocks + 255) / 256;
+    if (grid > 148 * 32) grid = 148 * 32;
+    if (fmt == FMT_ASCII)
+        encode_2bit_kernel<FMT_ASCII><<<(unsigned)grid, 256, 0, st>>>(static_cast<const uint8_t*>(bases), nblocks, n, codes, valid);
+    else
+        encode_2bit_kernel<FMT_CODES><<<(unsigned)grid, 256, 0, st>>>(static_cast<const uint8_t*>(bases), nblocks, n, codes, valid);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+}  // namespace cfrk

@@ -1,0 +1,27 @@
+// kernels.h -- launchers of the sm_100a kernels (kernels.cu); internal to libcfrk_b200.so.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cfrk {
+
+// Rows [read_begin, read_end) of a batch of nS reads -> out[(i-read_begin)*4^k ..]; k in 1..8.
+// compat: read i opens a reference chunk (its spill is dropped) iff i == 0 when chunk_size == 0,
+// else iff (index_base + i) % chunk_size == 0.
+cudaError_t launch_dense(const void* bases, int fmt, const int64_t* start, const int32_t* length,
+                         int64_t nS, int64_t read_begin, int64_t read_end, int k, int mode,
+                         int64_t chunk_size, int64_t index_base, int32_t* out, cudaStream_t st);
+int dense_reads_per_tile(int k);
+
+// hist[4^k] += exact-mode k-mer counts of the whole batch; k in 1..15.
+cudaError_t launch_global_hist(const void* bases, int fmt, const int64_t* start, const int32_t* length,
+                               int64_t nS, int k, uint32_t* hist, cudaStream_t st);
+
+// n bytes of bases -> ceil(n/16) words of 2-bit codes + 16-bit validity masks.
+cudaError_t launch_encode_2bit(const void* bases, int fmt, int64_t n, uint32_t* codes, uint16_t* valid,
+                               cudaStream_t st);
+
+uint64_t launch_count();
+
+}  // namespace cfrk

@@ -1,0 +1,255 @@
+// kmer_device.cuh -- device-side building blocks of the B200 k-mer counting path.
+//
+// Replaces the reference's ComputeIndex (src/kmer_kernel.cu:21-49: k byte loads + k powf
+// per position, Index[] written to HBM) and ComputeFreqNew (src/kmer_kernel.cu:73-90: one
+// 1024-thread block per read, one L2 atomic per k-mer) with one fused pass in which
+//   * a lane owns one 16-byte aligned block of the bases buffer (one 128-bit load),
+//   * the block is encoded in registers to 16 x 2-bit codes + a 16-bit validity mask,
+//   * the k-1 bases of context come from the previous lane by warp shuffle,
+//   * window validity for all 16 positions is one bit-parallel AND chain,
+//   * the index of the window ending at base j is one funnel shift of (carry:codes).
+// Nothing but the bases and the result rows ever touches HBM.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cfrk {
+
+constexpr int FMT_CODES = 0;
+constexpr int FMT_ASCII = 1;
+constexpr int MODE_COMPAT = 0;
+constexpr int MODE_EXACT = 1;
+constexpr int kRefBlockThreads = 1024;  // reference blockDim (src/kmer_main.cu:82)
+constexpr int kMaxGroupReads = 256;     // reads per work group (tile) at most
+
+// ------------------------------------------------------------------------------------------
+// 128-bit streaming load of one block of bases (read once: keep it out of L1)
+__device__ __forceinline__ uint4 ld_block(const uint8_t* p)
+{
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// 4 bases (one little-endian 32-bit word, byte 0 = first base) -> 8 bits of codes (first
+// base in bits 7:6) and a 4-bit validity mask (first base in bit 3).
+//
+// ASCII: code = ((c>>1)^(c>>2))&3 maps A/C/G/T (either case) to 0/1/2/3 (src/fastaIO.h:123-139);
+// a byte is valid iff (c & 0xDF) equals the letter its code stands for, checked for the 4
+// bytes at once with a PRMT table lookup.  CODES: value & 3, valid iff bit 7 is clear
+// (the only negative value the reference layout holds is -1, src/fastaIO.h:137).
+template <int FMT>
+__device__ __forceinline__ void encode4(uint32_t w, uint32_t& codes8, uint32_t& valid4)
+{
+    uint32_t x, z;
+    if (FMT == FMT_ASCII) {
+        x = ((w >> 1) ^ (w >> 2)) & 0x03030303u;
+        // selector nibbles (c0, c2, c1, c3): expected letters in byte order (0, 2, 1, 3)
+        uint32_t sel = (x | (x >> 12)) & 0x3333u;
+        uint32_t expect = __byte_perm(0x54474341u /* "ACGT" */, 0u, sel);
+        uint32_t d = (__byte_perm(w, 0u, 0x3120u) & 0xDFDFDFDFu) ^ expect;
+        // bit 7 of each byte <- (byte == 0)
+        z = ~(((d & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | d) & 0x80808080u;
+        // bits 7 (base0), 23 (base1), 15 (base2), 31 (base3) -> bits 35, 34, 33, 32
+        valid4 = __umulhi(z, (1u << 28) | (1u << 18) | (1u << 11) | (1u << 1)) & 0xFu;
+    } else {
+        x = w & 0x03030303u;
+        z = ~w & 0x80808080u;
+        // bits 7, 15, 23, 31 (bases 0..3) -> bits 35, 34, 33, 32
+        valid4 = __umulhi(z, (1u << 28) | (1u << 19) | (1u << 10) | (1u << 1)) & 0xFu;
+    }
+    // 2-bit fields at bits 0, 8, 16, 24 -> bits 30, 28, 26, 24 (no overlapping partial products)
+    codes8 = (x * 0x40100401u) >> 24;
+}
+
+// 16 bases -> codes (base j in bits 31-2j:30-2j) and valid (base j in bit 15-j)
+template <int FMT>
+__device__ __forceinline__ void encode16(const uint4 v, uint32_t& codes, uint32_t& valid)
+{
+    uint32_t c0, c1, c2, c3, m0, m1, m2, m3;
+    encode4<FMT>(v.x, c0, m0);
+    encode4<FMT>(v.y, c1, m1);
+    encode4<FMT>(v.z, c2, m2);
+    encode4<FMT>(v.w, c3, m3);
+    codes = (c0 << 24) | (c1 << 16) | (c2 << 8) | c3;
+    valid = (m0 << 12) | (m1 << 8) | (m2 << 4) | m3;
+}
+
+// mask with the bits of positions [p, 16) set (position j <-> bit 15-j); p in [0, 16]
+__device__ __forceinline__ uint32_t from_pos(int p) { return (0x10000u >> p) - 1u; }
+
+// ------------------------------------------------------------------------------------------
+// Per-group (tile) read table in shared memory.
+struct ReadTable {
+    int64_t*  start;  // byte offset of the read in the bases buffer
+    int32_t*  tend;   // bytes [0, tend) of the read carry a counted window end
+    int32_t*  extra;  // compat: windows that straddle the terminator (always invalid)
+    uint32_t* cum;    // exclusive prefix sum of 16-byte blocks per read; cum[n] = total
+};
+
+// Which window-end positions of a read are visited.
+//   compat: starts t < min(len-1, 1024) (src/kmer_kernel.cu:85, src/kmer_main.cu:82), so ends
+//           < min(len-1,1024) + k-1; those at or beyond len hold the terminator -> `extra`.
+//   exact : every window inside the read.
+template <int K>
+__device__ __forceinline__ void read_extent(int mode, int len, int& tend, int& extra)
+{
+    int vis = (mode == MODE_COMPAT) ? min(len - 1, kRefBlockThreads) : len - K + 1;
+    if (vis <= 0) { tend = 0; extra = 0; return; }
+    int last = vis + K - 1;
+    tend = min(len, last);
+    extra = (mode == MODE_COMPAT) ? max(0, last - len) : 0;
+}
+
+// Fill the table for reads [r0, r0+n) (n <= kMaxGroupReads+1).  Call with all threads, then
+// __syncthreads(), then scan_read_table() from warp 0, then __syncthreads().
+template <int K>
+__device__ __forceinline__ void fill_read_table(const ReadTable& tb, const int64_t* __restrict__ start,
+                                                const int32_t* __restrict__ length, int64_t r0, int n,
+                                                int mode)
+{
+    for (int q = threadIdx.x; q < n; q += blockDim.x) {
+        int64_t s = start[r0 + q];
+        int len = length[r0 + q];
+        int tend, extra;
+        read_extent<K>(mode, len, tend, extra);
+        tb.start[q] = s;
+        tb.tend[q] = tend;
+        tb.extra[q] = extra;
+        tb.cum[q] = tend > 0 ? (uint32_t)(((s + tend - 1) >> 4) - (s >> 4) + 1) : 0u;
+    }
+}
+
+// exclusive scan of tb.cum[0..n) in place, total to tb.cum[n]; one warp
+__device__ __forceinline__ void scan_read_table(const ReadTable& tb, int n)
+{
+    const int lane = threadIdx.x & 31;
+    uint32_t run = 0;
+    for (int base = 0; base < n; base += 32) {
+        int q = base + lane;
+        uint32_t v = q < n ? tb.cum[q] : 0u;
+        uint32_t inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (q < n) tb.cum[q] = run + inc - v;
+        run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) tb.cum[n] = run;
+}
+
+template <int N> struct Log2Ceil { static constexpr int value = 1 + Log2Ceil<(N + 1) / 2>::value; };
+template <> struct Log2Ceil<1> { static constexpr int value = 0; };
+
+// ------------------------------------------------------------------------------------------
+// The item loop.  An item is one 16-byte aligned block of one read's counted byte range.
+// Lanes 1..31 of a warp take 31 consecutive items; lane 0 re-encodes the item before them
+// so that every counting lane gets its k-1 bases of context with one shuffle.
+//
+//   sink.kmer(q, idx)        one valid window of read q (table-local index) with index idx
+//   sink.invalid(q, count)   compat only: `count` visited windows of read q held a non-ACGT
+//                            byte or the terminator
+// Reads q >= ncount (the halo read of a compat tile) only report invalid windows.
+// MAXREADS bounds n (binary search depth).
+template <int K, int FMT, int MAXREADS, class Sink>
+__device__ __forceinline__ void for_each_window(const uint8_t* __restrict__ bases, const ReadTable& tb,
+                                                int n, int ncount, int mode, Sink& sink)
+{
+    static_assert(K >= 1 && K <= 16, "one 32-bit funnel shift per window needs k <= 16");
+    constexpr uint32_t IDX_MASK = (K == 16) ? 0xFFFFFFFFu : ((1u << (2 * K)) - 1u);
+    constexpr int STEPS = Log2Ceil<MAXREADS>::value;
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int nwarps = blockDim.x >> 5;
+    const uint32_t total = tb.cum[n];
+    const uint32_t nchunks = (total + 30u) / 31u;
+
+    for (uint32_t chunk = warp; chunk < nchunks; chunk += nwarps) {
+        const int64_t item = (int64_t)chunk * 31 + lane - 1;
+        const bool live = item >= 0 && item < (int64_t)total;
+        uint32_t codes = 0, valid = 0, count_mask = 0;
+        int q = 0;
+        bool first_block = true;
+        if (live) {
+            // largest q with cum[q] <= item  (cum[0] == 0; interval [lo, hi) halves each step)
+            int lo = 0, hi = n;
+#pragma unroll
+            for (int s = 0; s < STEPS; s++) {
+                const int mid = (lo + hi) >> 1;
+                const bool right = tb.cum[mid] <= (uint32_t)item;
+                lo = right ? mid : lo;
+                hi = right ? hi : mid;
+            }
+            q = lo;
+            const uint32_t c = (uint32_t)item - tb.cum[q];
+            const int64_t s = tb.start[q];
+            const int tend = tb.tend[q];
+            const int64_t blk = (s >> 4) + c;
+            const int t0 = (int)(blk * 16 - s);  // read-relative position of byte 0 of the block
+            first_block = (c == 0);
+            encode16<FMT>(ld_block(bases + blk * 16), codes, valid);
+            const int hi_pos = min(16, tend - t0);
+            const uint32_t upto = ~from_pos(hi_pos);
+            valid &= from_pos(max(0, -t0)) & upto;                    // bases of this read only
+            count_mask = from_pos(min(16, max(0, K - 1 - t0))) & upto;  // window ends that count
+        }
+        uint32_t pcodes = __shfl_up_sync(0xffffffffu, codes, 1);
+        uint32_t pvalid = __shfl_up_sync(0xffffffffu, valid, 1);
+        if (first_block) pvalid = 0;  // no context across a read start
+        const bool counting = live && lane != 0;  // lane 0 only feeds lane 1
+        if (!counting) count_mask = 0;
+
+        // bit b of `ok` <- bases b .. b+K-1 (this window) are all valid
+        const uint32_t v32 = (pvalid << 16) | valid;
+        uint32_t ok = v32;
+#pragma unroll
+        for (int i = 1; i < K; i++) ok &= v32 >> i;
+        const uint32_t good = q < ncount ? (ok & count_mask) : 0u;
+        const uint32_t bad = ~ok & count_mask;
+        if (mode == MODE_COMPAT) {
+            int nbad = __popc(bad) + ((counting && first_block) ? tb.extra[q] : 0);
+            if (nbad) sink.invalid(q, nbad);
+        }
+        if (good) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int bit = 15 - j;
+                if (good & (1u << bit)) {
+                    uint32_t idx = __funnelshift_r(codes, pcodes, 2 * bit) & IDX_MASK;
+                    sink.kmer(q, idx);
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA (bulk async-copy engine) shared -> global store of one finished row tile.
+__device__ __forceinline__ void fence_async_proxy_shared()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_tile(void* gdst, const void* ssrc, uint32_t bytes)
+{
+    uint32_t saddr = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all()
+{
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+}  // namespace cfrk

@@ -1,0 +1,482 @@
+// runfile.cu -- cfrk_run_file(): FASTA file -> GPU count -> .cfrk text, the whole of the
+// reference's main() (src/main.cu:232-305) re-designed around the GPU.
+//
+//   reader   FastaStreamer: a thread preads the file into a ring of PINNED buffers; the raw
+//            bytes are what the GPU consumes (CFRK_FMT_ASCII).  The record text of the
+//            reference parser (src/fastaIO.h:38-69: every non-header line, '\n' included,
+//            minus the last byte) is a contiguous span of the file, so a record is described
+//            by (start, length) into the raw bytes and nothing is copied or encoded on the
+//            host -- newline-as-base, CRLF, missing final newline all fall out.
+//            Replaces popen("grep -c") + getline + 3 malloc/record + strcat + per-base switch
+//            + ProcessData + SelectChunk (src/fastaIO.h:12-148, src/main.cu:110-206).
+//   scan     the host only looks for '>' (memchr); a '>' that does not start a line, or text
+//            before the first header, is where the reference is undefined: CFRK_EFORMAT.
+//   count    dense_count_kernel over the buffer, rows through a two-slot device/pinned ring.
+//   writer   nt threads format rows ("bin:count ", src/main.cu:53-55) into private buffers
+//            that are written in order; "\n" before every row but the first, none at EOF.
+//
+// Default (compat) output = only reads [ (nS/chunkSize)*chunkSize, nS ), because the reference
+// re-opens the output with "w" for the remainder chunk (src/main.cu:34,303-305): the file is
+// scanned once for headers and only that tail is uploaded.  CFRK_RUN_ALL_ROWS streams every read.
+#include "../../include/cfrk_b200.h"
+#include "kernels.h"
+#include "kmer_device.cuh"
+#include "internal.h"
+
+#include <algorithm>
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <fcntl.h>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <sys/stat.h>
+#include <thread>
+#include <unistd.h>
+#include <vector>
+
+namespace {
+
+struct Err {
+    int code = CFRK_OK;
+    std::string msg;
+};
+#define RF_CU(call)                                                                  \
+    do {                                                                             \
+        cudaError_t e_ = (call);                                                     \
+        if (e_ != cudaSuccess) {                                                     \
+            err.code = CFRK_ECUDA;                                                   \
+            err.msg = std::string(#call) + ": " + cudaGetErrorString(e_);            \
+            return false;                                                            \
+        }                                                                            \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// Pinned, multi-buffered sequential file reader.  Each buffer has `headroom` bytes in front of
+// the region the reader fills, so the consumer can prepend the unfinished records of the
+// previous buffer and hand the GPU one contiguous span.
+class FastaStreamer {
+public:
+    static constexpr int NB = 3;
+    struct Buf { char* base = nullptr; size_t n = 0; bool eof = false; bool filled = false; };
+
+    bool open(const char* path, size_t chunk, size_t headroom, Err& err)
+    {
+        fd_ = ::open(path, O_RDONLY);
+        if (fd_ < 0) { err.code = CFRK_EIO; err.msg = std::string("cannot open ") + path; return false; }
+        struct stat st;
+        if (fstat(fd_, &st) != 0) { err.code = CFRK_EIO; err.msg = "fstat failed"; return false; }
+        size_ = (size_t)st.st_size;
+        chunk_ = chunk; headroom_ = headroom;
+        for (int i = 0; i < NB; i++) {
+            if (cudaMallocHost(reinterpret_cast<void**>(&bufs_[i].base), headroom + chunk + CFRK_PAD) != cudaSuccess) {
+                cudaGetLastError();
+                err.code = CFRK_ENOMEM; err.msg = "cudaMallocHost(stream buffer)";
+                return false;
+            }
+        }
+        th_ = std::thread([this] { run(); });
+        return true;
+    }
+    // i-th buffer of the file (blocks until read). The new bytes are at base+headroom.
+    Buf* acquire(size_t i)
+    {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return bufs_[i % NB].filled && seq_[i % NB] == i; });
+        return &bufs_[i % NB];
+    }
+    void release(size_t i)
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        bufs_[i % NB].filled = false;
+        cv_.notify_all();
+    }
+    char* next_base(size_t i) { return bufs_[(i + 1) % NB].base; }
+    size_t headroom() const { return headroom_; }
+    size_t file_size() const { return size_; }
+    int fd() const { return fd_; }
+    ~FastaStreamer()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+            cv_.notify_all();
+        }
+        if (th_.joinable()) th_.join();
+        for (int i = 0; i < NB; i++) if (bufs_[i].base) cudaFreeHost(bufs_[i].base);
+        if (fd_ >= 0) ::close(fd_);
+    }
+
+private:
+    void run()
+    {
+        size_t off = 0;
+        for (size_t i = 0;; i++) {
+            Buf& b = bufs_[i % NB];
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return stop_ || !b.filled; });
+                if (stop_) return;
+            }
+            size_t want = std::min(chunk_, size_ - off), got = 0;
+            while (got < want) {
+                ssize_t r = pread(fd_, b.base + headroom_ + got, want - got, (off_t)(off + got));
+                if (r <= 0) break;
+                got += (size_t)r;
+            }
+            off += got;
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                b.n = got; b.eof = (off >= size_) || got < want; b.filled = true; seq_[i % NB] = i;
+                cv_.notify_all();
+            }
+            if (b.eof) return;
+        }
+    }
+    int fd_ = -1;
+    size_t size_ = 0, chunk_ = 0, headroom_ = 0;
+    Buf bufs_[NB];
+    size_t seq_[NB] = {0, 0, 0};
+    std::thread th_;
+    std::mutex mu_;
+    std::condition_variable cv_;
+    bool stop_ = false;
+};
+
+// ------------------------------------------------------------------------------------------
+// Header scan of data[0, n).  data[0] must be '>' (the caller cuts buffers at headers).
+// Appends (start, length) for every record whose end is known: all of them when `final`,
+// else all but the last.  Returns false on input the reference is undefined on.
+struct RecordIndex {
+    std::vector<int64_t> start;
+    std::vector<int32_t> length;
+    std::vector<size_t> header;  // position of each header's '>'
+};
+
+bool scan_records(const char* data, size_t n, bool final, RecordIndex& ri, Err& err)
+{
+    ri.start.clear(); ri.length.clear(); ri.header.clear();
+    if (n == 0) return true;
+    if (data[0] != '>') { err.code = CFRK_EFORMAT; err.msg = "sequence text before the first '>' header (undefined in the reference, src/fastaIO.h:49-52)"; return false; }
+    size_t p = 0;
+    while (p < n) {
+        const char* g = static_cast<const char*>(memchr(data + p, '>', n - p));
+        if (!g) break;
+        size_t h = (size_t)(g - data);
+        if (h != 0 && data[h - 1] != '\n') { err.code = CFRK_EFORMAT; err.msg = "'>' inside a line (grep -c over-counts nS in the reference, src/fastaIO.h:16)"; return false; }
+        ri.header.push_back(h);
+        const char* nl = static_cast<const char*>(memchr(g, '\n', n - h));
+        p = nl ? (size_t)(nl - data) + 1 : n;
+        // (a second '>' inside the header line is fine: grep -c counts lines, not characters)
+    }
+    const size_t m = ri.header.size();
+    const size_t complete = final ? m : (m ? m - 1 : 0);
+    for (size_t i = 0; i < complete; i++) {
+        const size_t h = ri.header[i];
+        const size_t end = (i + 1 < m) ? ri.header[i + 1] : n;
+        const char* nl = static_cast<const char*>(memchr(data + h, '\n', end - h));
+        const size_t s = nl ? (size_t)(nl - data) + 1 : end;
+        const size_t text = end - s;
+        if (text > (size_t)INT32_MAX) { err.code = CFRK_EFORMAT; err.msg = "record longer than 2^31-1 bytes (length is int in the reference, src/tipos.h:26)"; return false; }
+        ri.start.push_back((int64_t)s);
+        ri.length.push_back(text > 0 ? (int32_t)(text - 1) : 0);  // len = strlen(text) - 1, src/fastaIO.h:53,65
+    }
+    return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// .cfrk text writer
+struct BinLabels {
+    std::vector<char> text;      // "0:" "1:" ...
+    std::vector<uint32_t> off;   // offsets, size bins+1
+    explicit BinLabels(size_t bins)
+    {
+        off.resize(bins + 1);
+        char tmp[16];
+        for (size_t b = 0; b < bins; b++) {
+            off[b] = (uint32_t)text.size();
+            int l = snprintf(tmp, sizeof tmp, "%zu:", b);
+            text.insert(text.end(), tmp, tmp + l);
+        }
+        off[bins] = (uint32_t)text.size();
+    }
+};
+
+inline char* put_int(char* p, int32_t v)
+{
+    if (v < 0) { *p++ = '-'; v = -v; }  // cannot happen (counts), kept for "%d" fidelity
+    char tmp[12];
+    int l = 0;
+    uint32_t u = (uint32_t)v;
+    do { tmp[l++] = (char)('0' + u % 10); u /= 10; } while (u);
+    while (l) *p++ = tmp[--l];
+    return p;
+}
+
+void format_rows(const int32_t* rows, size_t nrows, size_t bins, const BinLabels& lab, bool sparse,
+                 bool first_row_of_file, std::vector<char>& out)
+{
+    // worst case per token: label + 11 digits + space
+    const size_t worst_row = lab.text.size() + bins * 12 + 1;
+    out.resize(nrows * worst_row);
+    char* p = out.data();
+    for (size_t r = 0; r < nrows; r++) {
+        if (!(first_row_of_file && r == 0)) *p++ = '\n';
+        const int32_t* row = rows + r * bins;
+        for (size_t b = 0; b < bins; b++) {
+            if (sparse && row[b] == 0) continue;
+            const uint32_t l0 = lab.off[b], l1 = lab.off[b + 1];
+            memcpy(p, lab.text.data() + l0, l1 - l0);
+            p += l1 - l0;
+            p = put_int(p, row[b]);
+            *p++ = ' ';
+        }
+    }
+    out.resize((size_t)(p - out.data()));
+}
+
+class CfrkWriter {
+public:
+    bool open(const char* path, int k, int nt, bool sparse, Err& err)
+    {
+        f_ = fopen(path, "w");
+        if (!f_) { err.code = CFRK_EIO; err.msg = std::string("cannot open output ") + path; return false; }
+        bins_ = (size_t)1 << (2 * k);
+        labels_.reset(new BinLabels(bins_));
+        nt_ = std::max(1, std::min(nt, 64));
+        sparse_ = sparse;
+        return true;
+    }
+    bool write_rows(const int32_t* rows, size_t nrows, Err& err)
+    {
+        if (!nrows) return true;
+        const int nt = (int)std::min<size_t>((size_t)nt_, nrows);
+        std::vector<std::vector<char>> parts(nt);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) {
+            const size_t a = nrows * t / nt, b = nrows * (t + 1) / nt;
+            const bool first = first_ && a == 0;
+            th.emplace_back([=, &parts] { format_rows(rows + a * bins_, b - a, bins_, *labels_, sparse_, first, parts[t]); });
+        }
+        for (auto& x : th) x.join();
+        first_ = false;
+        for (auto& part : parts)
+            if (!part.empty() && fwrite(part.data(), 1, part.size(), f_) != part.size()) {
+                err.code = CFRK_EIO; err.msg = "short write"; return false;
+            }
+        return true;
+    }
+    ~CfrkWriter() { if (f_) fclose(f_); }
+
+private:
+    FILE* f_ = nullptr;
+    size_t bins_ = 0;
+    std::unique_ptr<BinLabels> labels_;
+    int nt_ = 1;
+    bool sparse_ = false, first_ = true;
+};
+
+// ------------------------------------------------------------------------------------------
+// GPU side of the file pipeline: input double buffer + row ring.
+struct Pipeline {
+    static constexpr size_t kSlotBytes = (size_t)128 << 20;
+    cudaStream_t compute = nullptr, copy = nullptr;
+    cudaEvent_t done[2] = {}, drained[2] = {};
+    char* d_in = nullptr; size_t cap_in = 0;
+    int64_t* d_start = nullptr; int32_t* d_length = nullptr; size_t cap_reads = 0;
+    int32_t* d_rows[2] = {}; int32_t* h_rows[2] = {}; size_t cap_rows = 0;
+
+    bool init(Err& err)
+    {
+        RF_CU(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking));
+        RF_CU(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            RF_CU(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+            RF_CU(cudaEventCreateWithFlags(&drained[i], cudaEventDisableTiming));
+        }
+        return true;
+    }
+    bool reserve(size_t in_bytes, size_t nreads, size_t row_bytes, Err& err)
+    {
+        if (in_bytes + CFRK_PAD > cap_in) {
+            cudaFree(d_in);
+            cap_in = in_bytes + CFRK_PAD + in_bytes / 8;
+            RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_in), cap_in));
+        }
+        if (nreads > cap_reads) {
+            cudaFree(d_start); cudaFree(d_length);
+            cap_reads = nreads + nreads / 4 + 64;
+            RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_start), cap_reads * 8));
+            RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_length), cap_reads * 4));
+        }
+        const size_t need = std::max(row_bytes, kSlotBytes);
+        if (need > cap_rows) {
+            for (int i = 0; i < 2; i++) {
+                cudaFree(d_rows[i]); if (h_rows[i]) cudaFreeHost(h_rows[i]);
+                RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_rows[i]), need));
+                RF_CU(cudaMallocHost(reinterpret_cast<void**>(&h_rows[i]), need));
+            }
+            cap_rows = need;
+        }
+        return true;
+    }
+    // Count reads [0, nreads) of the span, produce rows [0, nrows) and hand them to the writer.
+    bool run(const char* h_in, size_t in_bytes, const RecordIndex& ri, size_t nrows, int k, int mode,
+             int64_t chunk_size, int64_t index_base, CfrkWriter& w, Err& err)
+    {
+        const size_t nreads = ri.start.size();
+        if (nrows == 0) return true;
+        const size_t bins = (size_t)1 << (2 * k), row_bytes = bins * 4;
+        if (!reserve(in_bytes, nreads, row_bytes, err)) return false;
+        const size_t rpt = (size_t)cfrk::dense_reads_per_tile(k);
+        size_t slice = std::max<size_t>(1, cap_rows / row_bytes);
+        slice = std::max(rpt, slice / rpt * rpt);
+
+        RF_CU(cudaMemcpyAsync(d_in, h_in, in_bytes, cudaMemcpyHostToDevice, compute));
+        RF_CU(cudaMemsetAsync(d_in + in_bytes, 0, CFRK_PAD, compute));
+        RF_CU(cudaMemcpyAsync(d_start, ri.start.data(), nreads * 8, cudaMemcpyHostToDevice, compute));
+        RF_CU(cudaMemcpyAsync(d_length, ri.length.data(), nreads * 4, cudaMemcpyHostToDevice, compute));
+
+        const size_t nslices = (nrows + slice - 1) / slice;
+        for (size_t s = 0; s <= nslices; s++) {
+            if (s < nslices) {
+                const int slot = (int)(s & 1);
+                const size_t r0 = s * slice, r1 = std::min(nrows, r0 + slice);
+                // slot reuse: the host finished formatting slice s-2 before we get here (below);
+                // the kernel must not overwrite d_rows[slot] before the D2H of slice s-2 is done
+                if (s >= 2) RF_CU(cudaStreamWaitEvent(compute, drained[slot], 0));
+                cudaError_t e = cfrk::launch_dense(d_in, cfrk::FMT_ASCII, d_start, d_length, (int64_t)nreads,
+                                                   (int64_t)r0, (int64_t)r1, k, mode, chunk_size, index_base,
+                                                   d_rows[slot], compute);
+                if (e != cudaSuccess) { err.code = CFRK_ECUDA; err.msg = std::string("dense_count_kernel: ") + cudaGetErrorString(e); return false; }
+                RF_CU(cudaEventRecord(done[slot], compute));
+                RF_CU(cudaStreamWaitEvent(copy, done[slot], 0));
+                RF_CU(cudaMemcpyAsync(h_rows[slot], d_rows[slot], (r1 - r0) * row_bytes, cudaMemcpyDeviceToHost, copy));
+                RF_CU(cudaEventRecord(drained[slot], copy));
+            }
+            if (s >= 1) {  // format slice s-1 while slice s is on the GPU
+                const size_t q = s - 1;
+                const int slot = (int)(q & 1);
+                const size_t r0 = q * slice, r1 = std::min(nrows, r0 + slice);
+                RF_CU(cudaEventSynchronize(drained[slot]));
+                if (!w.write_rows(h_rows[slot], r1 - r0, err)) return false;
+            }
+        }
+        RF_CU(cudaStreamSynchronize(compute));
+        return true;
+    }
+    ~Pipeline()
+    {
+        cudaFree(d_in); cudaFree(d_start); cudaFree(d_length);
+        for (int i = 0; i < 2; i++) {
+            cudaFree(d_rows[i]);
+            if (h_rows[i]) cudaFreeHost(h_rows[i]);
+            if (done[i]) cudaEventDestroy(done[i]);
+            if (drained[i]) cudaEventDestroy(drained[i]);
+        }
+        if (compute) cudaStreamDestroy(compute);
+        if (copy) cudaStreamDestroy(copy);
+    }
+};
+
+bool run_file(const char* fasta, const char* out_path, int k, int nt, int64_t chunk_size, int flags, int device,
+              Err& err)
+{
+    const bool all_rows = flags & CFRK_RUN_ALL_ROWS;
+    const int mode = (flags & CFRK_RUN_EXACT) ? CFRK_MODE_EXACT : CFRK_MODE_COMPAT;
+    RF_CU(cudaSetDevice(device));
+
+    constexpr size_t kChunk = (size_t)64 << 20, kHeadroom = (size_t)64 << 20;
+    FastaStreamer rd;
+    if (!rd.open(fasta, kChunk, kHeadroom, err)) return false;
+    CfrkWriter w;
+    if (!w.open(out_path, k, nt, flags & CFRK_RUN_SPARSE, err)) return false;
+    Pipeline gpu;
+    if (!gpu.init(err)) return false;
+
+    RecordIndex ri;
+    size_t carry = 0;            // bytes of unfinished records prepended to the current buffer
+    int64_t reads_done = 0;      // index of the first record of the current span
+    int64_t tail_off = -1;       // file offset of the header that opens the last (partial) chunk
+    size_t span_file_off = 0;    // file offset of data[0]
+    for (size_t i = 0;; i++) {
+        FastaStreamer::Buf* b = rd.acquire(i);
+        char* data = b->base + rd.headroom() - carry;
+        const size_t n = carry + b->n;
+        if (!scan_records(data, n, b->eof, ri, err)) return false;
+        const size_t m = ri.start.size();  // records whose end is known
+
+        size_t keep_from;  // data[keep_from, n) goes in front of the next buffer
+        if (all_rows) {
+            // rows for all complete records but the last one, which is only needed for its spill
+            // into its predecessor and is counted again as read 0 of the next span
+            const size_t nrows = b->eof ? m : (m ? m - 1 : 0);
+            if (!gpu.run(data, n, ri, nrows, k, mode, chunk_size, reads_done, w, err)) return false;
+            reads_done += (int64_t)nrows;
+            keep_from = b->eof ? n : (m ? ri.header[m - 1] : 0);
+        } else {
+            for (size_t r = 0; r < m; r++)
+                if ((reads_done + (int64_t)r) % chunk_size == 0) tail_off = (int64_t)(span_file_off + ri.header[r]);
+            reads_done += (int64_t)m;
+            keep_from = b->eof ? n : (ri.header.empty() ? 0 : ri.header[m]);
+        }
+        if (b->eof) { rd.release(i); break; }
+        carry = n - keep_from;
+        if (carry > rd.headroom()) {
+            err.code = CFRK_EFORMAT;
+            err.msg = "a single FASTA record (plus its predecessor) exceeds the 64 MiB streaming window";
+            return false;
+        }
+        memcpy(rd.next_base(i) + rd.headroom() - carry, data + keep_from, carry);
+        span_file_off += keep_from;
+        rd.release(i);
+    }
+
+    if (!all_rows) {
+        // reference: only the remainder chunk reaches the file; nothing when nS % chunkSize == 0
+        const int64_t nS = reads_done;
+        if (nS % chunk_size != 0 && tail_off >= 0) {
+            const size_t bytes = rd.file_size() - (size_t)tail_off;
+            char* h = nullptr;
+            if (cudaMallocHost(reinterpret_cast<void**>(&h), bytes + CFRK_PAD) != cudaSuccess) {
+                cudaGetLastError();
+                err.code = CFRK_ENOMEM; err.msg = "cudaMallocHost(tail chunk)"; return false;
+            }
+            size_t got = 0;
+            while (got < bytes) {
+                ssize_t r = pread(rd.fd(), h + got, bytes - got, (off_t)((size_t)tail_off + got));
+                if (r <= 0) break;
+                got += (size_t)r;
+            }
+            bool ok = got == bytes && scan_records(h, bytes, true, ri, err);
+            if (got != bytes) { err.code = CFRK_EIO; err.msg = "short read of the tail chunk"; }
+            if (ok) ok = gpu.run(h, bytes, ri, ri.start.size(), k, mode, chunk_size, (nS / chunk_size) * chunk_size, w, err);
+            cudaFreeHost(h);
+            if (!ok) return false;
+        }
+    }
+    return true;
+}
+
+}  // namespace
+
+extern "C" int cfrk_run_file(const char* fasta_path, const char* out_path, int k, int nt, int64_t chunk_size,
+                             int flags, int device)
+{
+    Err err;
+    if (!fasta_path || !out_path) { err.code = CFRK_EINVAL; err.msg = "null path"; }
+    else if (k < 1 || k > CFRK_DENSE_MAX_K) { err.code = CFRK_EINVAL; err.msg = "k must be in 1..8 for dense .cfrk output"; }
+    else if (chunk_size <= 0) { err.code = CFRK_EINVAL; err.msg = "chunkSize must be positive"; }
+    else {
+        int ndev = 0;
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+            cudaGetLastError();
+            err.code = CFRK_ECUDA; err.msg = "no such CUDA device (this library has no CPU fallback)";
+        } else {
+            run_file(fasta_path, out_path, k, nt, chunk_size, flags, device, err);
+        }
+    }
+    if (err.code != CFRK_OK) cfrk::set_last_error(err.msg);
+    return err.code;
+}

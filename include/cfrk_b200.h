@@ -1,0 +1,134 @@
+/*
+ * cfrk_b200.h -- C ABI of the B200-native CFRK hot path (libcfrk_b200.so).
+ *
+ * Drop-in boundary for the reference's in-process operator
+ *     void kmer_main(struct read *rd, lint nN, lint nS, int k, ushort device);
+ *                                                   (reference src/kmer.cuh:6,
+ *                                                    src/kmer_main.cu:20-128)
+ * and for the stages either side of it (reader src/fastaIO.h:24-148, writer
+ * src/main.cu:26-62, chunk/tail driver src/main.cu:232-305).
+ *
+ * Plain pointers and sizes only; no C++ or torch types.  Every function returns
+ * CFRK_OK (0) or a negative CFRK_E* code; cfrk_last_error() gives the text for
+ * the calling thread.  There is no CPU fallback: without a usable CUDA device
+ * every compute entry point fails with CFRK_ECUDA.
+ *
+ * INTEGRATION.md shows the two-line change that makes the reference's own
+ * main.cu call this library.
+ */
+#ifndef CFRK_B200_H
+#define CFRK_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CFRK_OK        0
+#define CFRK_EINVAL   -1  /* bad argument (k out of range, null pointer, ...)   */
+#define CFRK_ECUDA    -2  /* CUDA runtime error, text in cfrk_last_error()      */
+#define CFRK_ENOMEM   -3  /* host or device allocation failed                   */
+#define CFRK_EIO      -4  /* cannot open / read / write a file                  */
+#define CFRK_EFORMAT  -5  /* FASTA input on which the reference is undefined    */
+
+/* semantics */
+#define CFRK_MODE_COMPAT 0 /* bit-exact with the reference, quirks included:
+                              positions t < min(len-1,1024) are visited, a window holding
+                              a non-ACGT byte or the terminator adds 1 to the LAST bin of
+                              the PREVIOUS read (src/kmer_kernel.cu:83-88)              */
+#define CFRK_MODE_EXACT  1 /* every one of the len-k+1 windows; invalid windows skipped */
+
+/* layout of the bases buffer */
+#define CFRK_FMT_CODES 0   /* reference layout (src/tipos.h:23-30, src/fastaIO.h:123-139):
+                              one int8 per base, A/C/G/T = 0/1/2/3, anything else -1, one
+                              -1 terminator after each read                             */
+#define CFRK_FMT_ASCII 1   /* FASTA letters as read from the file (upper or lower case);
+                              one separator byte (any non-ACGT byte) after each read    */
+
+#define CFRK_DENSE_MAX_K 8   /* shared-memory tile path (4^k int32 per read)            */
+#define CFRK_HIST_MAX_K  15  /* whole-dataset histogram, 4^k uint32 in HBM              */
+#define CFRK_PAD         16  /* device bases buffers must be readable up to the next
+                                16-byte boundary and 16-byte aligned                    */
+
+const char *cfrk_version(void);
+const char *cfrk_last_error(void);
+int         cfrk_device_count(void);
+
+/* Number of kernels this library has launched since load (all threads). */
+uint64_t    cfrk_launch_count(void);
+
+/* ---- the operator: replaces kmer_main (src/kmer_main.cu:20-128) --------------------- */
+
+/*
+ * Host buffers in, host rows out; synchronous, like kmer_main.
+ *   bases[nN], start[nS] (byte offset of each read in bases), length[nS]: caller-owned,
+ *   pinned or pageable.  freq_out[nS * 4^k]: caller-owned (pinned memory makes the
+ *   device->host copy asynchronous and full speed).
+ * Replaces: the 5 cudaMalloc + 3 H2D + 4 launches + cudaMallocHost + D2H + 5 cudaFree of
+ * src/kmer_main.cu:59-124.  Unlike the reference it returns errors instead of printing
+ * them, uses 64-bit indexing throughout (no nS*4^k < 2^31 limit) and never
+ * writes outside freq_out (the reference stores Freq[-1] for read 0).
+ */
+int cfrk_count_dense_host(const void *bases, int fmt, const int64_t *start, const int32_t *length,
+                          int64_t nN, int64_t nS, int k, int mode, int device,
+                          int32_t *freq_out);
+
+/*
+ * Device-resident variant: every pointer is device memory on `device`, `stream` is a
+ * cudaStream_t (NULL = the legacy default stream).  Asynchronous.  d_bases must honour
+ * CFRK_PAD; d_freq must be 16-byte aligned.  Reads [read_begin, read_end) of the batch
+ * are counted into d_freq[(i-read_begin)*4^k ...]; read_begin must be a multiple of
+ * cfrk_dense_reads_per_tile(k) unless it is 0 (so that row tiles line up).
+ * compat mode: the reference drops the spill of the first read of every kmer_main call
+ * (one call per chunk, src/main.cu:222,294,300).  chunk_size == 0: the batch is one such
+ * call.  chunk_size > 0: read i opens a chunk iff (first_read_index + i) % chunk_size == 0,
+ * so one launch reproduces many reference calls.
+ */
+int cfrk_count_dense_device(const void *d_bases, int fmt, const int64_t *d_start,
+                            const int32_t *d_length, int64_t nN, int64_t nS,
+                            int64_t read_begin, int64_t read_end, int k, int mode,
+                            int64_t chunk_size, int64_t first_read_index,
+                            int32_t *d_freq, void *stream);
+int cfrk_dense_reads_per_tile(int k);
+
+/* ---- stages of the north-star pipeline exposed on their own ------------------------- */
+
+/*
+ * Base -> 2-bit encode with ambiguous-base masking (replaces the per-base switch of
+ * src/fastaIO.h:123-139 and the int8 batch layout of src/tipos.h:23-30).
+ * 16 bases per uint32 word, first base in the two most significant bits; valid[w] bit
+ * (15-j) is set iff base 16w+j is A/C/G/T.  n = number of bytes; d_codes has ceil(n/16)
+ * words, d_valid ceil(n/16) uint16.
+ */
+int cfrk_encode_2bit_device(const void *d_bases, int fmt, int64_t n, uint32_t *d_codes,
+                            uint16_t *d_valid, void *stream);
+
+/*
+ * Whole-dataset k-mer histogram (exact semantics), accumulated INTO d_hist[4^k] uint32
+ * (caller zeroes it; several calls / several GPUs add up, reduce across ranks with NCCL).
+ */
+int cfrk_global_hist_device(const void *d_bases, int fmt, const int64_t *d_start,
+                            const int32_t *d_length, int64_t nN, int64_t nS, int k,
+                            uint32_t *d_hist, void *stream);
+
+/* ---- file level: replaces main() of src/main.cu:232-305 ----------------------------- */
+
+#define CFRK_RUN_ALL_ROWS   1  /* print every read (chunk by chunk) instead of only the
+                                  last nS mod chunkSize reads (src/main.cu:303-305)     */
+#define CFRK_RUN_EXACT      2  /* CFRK_MODE_EXACT instead of compat                     */
+#define CFRK_RUN_SPARSE     4  /* write only non-zero bins (the filter commented out at
+                                  src/main.cu:51,56)                                    */
+
+/*
+ * cfrk <fasta> <out> <k> [nt] [chunkSize] as a function: pinned double-buffered FASTA
+ * streamer -> GPU count -> multi-threaded .cfrk writer.  nt = host writer threads.
+ */
+int cfrk_run_file(const char *fasta_path, const char *out_path, int k, int nt,
+                  int64_t chunk_size, int flags, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CFRK_B200_H */

@@ -1,0 +1,52 @@
+"""GPU parity: the CUDA path through the C ABI vs the CPU oracle, bit-exact."""
+import numpy as np
+import pytest
+
+import cfrk_b200 as cf
+import fixtures as fx
+import oracle_binding as ob
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,text,ks", fx.EDGE_SET, ids=[e[0] for e in fx.EDGE_SET])
+@pytest.mark.parametrize("mode", [cf.MODE_COMPAT, cf.MODE_EXACT], ids=["compat", "exact"])
+def test_edge_set_codes(name, text, ks, mode):
+    data, start, length = ob.parse_fasta(text=text)
+    for k in ks:
+        want = ob.count_dense(data, start, length, k, mode)
+        got = cf.count_dense_host(data, start, length, k, mode, cf.FMT_CODES)
+        np.testing.assert_array_equal(got, want, err_msg=f"{name} k={k} mode={mode}")
+
+
+@pytest.mark.parametrize("name,text,ks", fx.EDGE_SET, ids=[e[0] for e in fx.EDGE_SET])
+@pytest.mark.parametrize("mode", [cf.MODE_COMPAT, cf.MODE_EXACT], ids=["compat", "exact"])
+def test_edge_set_ascii(name, text, ks, mode):
+    """raw file bytes + (start,length) into them == oracle on the parsed codes"""
+    data, start, length = ob.parse_fasta(text=text)
+    raw, rstart, rlength = fx.ascii_batch(text)
+    np.testing.assert_array_equal(rlength, length)
+    for k in ks:
+        want = ob.count_dense(data, start, length, k, mode)
+        got = cf.count_dense_host(raw, rstart, rlength, k, mode, cf.FMT_ASCII)
+        np.testing.assert_array_equal(got, want, err_msg=f"{name} k={k} mode={mode}")
+
+
+@pytest.mark.parametrize("k", range(1, 9))
+def test_synthetic_150bp(k):
+    nS = 20000 if k <= 6 else 3000
+    data, start, length = fx.synthetic_codes(nS, 150, seed=42 + k, n_frac=0.001)
+    for mode in (cf.MODE_COMPAT, cf.MODE_EXACT):
+        want = ob.count_dense_fast(data, start, length, k, mode)
+        got = cf.kmer_main(data, start, length, k) if mode == cf.MODE_COMPAT else \
+            cf.count_dense_host(data, start, length, k, mode)
+        np.testing.assert_array_equal(got, want)
+
+
+def test_empty_and_tiny():
+    z = cf.count_dense_host(np.zeros(0, np.int8), np.zeros(0, np.int64), np.zeros(0, np.int32), 3)
+    assert z.shape == (0, 64)
+    data = np.array([0, 1, 2, 3, -1], dtype=np.int8)
+    got = cf.kmer_main(data, np.array([0]), np.array([4]), 2)
+    want = ob.count_dense(data, np.array([0]), np.array([4]), 2)
+    np.testing.assert_array_equal(got, want)
