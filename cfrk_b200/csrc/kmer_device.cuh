@@ -102,7 +102,8 @@ __device__ __forceinline__ void read_extent(int mode, int len, int& tend, int& e
     if (vis <= 0) { tend = 0; extra = 0; return; }
     int last = vis + K - 1;
     tend = min(len, last);
-    extra = (mode == MODE_COMPAT) ? max(0, last - len) : 0;
+    // visited starts t0 >= len-K+1 end at or beyond the terminator
+    extra = (mode == MODE_COMPAT) ? max(0, vis - max(0, len - K + 1)) : 0;
 }
 
 // Fill the table for reads [r0, r0+n) (n <= kMaxGroupReads+1).  Call with all threads, then
