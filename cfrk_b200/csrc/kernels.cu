@@ -10,6 +10,7 @@
 #include "kmer_device.cuh"
 
 #include <atomic>
+#include <cstdlib>
 
 namespace cfrk {
 
@@ -36,6 +37,7 @@ struct Geo {
 template <int K, int TILE_BINS_T>
 struct DenseSink {
     using G = Geo<K, TILE_BINS_T>;
+    static constexpr bool kCtaUniform = false;
     uint32_t* hist;   // current tile buffer
     int sub;          // which TILE_BINS-slice of the row (k >= 7)
     bool has_last;    // tile holds bin 4^k-1 of its rows
@@ -141,6 +143,172 @@ __global__ void __launch_bounds__(NTHREADS) dense_count_kernel(const DenseArgs a
 }
 
 // ------------------------------------------------------------------------------------------
+// Big rows (k >= 6: 16 / 64 / 256 KiB per read, of which a read touches <= 1024+1 bins).
+// The row write IS the roofline, so the kernel is a streaming zero-writer with sparse patches:
+//   1. one thread streams the rows of a group of reads as zeros with TMA bulk stores whose source
+//      is a CONSTANT zero buffer in shared memory (never modified: any number of stores in flight,
+//      nothing to re-zero, no buffer hand-over),
+//   2. meanwhile all warps load + encode the group's bases,
+//   3. once the zero stores have completed, the counts are scattered with red.global.add: the
+//      rows were written microseconds ago and are still L2-resident, so the reductions merge in
+//      L2 and DRAM sees each row exactly once.
+// L2 residency is what makes this work, so the bytes in flight (resident CTAs x tile) are bounded
+// far below the 126 MB L2: measured on B200 (profiles/r1_notes.md) 888 CTAs x 256 KiB = 227 MB gave
+// 3 % L2 hits for the reductions and 0.65-0.79 of the HBM roofline; 444 x 64 KiB = 28 MB gives 0.91
+// (k=7) and 1.06 (k=8) of the measured copy bandwidth.
+template <int K, int TILE_BYTES>
+struct BigGeo {
+    static constexpr int BINS = 1 << (2 * K);
+    static constexpr int ROW_BYTES = BINS * 4;
+    static constexpr int SUB = ROW_BYTES > TILE_BYTES ? ROW_BYTES / TILE_BYTES : 1;  // tiles per row
+    static constexpr int GROUP = ROW_BYTES >= TILE_BYTES ? 1 : TILE_BYTES / ROW_BYTES;  // rows per tile
+    static constexpr int TILE_BINS = SUB > 1 ? TILE_BYTES / 4 : BINS;
+    static constexpr int TABLE_READS = GROUP + 1;
+};
+
+template <int K, int TILE_BYTES>
+struct BigRowSink {
+    using G = BigGeo<K, TILE_BYTES>;
+    static constexpr bool kCtaUniform = true;
+    uint32_t* rows;   // row of table-local read 0
+    int sub;          // which slice of the row this tile covers (SUB > 1)
+    bool has_last;
+    int qb, period;   // chunk openers (see DenseSink)
+    __device__ __forceinline__ void before_first_emit()
+    {
+        if (threadIdx.x == 0) { bulk_wait_all(); fence_async_proxy_global(); }
+        __syncthreads();
+    }
+    __device__ __forceinline__ void kmer(int q, uint32_t idx)
+    {
+        if (G::SUB > 1 && (int)(idx / G::TILE_BINS) != sub) return;
+        atomicAdd(rows + (int64_t)q * G::BINS + idx, 1u);
+    }
+    __device__ __forceinline__ void invalid(int q, int n)
+    {
+        if (period > 0 && q >= qb && (q - qb) % period == 0) return;
+        if (q >= 1 && has_last) atomicAdd(rows + (int64_t)q * G::BINS - 1, (uint32_t)n);
+    }
+};
+
+constexpr int kBigZeroBytes = 32 << 10;    // constant zero source
+constexpr int kBigThreads = 256;
+
+template <int K, int FMT, int TILE_BYTES>
+__global__ void __launch_bounds__(kBigThreads) dense_bigrow_kernel(const DenseArgs a)
+{
+    using G = BigGeo<K, TILE_BYTES>;
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint4* zero = reinterpret_cast<uint4*>(smem);
+    unsigned char* tp = smem + kBigZeroBytes;
+    ReadTable tb;
+    tb.start = reinterpret_cast<int64_t*>(tp);
+    tb.tend = reinterpret_cast<int32_t*>(tp + G::TABLE_READS * 8);
+    tb.extra = reinterpret_cast<int32_t*>(tp + G::TABLE_READS * 12);
+    tb.cum = reinterpret_cast<uint32_t*>(tp + G::TABLE_READS * 16);
+
+    for (int i = threadIdx.x; i < kBigZeroBytes / 16; i += kBigThreads) zero[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_async_proxy_shared();
+    __syncthreads();
+
+    for (int64_t tile = blockIdx.x; tile < a.num_tiles; tile += gridDim.x) {
+        const int64_t group = tile / G::SUB;
+        const int sub = (int)(tile - group * G::SUB);
+        const int64_t r0 = a.read_begin + group * G::GROUP;
+        const int nrows = (int)min((int64_t)G::GROUP, a.read_end - r0);
+        const bool has_last = (sub == G::SUB - 1);
+        int qb = 0, period = 0;
+        if (a.chunk_size > 0) {
+            const int64_t phase = (a.index_base + r0) % a.chunk_size;
+            const int64_t first = phase == 0 ? 0 : a.chunk_size - phase;
+            if (first <= G::TABLE_READS) {
+                qb = (int)first;
+                period = (int)min(a.chunk_size, (int64_t)(4 * kMaxGroupReads));
+            }
+        } else if (r0 == 0) {
+            period = 4 * kMaxGroupReads;
+        }
+        const bool next_opens_chunk = period > 0 && nrows >= qb && (nrows - qb) % period == 0;
+        const bool halo = a.mode == MODE_COMPAT && has_last && (r0 + nrows < a.nS) && !next_opens_chunk;
+        const int nreads = nrows + (halo ? 1 : 0);
+        uint32_t* rows = a.out + (r0 - a.read_begin) * G::BINS;
+
+        if (threadIdx.x == 0) {  // 1. zero stream
+            unsigned char* dst = reinterpret_cast<unsigned char*>(rows) + (int64_t)sub * TILE_BYTES;
+            int64_t left = G::SUB > 1 ? (int64_t)TILE_BYTES : (int64_t)nrows * G::ROW_BYTES;
+            while (left > 0) {
+                const uint32_t n = (uint32_t)min((int64_t)kBigZeroBytes, left);
+                bulk_store_issue(dst, zero, n);
+                dst += n; left -= n;
+            }
+            bulk_commit();
+        }
+        fill_read_table<K>(tb, a.start, a.length, r0, nreads, a.mode);
+        __syncthreads();
+        if (threadIdx.x < 32) scan_read_table(tb, nreads);
+        __syncthreads();
+        BigRowSink<K, TILE_BYTES> sink{rows, sub, has_last, qb, period};
+        for_each_window<K, FMT, G::TABLE_READS>(a.bases, tb, nreads, nrows, a.mode, sink);  // 2. + 3.
+        __syncthreads();  // table is reused by the next tile
+    }
+    if (threadIdx.x == 0) bulk_wait_all();
+}
+
+static int env_int(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+template <int K, int FMT, int TILE_BYTES>
+static cudaError_t launch_bigrow_t(const DenseArgs& a0, cudaStream_t st, int ctas_cap)
+{
+    using G = BigGeo<K, TILE_BYTES>;
+    auto kern = dense_bigrow_kernel<K, FMT, TILE_BYTES>;
+    const int smem = kBigZeroBytes + G::TABLE_READS * 16 + (G::TABLE_READS + 1) * 4 + 16;
+    static thread_local int configured_dev = -1;
+    static thread_local int ctas_per_sm = 0, num_sms = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (configured_dev != dev) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kBigThreads, smem);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        configured_dev = dev;
+    }
+    DenseArgs a = a0;
+    a.num_tiles = (a.read_end - a.read_begin + G::GROUP - 1) / G::GROUP * G::SUB;
+    if (a.num_tiles <= 0) return cudaSuccess;
+    // Rows must still be L2-resident when their reductions arrive: bound the bytes in flight
+    // (CTAs x tile) well below the 126 MB L2 (measured: profiles/r1_notes.md).
+    const int per_sm = ctas_cap > 0 && ctas_cap < ctas_per_sm ? ctas_cap : ctas_per_sm;
+    const int64_t resident = (int64_t)num_sms * per_sm;
+    const unsigned grid = (unsigned)(a.num_tiles < resident ? a.num_tiles : resident);
+    kern<<<grid, kBigThreads, smem, st>>>(a);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
+}
+
+template <int K, int FMT>
+static cudaError_t launch_bigrow_k(const DenseArgs& a, cudaStream_t st)
+{
+    static const int tile_kb = env_int("CFRK_BIG_TILE_KB", 64);
+    static const int ctas = env_int("CFRK_BIG_CTAS", 3);
+    switch (tile_kb) {
+    case 16: return launch_bigrow_t<K, FMT, (16 << 10)>(a, st, ctas);
+    case 32: return launch_bigrow_t<K, FMT, (32 << 10)>(a, st, ctas);
+    case 128: return launch_bigrow_t<K, FMT, (128 << 10)>(a, st, ctas);
+    case 256: return launch_bigrow_t<K, FMT, (256 << 10)>(a, st, ctas);
+    default: return launch_bigrow_t<K, FMT, (64 << 10)>(a, st, ctas);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 constexpr int kTileBins = 4096;  // 16 KiB tiles
 constexpr int kDenseThreads = 256;
 constexpr int kDenseBufs = 2;
@@ -177,6 +345,16 @@ static cudaError_t launch_dense_k(const DenseArgs& a0, cudaStream_t st)
     return cudaGetLastError();
 }
 
+// k >= this uses dense_bigrow_kernel; CFRK_BIGROW_MIN_K overrides (tuning / A-B measurements)
+static int big_row_min_k()
+{
+    static const int v = [] {
+        const char* e = getenv("CFRK_BIGROW_MIN_K");
+        return e ? atoi(e) : 6;
+    }();
+    return v;
+}
+
 template <int FMT>
 static cudaError_t launch_dense_fmt(int k, const DenseArgs& a, cudaStream_t st)
 {
@@ -186,9 +364,9 @@ static cudaError_t launch_dense_fmt(int k, const DenseArgs& a, cudaStream_t st)
     case 3: return launch_dense_k<3, FMT>(a, st);
     case 4: return launch_dense_k<4, FMT>(a, st);
     case 5: return launch_dense_k<5, FMT>(a, st);
-    case 6: return launch_dense_k<6, FMT>(a, st);
-    case 7: return launch_dense_k<7, FMT>(a, st);
-    case 8: return launch_dense_k<8, FMT>(a, st);
+    case 6: return big_row_min_k() <= 6 ? launch_bigrow_k<6, FMT>(a, st) : launch_dense_k<6, FMT>(a, st);
+    case 7: return big_row_min_k() <= 7 ? launch_bigrow_k<7, FMT>(a, st) : launch_dense_k<7, FMT>(a, st);
+    case 8: return big_row_min_k() <= 8 ? launch_bigrow_k<8, FMT>(a, st) : launch_dense_k<8, FMT>(a, st);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -222,6 +400,7 @@ cudaError_t launch_dense(const void* bases, int fmt, const int64_t* start, const
 // ------------------------------------------------------------------------------------------
 // Whole-dataset histogram: same item loop, sink = one red.global per valid window.
 struct HistSink {
+    static constexpr bool kCtaUniform = false;
     uint32_t* hist;
     __device__ __forceinline__ void kmer(int, uint32_t idx) { atomicAdd(&hist[idx], 1u); }
     __device__ __forceinline__ void invalid(int, int) {}

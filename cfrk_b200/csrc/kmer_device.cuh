@@ -156,6 +156,9 @@ template <> struct Log2Ceil<1> { static constexpr int value = 0; };
 //   sink.kmer(q, idx)        one valid window of read q (table-local index) with index idx
 //   sink.invalid(q, count)   compat only: `count` visited windows of read q held a non-ACGT
 //                            byte or the terminator
+//   sink.before_first_emit() (only if Sink::kCtaUniform) is reached by EVERY thread of the CTA
+//                            exactly once, after the first chunk's loads were issued and before
+//                            anything is emitted (a place for a CTA-wide wait + barrier)
 // Reads q >= ncount (the halo read of a compat tile) only report invalid windows.
 // MAXREADS bounds n (binary search depth).
 template <int K, int FMT, int MAXREADS, class Sink>
@@ -171,9 +174,12 @@ __device__ __forceinline__ void for_each_window(const uint8_t* __restrict__ base
     const uint32_t total = tb.cum[n];
     const uint32_t nchunks = (total + 30u) / 31u;
 
-    for (uint32_t chunk = warp; chunk < nchunks; chunk += nwarps) {
+    // kCtaUniform: every warp runs the same number of iterations (idle ones with no live lane)
+    const uint32_t niter = (nchunks + nwarps - 1) / nwarps;
+    for (uint32_t it = 0, chunk = warp; Sink::kCtaUniform ? (it < niter) : (chunk < nchunks);
+         ++it, chunk += nwarps) {
         const int64_t item = (int64_t)chunk * 31 + lane - 1;
-        const bool live = item >= 0 && item < (int64_t)total;
+        const bool live = chunk < nchunks && item >= 0 && item < (int64_t)total;
         uint32_t codes = 0, valid = 0, count_mask = 0;
         int q = 0;
         bool first_block = true;
@@ -213,6 +219,7 @@ __device__ __forceinline__ void for_each_window(const uint8_t* __restrict__ base
         for (int i = 1; i < K; i++) ok &= v32 >> i;
         const uint32_t good = q < ncount ? (ok & count_mask) : 0u;
         const uint32_t bad = ~ok & count_mask;
+        if constexpr (Sink::kCtaUniform) { if (it == 0) sink.before_first_emit(); }
         if (mode == MODE_COMPAT) {
             int nbad = __popc(bad) + ((counting && first_block) ? tb.extra[q] : 0);
             if (nbad) sink.invalid(q, nbad);
@@ -242,6 +249,18 @@ __device__ __forceinline__ void bulk_store_tile(void* gdst, const void* ssrc, ui
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
                  :: "l"(gdst), "r"(saddr), "r"(bytes) : "memory");
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_store_issue(void* gdst, const void* ssrc, uint32_t bytes)
+{
+    uint32_t saddr = (uint32_t)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// order async-proxy (TMA) writes to global before later generic-proxy accesses
+__device__ __forceinline__ void fence_async_proxy_global()
+{
+    asm volatile("fence.proxy.async.global;" ::: "memory");
 }
 template <int N>
 __device__ __forceinline__ void bulk_wait_read()
