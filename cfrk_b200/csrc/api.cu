@@ -140,7 +140,7 @@ int cfrk_count_dense_device(const void* d_bases, int fmt, const int64_t* d_start
         return fail(CFRK_EINVAL, "d_bases and d_freq must be 16-byte aligned");
     if (read_begin % cfrk::dense_reads_per_tile(k))
         return fail(CFRK_EINVAL, "read_begin must be a multiple of cfrk_dense_reads_per_tile(k)");
-    cudaError_t e = cfrk::launch_dense(d_bases, fmt, d_start, d_length, nS, read_begin, read_end, k, mode,
+    cudaError_t e = cfrk::launch_dense(d_bases, fmt, d_start, d_length, nN, nS, read_begin, read_end, k, mode,
                                        chunk_size, first_read_index, d_freq, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail_cuda(e, "dense_count_kernel launch");
     return CFRK_OK;
@@ -211,7 +211,7 @@ int cfrk_count_dense_host(const void* bases, int fmt, const int64_t* start, cons
         const int slot = (int)(s & 1);
         const int64_t r0 = s * slice, r1 = std::min(nS, r0 + slice);
         if (s >= 2) CU(cudaStreamWaitEvent(c.compute, c.drained[slot], 0));
-        cudaError_t e = cfrk::launch_dense(c.d_bases, fmt, c.d_start, c.d_length, nS, r0, r1, k, mode,
+        cudaError_t e = cfrk::launch_dense(c.d_bases, fmt, c.d_start, c.d_length, nN, nS, r0, r1, k, mode,
                                            0, 0, c.d_ring[slot], c.compute);
         if (e != cudaSuccess) return fail_cuda(e, "dense_count_kernel launch");
         CU(cudaEventRecord(c.done[slot], c.compute));

@@ -66,6 +66,7 @@ struct DenseArgs {
     const int64_t* start;
     const int32_t* length;
     int64_t nS;          // reads in the batch (halo / spill scope)
+    int64_t nN;          // bytes in the bases buffer
     int64_t read_begin;  // rows [read_begin, read_end) are produced by this launch
     int64_t read_end;
     uint32_t* out;       // row read_begin at out[0]
@@ -114,7 +115,7 @@ __global__ void __launch_bounds__(NTHREADS) dense_count_kernel(const DenseArgs a
 
         // the TMA store that last used this buffer (NBUF tiles ago) must have read it out
         if (threadIdx.x == 0) bulk_wait_read<NBUF - 1>();
-        fill_read_table<K>(tb, a.start, a.length, r0, nreads, a.mode);
+        fill_read_table<K>(tb, a.start, a.length, r0, nreads, a.mode, a.nN);
         __syncthreads();
 
         {   // zero the tile (replaces SetMatrix(d_Freq, 0), src/kmer_main.cu:108) ...
@@ -243,7 +244,7 @@ __global__ void __launch_bounds__(kBigThreads) dense_bigrow_kernel(const DenseAr
             }
             bulk_commit();
         }
-        fill_read_table<K>(tb, a.start, a.length, r0, nreads, a.mode);
+        fill_read_table<K>(tb, a.start, a.length, r0, nreads, a.mode, a.nN);
         __syncthreads();
         if (threadIdx.x < 32) scan_read_table(tb, nreads);
         __syncthreads();
@@ -384,12 +385,12 @@ int dense_reads_per_tile(int k)
 }
 
 cudaError_t launch_dense(const void* bases, int fmt, const int64_t* start, const int32_t* length,
-                         int64_t nS, int64_t read_begin, int64_t read_end, int k, int mode,
+                         int64_t nN, int64_t nS, int64_t read_begin, int64_t read_end, int k, int mode,
                          int64_t chunk_size, int64_t index_base, int32_t* out, cudaStream_t st)
 {
     DenseArgs a;
     a.bases = static_cast<const uint8_t*>(bases);
-    a.start = start; a.length = length; a.nS = nS;
+    a.start = start; a.length = length; a.nS = nS; a.nN = nN;
     a.read_begin = read_begin; a.read_end = read_end;
     a.out = reinterpret_cast<uint32_t*>(out);
     a.mode = mode; a.num_tiles = 0;
@@ -425,7 +426,7 @@ __global__ void __launch_bounds__(kHistThreads) global_hist_kernel(const uint8_t
         const int64_t r0 = g * kHistGroup;
         const int n = (int)min((int64_t)kHistGroup, nS - r0);
         __syncthreads();  // previous group's item loop is done with the table
-        fill_read_table<K>(tb, start, length, r0, n, MODE_EXACT);
+        fill_read_table<K>(tb, start, length, r0, n, MODE_EXACT, INT64_MAX);
         __syncthreads();
         if (threadIdx.x < 32) scan_read_table(tb, n);
         __syncthreads();

@@ -10,7 +10,7 @@ namespace cfrk {
 // compat: read i opens a reference chunk (its spill is dropped) iff i == 0 when chunk_size == 0,
 // else iff (index_base + i) % chunk_size == 0.
 cudaError_t launch_dense(const void* bases, int fmt, const int64_t* start, const int32_t* length,
-                         int64_t nS, int64_t read_begin, int64_t read_end, int k, int mode,
+                         int64_t nN, int64_t nS, int64_t read_begin, int64_t read_end, int k, int mode,
                          int64_t chunk_size, int64_t index_base, int32_t* out, cudaStream_t st);
 int dense_reads_per_tile(int k);
 

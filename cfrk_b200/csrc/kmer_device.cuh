@@ -95,10 +95,24 @@ struct ReadTable {
 //   compat: starts t < min(len-1, 1024) (src/kmer_kernel.cu:85, src/kmer_main.cu:82), so ends
 //           < min(len-1,1024) + k-1; those at or beyond len hold the terminator -> `extra`.
 //   exact : every window inside the read.
+//   compat, len == 0: `threadIdx.x < length[i]-1` is an UNSIGNED compare in the reference, so an
+//           empty read lets all 1024 threads through: the block walks over the bytes that follow
+//           (terminators, later reads) and counts them into the empty read's row.  Modelled as a
+//           read that extends to the end of the buffer (`avail` bytes) with 1024 visited starts.
 template <int K>
-__device__ __forceinline__ void read_extent(int mode, int len, int& tend, int& extra)
+__device__ __forceinline__ void read_extent(int mode, int len, int64_t avail, int& tend, int& extra)
 {
-    int vis = (mode == MODE_COMPAT) ? min(len - 1, kRefBlockThreads) : len - K + 1;
+    int vis;
+    if (mode == MODE_COMPAT) {
+        if (len == 0) {
+            len = (int)min(avail, (int64_t)(kRefBlockThreads + K));
+            vis = min(len, kRefBlockThreads);
+        } else {
+            vis = min(len - 1, kRefBlockThreads);
+        }
+    } else {
+        vis = len - K + 1;
+    }
     if (vis <= 0) { tend = 0; extra = 0; return; }
     int last = vis + K - 1;
     tend = min(len, last);
@@ -111,13 +125,13 @@ __device__ __forceinline__ void read_extent(int mode, int len, int& tend, int& e
 template <int K>
 __device__ __forceinline__ void fill_read_table(const ReadTable& tb, const int64_t* __restrict__ start,
                                                 const int32_t* __restrict__ length, int64_t r0, int n,
-                                                int mode)
+                                                int mode, int64_t nN)
 {
     for (int q = threadIdx.x; q < n; q += blockDim.x) {
         int64_t s = start[r0 + q];
         int len = length[r0 + q];
         int tend, extra;
-        read_extent<K>(mode, len, tend, extra);
+        read_extent<K>(mode, len, nN - s, tend, extra);
         tb.start[q] = s;
         tb.tend[q] = tend;
         tb.extra[q] = extra;

@@ -322,11 +322,36 @@ struct Pipeline {
         return true;
     }
     // Count reads [0, nreads) of the span, produce rows [0, nrows) and hand them to the writer.
-    bool run(const char* h_in, size_t in_bytes, const RecordIndex& ri, size_t nrows, int k, int mode,
+    bool run(const char* h_in, size_t in_bytes, const RecordIndex& ri_in, size_t nrows, int k, int mode,
              int64_t chunk_size, int64_t index_base, CfrkWriter& w, Err& err)
     {
-        const size_t nreads = ri.start.size();
         if (nrows == 0) return true;
+        // An EMPTY read makes the reference walk over the bytes that FOLLOW it in its batch layout
+        // (kmer_device.cuh read_extent).  Raw file bytes have header lines there, so for such a
+        // (rare) span the records are first compacted into the reference layout: text, one
+        // separator, next text, ...
+        const RecordIndex* rip = &ri_in;
+        RecordIndex packed;
+        std::vector<char> pack_buf;
+        if (mode == CFRK_MODE_COMPAT &&
+            std::find(ri_in.length.begin(), ri_in.length.end(), 0) != ri_in.length.end()) {
+            size_t total = 0;
+            for (int32_t l : ri_in.length) total += (size_t)l + 1;
+            pack_buf.resize(total + CFRK_PAD);
+            size_t wpos = 0;
+            for (size_t i = 0; i < ri_in.start.size(); i++) {
+                packed.start.push_back((int64_t)wpos);
+                packed.length.push_back(ri_in.length[i]);
+                memcpy(pack_buf.data() + wpos, h_in + ri_in.start[i], (size_t)ri_in.length[i]);
+                wpos += (size_t)ri_in.length[i];
+                pack_buf[wpos++] = '\n';
+            }
+            h_in = pack_buf.data();
+            in_bytes = wpos;
+            rip = &packed;
+        }
+        const RecordIndex& ri = *rip;
+        const size_t nreads = ri.start.size();
         const size_t bins = (size_t)1 << (2 * k), row_bytes = bins * 4;
         if (!reserve(in_bytes, nreads, row_bytes, err)) return false;
         const size_t rpt = (size_t)cfrk::dense_reads_per_tile(k);
@@ -346,7 +371,7 @@ struct Pipeline {
                 // slot reuse: the host finished formatting slice s-2 before we get here (below);
                 // the kernel must not overwrite d_rows[slot] before the D2H of slice s-2 is done
                 if (s >= 2) RF_CU(cudaStreamWaitEvent(compute, drained[slot], 0));
-                cudaError_t e = cfrk::launch_dense(d_in, cfrk::FMT_ASCII, d_start, d_length, (int64_t)nreads,
+                cudaError_t e = cfrk::launch_dense(d_in, cfrk::FMT_ASCII, d_start, d_length, (int64_t)in_bytes, (int64_t)nreads,
                                                    (int64_t)r0, (int64_t)r1, k, mode, chunk_size, index_base,
                                                    d_rows[slot], compute);
                 if (e != cudaSuccess) { err.code = CFRK_ECUDA; err.msg = std::string("dense_count_kernel: ") + cudaGetErrorString(e); return false; }
@@ -409,12 +434,21 @@ bool run_file(const char* fasta, const char* out_path, int k, int nt, int64_t ch
 
         size_t keep_from;  // data[keep_from, n) goes in front of the next buffer
         if (all_rows) {
-            // rows for all complete records but the last one, which is only needed for its spill
-            // into its predecessor and is counted again as read 0 of the next span
-            const size_t nrows = b->eof ? m : (m ? m - 1 : 0);
+            // Rows for all complete records but a held-back tail: the record after the last row
+            // is needed for its spill into that row, and an empty read walks up to 1024+k bytes
+            // into its successors (kmer_device.cuh read_extent).  The held-back records are
+            // counted again at the head of the next span.
+            size_t nrows = m;
+            if (!b->eof) {
+                size_t held = 0;
+                while (nrows > 0 && (nrows == m || held < (size_t)cfrk::kRefBlockThreads + 64)) {
+                    nrows--;
+                    held += (size_t)ri.length[nrows] + 1;
+                }
+            }
             if (!gpu.run(data, n, ri, nrows, k, mode, chunk_size, reads_done, w, err)) return false;
             reads_done += (int64_t)nrows;
-            keep_from = b->eof ? n : (m ? ri.header[m - 1] : 0);
+            keep_from = b->eof ? n : (m ? ri.header[nrows] : 0);
         } else {
             for (size_t r = 0; r < m; r++)
                 if ((reads_done + (int64_t)r) % chunk_size == 0) tail_off = (int64_t)(span_file_off + ri.header[r]);

@@ -159,9 +159,15 @@ void oracle_count_compat(const int8_t *data, const int64_t *start, const int32_t
     const int64_t fourk = four_pow(k);
     memset(freq, 0, (size_t)(nS * fourk) * sizeof(int32_t)); /* SetMatrix, src/kmer_main.cu:108 */
     for (int64_t i = 0; i < nS; i++) {
-        int64_t visited = (int64_t)length[i] - 1;
+        /* `threadIdx.x < length[i]-1` compares unsigned (src/kmer_kernel.cu:85): for an EMPTY
+         * read the bound is (unsigned)-1 and all 1024 threads pass, so the block walks over
+         * the bytes that follow (terminators and later reads) and counts them into row i.
+         * Positions at or beyond nN read Index[] out of bounds in the reference (garbage);
+         * they are not counted here. */
+        int64_t visited = length[i] == 0 ? REF_BLOCK_THREADS : (int64_t)length[i] - 1;
         if (visited > REF_BLOCK_THREADS) visited = REF_BLOCK_THREADS;
         for (int64_t t = 0; t < visited; t++) {
+            if (start[i] + t >= nN) break;
             int64_t pos = fourk * i + window_index(data, nN, start[i] + t, k);
             if (pos >= 0) freq[pos] += 1;
         }
@@ -202,10 +208,16 @@ static void scan_read(const mt_job *j, int64_t i, int32_t *row, uint64_t *hist, 
 {
     const int k = j->k;
     const uint64_t mask = (k >= 32) ? ~0ull : (((uint64_t)1 << (2 * k)) - 1);
-    const int64_t len = j->length[i];
+    int64_t len = j->length[i];
     int64_t visited;
     if (j->mode == ORACLE_MODE_COMPAT) {
-        visited = len - 1; if (visited > REF_BLOCK_THREADS) visited = REF_BLOCK_THREADS;
+        if (len == 0) {   /* empty read: the unsigned compare lets all 1024 threads through */
+            len = j->nN - j->start[i];   /* ... over whatever follows in the buffer */
+            visited = len;
+        } else {
+            visited = len - 1;
+        }
+        if (visited > REF_BLOCK_THREADS) visited = REF_BLOCK_THREADS;
         if (visited < 0) visited = 0;
     } else {
         visited = len - k + 1; if (visited < 0) visited = 0;

@@ -85,6 +85,9 @@ def fx_ragged(seed=10, n=300):
         if L and rng.random() < 0.3:
             s[rng.randrange(L)] = "N"
         out.append(f">r{i}\n{''.join(s)}\n")
+    # an EMPTY read makes the reference walk 1024 positions into its successors; at the end of
+    # the batch that walk leaves the buffer (undefined in the reference), so close with clean reads
+    out += [f">tail{i}\n{_seq(rng, 150)}\n" for i in range(10)]
     return "".join(out)
 
 
@@ -130,6 +133,18 @@ def ascii_batch(text):
         lengths.append(max(0, e - s - 1))
     return (np.frombuffer(raw, dtype=np.uint8).copy(), np.array(starts, dtype=np.int64),
             np.array(lengths, dtype=np.int32))
+
+
+def ascii_compact(text):
+    """reference batch layout (one separator per read, no header lines) holding LETTERS: what
+    cfrk_run_file builds for spans with empty reads, and the layout bench.py generates"""
+    import oracle_binding as ob
+    data, start, length = ob.parse_fasta(text=text)
+    lut = np.array([ord(c) for c in "ACGT"], dtype=np.uint8)
+    raw = np.where(data >= 0, lut[np.clip(data, 0, 3)], ord("N")).astype(np.uint8)
+    for s_, l_ in zip(start, length):
+        raw[s_ + l_] = ord("\n")
+    return raw, start, length
 
 
 def synthetic_codes(nS, L, seed=42, n_frac=0.0):

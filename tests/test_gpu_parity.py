@@ -26,6 +26,9 @@ def test_edge_set_ascii(name, text, ks, mode):
     data, start, length = ob.parse_fasta(text=text)
     raw, rstart, rlength = fx.ascii_batch(text)
     np.testing.assert_array_equal(rlength, length)
+    if mode == cf.MODE_COMPAT and (length == 0).any():
+        # an empty read walks over the bytes that follow it: only the header-free layout matches
+        raw, rstart, rlength = fx.ascii_compact(text)
     for k in ks:
         want = ob.count_dense(data, start, length, k, mode)
         got = cf.count_dense_host(raw, rstart, rlength, k, mode, cf.FMT_ASCII)
