@@ -380,7 +380,7 @@ def run_reference(args):
         km = getattr(lib, "_Z9kmer_mainP4readllit")
         km.argtypes = [C.POINTER(_RefRead), C.c_long, C.c_long, C.c_int, C.c_ushort]
         km.restype = None
-        lib.cudaFreeHost.argtypes = [C.c_void_p]
+        lib.ref_free_host.argtypes = [C.c_void_p]
         torch.cuda.set_device(0)
         hb, hs, hl = make_reads_host(cn, L, 1000, "codes")
         hb_t = torch.from_numpy(hb).pin_memory(); hs_t = torch.from_numpy(hs).pin_memory()
@@ -392,7 +392,7 @@ def run_reference(args):
                 rd = _RefRead(hb_t.data_ptr(), hl_t.data_ptr(), hs_t.data_ptr(), None, None)
                 km(C.byref(rd), nN, cn, k, 0)
                 if rd.Freq:
-                    lib.cudaFreeHost(rd.Freq)   # the reference never frees it (src/kmer_main.cu:115)
+                    lib.ref_free_host(rd.Freq)   # the reference never frees it (src/kmer_main.cu:115)
         for _ in range(max(1, args.warmup)):
             sweep()
         torch.cuda.synchronize()

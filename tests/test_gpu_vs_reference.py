@@ -31,6 +31,9 @@ def call_kmer_main(lib, data, start, length, k):
     fn(C.byref(rd), nN, nS, k, 0)
     assert rd.Freq
     out = np.ctypeslib.as_array(C.cast(rd.Freq, C.POINTER(C.c_int32)), shape=(nS, 4 ** k)).copy()
+    if hasattr(lib, "ref_free_host"):      # the reference never frees rd->Freq (src/kmer_main.cu:115)
+        lib.ref_free_host.argtypes = [C.c_void_p]
+        lib.ref_free_host(rd.Freq)
     return out
 
 
