@@ -17,6 +17,12 @@ namespace cfrk {
 static std::atomic<uint64_t> g_launches{0};
 uint64_t launch_count() { return g_launches.load(); }
 
+static int env_int(const char* name, int dflt)
+{
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 // ------------------------------------------------------------------------------------------
 // Tile geometry.  A tile is TILE_BINS consecutive int32 of the output, i.e. a contiguous
 // TILE_BINS*4-byte span of HBM that one CTA builds in shared memory and ships with one TMA
@@ -30,7 +36,8 @@ struct Geo {
     static constexpr int TILE_BINS = SUB > 1 ? TILE_BINS_T : RPT * BINS;
     static constexpr int TILE_BYTES = TILE_BINS * 4;
     static constexpr int TABLE_READS = RPT + 1;  // + halo read (compat spill)
-    // shared memory: NBUF tile buffers, then the read table
+    static constexpr int ROW_ALIGN = BINS * 4 < 16 ? 16 : BINS * 4;  // rows aligned to their size
+    // shared memory: alignment slack, NBUF tile buffers, then the read table
     static constexpr int table_bytes() { return TABLE_READS * 16 + (TABLE_READS + 1) * 4 + 16; }
 };
 
@@ -38,26 +45,18 @@ template <int K, int TILE_BINS_T>
 struct DenseSink {
     using G = Geo<K, TILE_BINS_T>;
     static constexpr bool kCtaUniform = false;
-    uint32_t* hist;   // current tile buffer
-    int sub;          // which TILE_BINS-slice of the row (k >= 7)
-    bool has_last;    // tile holds bin 4^k-1 of its rows
-    int qb, period;   // table-local reads qb, qb+period, ... open a reference chunk (period 0: none)
-    __device__ __forceinline__ void kmer(int q, uint32_t idx)
-    {
-        if (G::SUB > 1) {
-            if ((int)(idx / G::TILE_BINS) != sub) return;
-            idx &= G::TILE_BINS - 1;
-        }
-        atomicAdd(&hist[q * G::BINS * (G::SUB > 1 ? 0 : 1) + idx], 1u);
-    }
+    static constexpr bool kSharedRows = true;
+    uint32_t hist_saddr;  // shared-window address of the tile buffer (aligned to the row size)
+    int qb, period;       // table-local reads qb, qb+period, ... open a reference chunk (period 0: none)
+    __device__ __forceinline__ uint32_t row_saddr(int q) const { return hist_saddr + (uint32_t)q * (G::BINS * 4); }
     // the reference adds at Freq[4^k*i + (-1)]: last bin of read i-1 (src/kmer_kernel.cu:84-87);
     // q == 0 belongs to the previous tile (counted there through its halo read); for the first
     // read of a reference chunk (a separate kmer_main call) it is the lost Freq[-1] store.
     __device__ __forceinline__ void invalid(int q, int n)
     {
         if (period > 0 && q >= qb && (q - qb) % period == 0) return;
-        if (q >= 1 && has_last)
-            atomicAdd(&hist[(G::SUB > 1 ? 0 : (q - 1) * G::BINS) + (G::SUB > 1 ? G::TILE_BINS : G::BINS) - 1], (uint32_t)n);
+        if (q >= 1)
+            asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(row_saddr(q) - 4u), "r"((uint32_t)n) : "memory");
     }
 };
 
@@ -80,7 +79,11 @@ template <int K, int FMT, int TILE_BINS_T, int NTHREADS, int NBUF>
 __global__ void __launch_bounds__(NTHREADS) dense_count_kernel(const DenseArgs a)
 {
     using G = Geo<K, TILE_BINS_T>;
-    extern __shared__ __align__(128) unsigned char smem[];
+    static_assert(G::SUB == 1, "rows larger than a tile go through dense_bigrow_kernel");
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // align the tile buffers to the row size in the shared window (emit_item ORs bin offsets in)
+    const uint32_t raw_saddr = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    unsigned char* smem = smem_raw + ((G::ROW_ALIGN - (raw_saddr & (G::ROW_ALIGN - 1))) & (G::ROW_ALIGN - 1));
     uint32_t* bufs = reinterpret_cast<uint32_t*>(smem);
     unsigned char* tp = smem + (size_t)NBUF * G::TILE_BYTES;
     ReadTable tb;
@@ -128,7 +131,7 @@ __global__ void __launch_bounds__(NTHREADS) dense_count_kernel(const DenseArgs a
         }
         __syncthreads();
 
-        DenseSink<K, TILE_BINS_T> sink{hist, sub, has_last, qb, period};
+        DenseSink<K, TILE_BINS_T> sink{(uint32_t)__cvta_generic_to_shared(hist), qb, period};
         for_each_window<K, FMT, G::TABLE_READS>(a.bases, tb, nreads, nrows, a.mode, sink);
 
         fence_async_proxy_shared();  // make the shared-memory counts visible to the TMA engine
@@ -141,6 +144,128 @@ __global__ void __launch_bounds__(NTHREADS) dense_count_kernel(const DenseArgs a
         }
     }
     if (threadIdx.x == 0) bulk_wait_all();
+}
+
+// ------------------------------------------------------------------------------------------
+// Small rows (k <= 5), warp-autonomous: every warp builds its own tiles of RW rows in its own two
+// shared-memory buffers and ships them with its own TMA bulk stores.  No CTA barrier, no
+// shared-memory read table (lane q holds read q, lookups are shuffles), the next tile's offsets
+// and the next chunk's bases are already in flight while the current ones are processed.  This
+// replaces the CTA-cooperative tile loop for small k, which ncu showed to be one serial chain per
+// 16 KiB (43-77 % of warp samples waiting at barriers, profiles/r1_notes.md).
+template <int K>
+struct WarpSink {
+    static constexpr bool kCtaUniform = false;
+    static constexpr bool kSharedRows = true;
+    static constexpr int BINS = 1 << (2 * K);
+    uint32_t hist_saddr;
+    int qb, period;
+    __device__ __forceinline__ uint32_t row_saddr(int q) const { return hist_saddr + (uint32_t)q * (BINS * 4); }
+    __device__ __forceinline__ void invalid(int q, int n)
+    {
+        if (period > 0 && q >= qb && (q - qb) % period == 0) return;
+        if (q >= 1)
+            asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(row_saddr(q) - 4u), "r"((uint32_t)n) : "memory");
+    }
+};
+
+template <int K, int FMT, int RW, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) dense_warp_kernel(const DenseArgs a)
+{
+    constexpr int BINS = 1 << (2 * K);
+    constexpr int TILE_BINS = RW * BINS;
+    constexpr int TILE_BYTES = TILE_BINS * 4;
+    static_assert(RW + 1 <= 32, "one lane per read of the tile (+ halo)");
+    constexpr int ROW_ALIGN = BINS * 4 < 16 ? 16 : BINS * 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const uint32_t raw_saddr = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    unsigned char* smem = smem_raw + ((ROW_ALIGN - (raw_saddr & (ROW_ALIGN - 1))) & (ROW_ALIGN - 1));
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* bufs = reinterpret_cast<uint32_t*>(smem) + (size_t)warp * 2 * TILE_BINS;
+    const int64_t nwarps = (int64_t)gridDim.x * WARPS;
+    int64_t tile = (int64_t)blockIdx.x * WARPS + warp;
+    if (tile >= a.num_tiles) return;
+
+    // offsets of the first tile; afterwards always one tile ahead
+    int64_t s = 0; int len = 0;
+    {
+        const int64_t r = a.read_begin + tile * RW + lane;
+        if (lane <= RW && r < a.nS) { s = a.start[r]; len = a.length[r]; }
+    }
+    for (int it = 0; tile < a.num_tiles; ++it) {
+        const int64_t r0 = a.read_begin + tile * RW;
+        const int nrows = (int)min((int64_t)RW, a.read_end - r0);
+        int qb = 0, period = 0;
+        if (a.chunk_size > 0) {
+            const int64_t phase = (a.index_base + r0) % a.chunk_size;
+            const int64_t first = phase == 0 ? 0 : a.chunk_size - phase;
+            if (first <= RW + 1) {
+                qb = (int)first;
+                period = (int)min(a.chunk_size, (int64_t)(4 * kMaxGroupReads));
+            }
+        } else if (r0 == 0) {
+            period = 4 * kMaxGroupReads;
+        }
+        const bool next_opens_chunk = period > 0 && nrows >= qb && (nrows - qb) % period == 0;
+        const bool halo = a.mode == MODE_COMPAT && (r0 + nrows < a.nS) && !next_opens_chunk;
+        const int nreads = nrows + (halo ? 1 : 0);
+        const LaneRead lr = make_lane_read<K>(lane < nreads, s, len, a.mode, a.nN);
+
+        const int64_t next_tile = tile + nwarps;
+        if (next_tile < a.num_tiles) {  // prefetch the next tile's offsets
+            const int64_t r = a.read_begin + next_tile * RW + lane;
+            if (lane <= RW && r < a.nS) { s = a.start[r]; len = a.length[r]; }
+        }
+
+        uint32_t* hist = bufs + (size_t)(it & 1) * TILE_BINS;
+        if (lane == 0) bulk_wait_read<1>();  // the store issued two tiles ago has read this buffer
+        __syncwarp();
+        {
+            uint4* h4 = reinterpret_cast<uint4*>(hist);
+            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+            for (int i = lane; i < TILE_BYTES / 16; i += 32) h4[i] = z;
+        }
+        __syncwarp();
+        WarpSink<K> sink{(uint32_t)__cvta_generic_to_shared(hist), qb, period};
+        warp_for_each_window<K, FMT, RW + 1>(a.bases, lr, nreads, nrows, a.mode, sink);
+        fence_async_proxy_shared();
+        __syncwarp();
+        if (lane == 0) bulk_store_tile(a.out + (r0 - a.read_begin) * BINS, hist, (uint32_t)nrows * BINS * 4u);
+        tile = next_tile;
+    }
+    if (lane == 0) bulk_wait_all();
+}
+
+template <int K, int FMT, int RW, int WARPS>
+static cudaError_t launch_warp_k(const DenseArgs& a0, cudaStream_t st)
+{
+    auto kern = dense_warp_kernel<K, FMT, RW, WARPS>;
+    constexpr int smem = WARPS * 2 * RW * (1 << (2 * K)) * 4 + ((1 << (2 * K)) * 4 < 16 ? 16 : (1 << (2 * K)) * 4);
+    static thread_local int configured_dev = -1;
+    static thread_local int ctas_per_sm = 0, num_sms = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (configured_dev != dev) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, WARPS * 32, smem);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        configured_dev = dev;
+    }
+    DenseArgs a = a0;
+    a.num_tiles = (a.read_end - a.read_begin + RW - 1) / RW;
+    if (a.num_tiles <= 0) return cudaSuccess;
+    const int64_t ctas_needed = (a.num_tiles + WARPS - 1) / WARPS;
+    const int64_t resident = (int64_t)num_sms * ctas_per_sm;
+    const unsigned grid = (unsigned)(ctas_needed < resident ? ctas_needed : resident);
+    kern<<<grid, WARPS * 32, smem, st>>>(a);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -171,6 +296,7 @@ template <int K, int TILE_BYTES>
 struct BigRowSink {
     using G = BigGeo<K, TILE_BYTES>;
     static constexpr bool kCtaUniform = true;
+    static constexpr bool kSharedRows = false;
     uint32_t* rows;   // row of table-local read 0
     int sub;          // which slice of the row this tile covers (SUB > 1)
     bool has_last;
@@ -255,12 +381,6 @@ __global__ void __launch_bounds__(kBigThreads) dense_bigrow_kernel(const DenseAr
     if (threadIdx.x == 0) bulk_wait_all();
 }
 
-static int env_int(const char* name, int dflt)
-{
-    const char* e = getenv(name);
-    return e ? atoi(e) : dflt;
-}
-
 template <int K, int FMT, int TILE_BYTES>
 static cudaError_t launch_bigrow_t(const DenseArgs& a0, cudaStream_t st, int ctas_cap)
 {
@@ -314,12 +434,12 @@ constexpr int kTileBins = 4096;  // 16 KiB tiles
 constexpr int kDenseThreads = 256;
 constexpr int kDenseBufs = 2;
 
-template <int K, int FMT>
+template <int K, int FMT, int TILE_BINS_T = kTileBins, int NTHREADS = kDenseThreads>
 static cudaError_t launch_dense_k(const DenseArgs& a0, cudaStream_t st)
 {
-    using G = Geo<K, kTileBins>;
-    auto kern = dense_count_kernel<K, FMT, kTileBins, kDenseThreads, kDenseBufs>;
-    const int smem = kDenseBufs * G::TILE_BYTES + G::table_bytes();
+    using G = Geo<K, TILE_BINS_T>;
+    auto kern = dense_count_kernel<K, FMT, TILE_BINS_T, NTHREADS, kDenseBufs>;
+    const int smem = kDenseBufs * G::TILE_BYTES + G::table_bytes() + G::ROW_ALIGN;
     static thread_local int configured_dev = -1;
     static thread_local int ctas_per_sm = 0, num_sms = 0;
     int dev = 0;
@@ -328,7 +448,7 @@ static cudaError_t launch_dense_k(const DenseArgs& a0, cudaStream_t st)
     if (configured_dev != dev) {
         e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kDenseThreads, smem);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, NTHREADS, smem);
         if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
@@ -341,7 +461,7 @@ static cudaError_t launch_dense_k(const DenseArgs& a0, cudaStream_t st)
     if (a.num_tiles <= 0) return cudaSuccess;
     const int64_t resident = (int64_t)num_sms * ctas_per_sm;  // persistent: one wave
     const unsigned grid = (unsigned)(a.num_tiles < resident ? a.num_tiles : resident);
-    kern<<<grid, kDenseThreads, smem, st>>>(a);
+    kern<<<grid, NTHREADS, smem, st>>>(a);
     g_launches.fetch_add(1);
     return cudaGetLastError();
 }
@@ -359,6 +479,15 @@ static int big_row_min_k()
 template <int FMT>
 static cudaError_t launch_dense_fmt(int k, const DenseArgs& a, cudaStream_t st)
 {
+    // k <= CFRK_WARP_MAX_K: warp-autonomous tiles; else the CTA-cooperative tile kernel
+    // tuning switches (A/B measurements, profiles/r1_notes.md); the defaults are the measured best
+    static const int k5_variant = env_int("CFRK_K5", 2);   // 0: CTA tiles, 1: warp tiles RW=2, 2: warp tiles RW=1
+    static const int k4_variant = env_int("CFRK_K4", 1);   // 0: CTA 16 KiB/256 thr, 1: 16 KiB/192, 2: 32 KiB/384, 3: warp RW=4
+    if (k == 5 && k5_variant == 1) return launch_warp_k<5, FMT, 2, 4>(a, st);
+    if (k == 5 && k5_variant == 2) return launch_warp_k<5, FMT, 1, 4>(a, st);
+    if (k == 4 && k4_variant == 1) return launch_dense_k<4, FMT, 4096, 192>(a, st);
+    if (k == 4 && k4_variant == 2) return launch_dense_k<4, FMT, 8192, 384>(a, st);
+    if (k == 4 && k4_variant == 3) return launch_warp_k<4, FMT, 4, 4>(a, st);
     switch (k) {
     case 1: return launch_dense_k<1, FMT>(a, st);
     case 2: return launch_dense_k<2, FMT>(a, st);
@@ -366,8 +495,8 @@ static cudaError_t launch_dense_fmt(int k, const DenseArgs& a, cudaStream_t st)
     case 4: return launch_dense_k<4, FMT>(a, st);
     case 5: return launch_dense_k<5, FMT>(a, st);
     case 6: return big_row_min_k() <= 6 ? launch_bigrow_k<6, FMT>(a, st) : launch_dense_k<6, FMT>(a, st);
-    case 7: return big_row_min_k() <= 7 ? launch_bigrow_k<7, FMT>(a, st) : launch_dense_k<7, FMT>(a, st);
-    case 8: return big_row_min_k() <= 8 ? launch_bigrow_k<8, FMT>(a, st) : launch_dense_k<8, FMT>(a, st);
+    case 7: return launch_bigrow_k<7, FMT>(a, st);
+    case 8: return launch_bigrow_k<8, FMT>(a, st);
     default: return cudaErrorInvalidValue;
     }
 }
@@ -402,6 +531,7 @@ cudaError_t launch_dense(const void* bases, int fmt, const int64_t* start, const
 // Whole-dataset histogram: same item loop, sink = one red.global per valid window.
 struct HistSink {
     static constexpr bool kCtaUniform = false;
+    static constexpr bool kSharedRows = false;
     uint32_t* hist;
     __device__ __forceinline__ void kmer(int, uint32_t idx) { atomicAdd(&hist[idx], 1u); }
     __device__ __forceinline__ void invalid(int, int) {}

@@ -163,24 +163,90 @@ template <int N> struct Log2Ceil { static constexpr int value = 1 + Log2Ceil<(N 
 template <> struct Log2Ceil<1> { static constexpr int value = 0; };
 
 // ------------------------------------------------------------------------------------------
-// The item loop.  An item is one 16-byte aligned block of one read's counted byte range.
-// Lanes 1..31 of a warp take 31 consecutive items; lane 0 re-encodes the item before them
-// so that every counting lane gets its k-1 bases of context with one shuffle.
-//
-//   sink.kmer(q, idx)        one valid window of read q (table-local index) with index idx
-//   sink.invalid(q, count)   compat only: `count` visited windows of read q held a non-ACGT
-//                            byte or the terminator
+// One item = one 16-byte aligned block of one read's counted byte range.
+struct Item {
+    uint4 raw;          // the 16 bytes
+    int q;              // table-local read
+    int t0;             // read-relative position of byte 0 of the block (negative in the first block)
+    int tend;           // counted window ends are t < tend
+    int extra;          // compat: invalid windows that reach the terminator (charged to block 0)
+    bool live, first_block;
+};
+
+// Everything that follows the load of an item: encode, context from the previous lane, window
+// validity, emission.  Must be called by all 32 lanes (shuffles).  Lane 0 only feeds lane 1.
+//   sink.kmer(q, idx)        one valid window of read q with index idx
+//   sink.invalid(q, count)   compat only: `count` visited windows of read q held a non-ACGT byte
+//                            or the terminator
+// Reads q >= ncount (the halo read of a compat tile) only report invalid windows.
+template <int K, int FMT, class Sink>
+__device__ __forceinline__ void emit_item(const Item& it, int ncount, int mode, Sink& sink)
+{
+    static_assert(K >= 1 && K <= 16, "one 32-bit funnel shift per window needs k <= 16");
+    constexpr uint32_t IDX_MASK = (K == 16) ? 0xFFFFFFFFu : ((1u << (2 * K)) - 1u);
+    const int lane = threadIdx.x & 31;
+    uint32_t codes = 0, valid = 0, count_mask = 0;
+    if (it.live) {
+        encode16<FMT>(it.raw, codes, valid);
+        const uint32_t upto = ~from_pos(min(16, it.tend - it.t0));
+        valid &= from_pos(max(0, -it.t0)) & upto;                       // bases of this read only
+        count_mask = from_pos(min(16, max(0, K - 1 - it.t0))) & upto;   // window ends that count
+    }
+    const uint32_t pcodes = __shfl_up_sync(0xffffffffu, codes, 1);
+    uint32_t pvalid = __shfl_up_sync(0xffffffffu, valid, 1);
+    if (it.first_block) pvalid = 0;  // no context across a read start
+    const bool counting = it.live && lane != 0;
+    if (!counting) count_mask = 0;
+
+    // bit b of `ok` <- bases b .. b+K-1 (the window ending at position 15-b) are all valid
+    const uint32_t v32 = (pvalid << 16) | valid;
+    uint32_t ok = v32;
+#pragma unroll
+    for (int i = 1; i < K; i++) ok &= v32 >> i;
+    const uint32_t good = it.q < ncount ? (ok & count_mask) : 0u;
+    if (mode == MODE_COMPAT) {
+        const int nbad = __popc(~ok & count_mask) + ((counting && it.first_block) ? it.extra : 0);
+        if (nbad) sink.invalid(it.q, nbad);
+    }
+    if constexpr (Sink::kSharedRows) {
+        // Rows live in shared memory, each aligned to its own size (4^K * 4 bytes): the address of
+        // a bin is row | (index << 2), so a window costs one funnel shift, one LOP3, one predicate
+        // and one predicated red.shared -- straight-line code, no branches.
+        static_assert(2 * K + 2 <= 32, "shared rows are for k <= 8");
+        if (good) {   // (warp-uniformly false only for halo-only chunks)
+            const uint32_t row = sink.row_saddr(it.q);
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int bit = 15 - j;
+                const uint32_t t = bit >= 1 ? __funnelshift_r(codes, pcodes, 2 * bit - 2) : (codes << 2);
+                const uint32_t addr = (t & (IDX_MASK << 2)) | row;
+                asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], 1;\n\t}"
+                             :: "r"(addr), "r"(good & (1u << bit)) : "memory");
+            }
+        }
+    } else {
+        if (good) {
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const int bit = 15 - j;
+                if (good & (1u << bit)) sink.kmer(it.q, __funnelshift_r(codes, pcodes, 2 * bit) & IDX_MASK);
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// CTA-cooperative item loop over a shared-memory ReadTable.  Lanes 1..31 of a warp take 31
+// consecutive items; lane 0 re-encodes the item before them so that every counting lane gets its
+// k-1 bases of context with one shuffle.
 //   sink.before_first_emit() (only if Sink::kCtaUniform) is reached by EVERY thread of the CTA
 //                            exactly once, after the first chunk's loads were issued and before
 //                            anything is emitted (a place for a CTA-wide wait + barrier)
-// Reads q >= ncount (the halo read of a compat tile) only report invalid windows.
 // MAXREADS bounds n (binary search depth).
 template <int K, int FMT, int MAXREADS, class Sink>
 __device__ __forceinline__ void for_each_window(const uint8_t* __restrict__ bases, const ReadTable& tb,
                                                 int n, int ncount, int mode, Sink& sink)
 {
-    static_assert(K >= 1 && K <= 16, "one 32-bit funnel shift per window needs k <= 16");
-    constexpr uint32_t IDX_MASK = (K == 16) ? 0xFFFFFFFFu : ((1u << (2 * K)) - 1u);
     constexpr int STEPS = Log2Ceil<MAXREADS>::value;
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -190,14 +256,14 @@ __device__ __forceinline__ void for_each_window(const uint8_t* __restrict__ base
 
     // kCtaUniform: every warp runs the same number of iterations (idle ones with no live lane)
     const uint32_t niter = (nchunks + nwarps - 1) / nwarps;
-    for (uint32_t it = 0, chunk = warp; Sink::kCtaUniform ? (it < niter) : (chunk < nchunks);
-         ++it, chunk += nwarps) {
+    for (uint32_t iter = 0, chunk = warp; Sink::kCtaUniform ? (iter < niter) : (chunk < nchunks);
+         ++iter, chunk += nwarps) {
         const int64_t item = (int64_t)chunk * 31 + lane - 1;
-        const bool live = chunk < nchunks && item >= 0 && item < (int64_t)total;
-        uint32_t codes = 0, valid = 0, count_mask = 0;
-        int q = 0;
-        bool first_block = true;
-        if (live) {
+        Item it;
+        it.live = chunk < nchunks && item >= 0 && item < (int64_t)total;
+        it.q = 0; it.t0 = 0; it.tend = 0; it.extra = 0; it.first_block = true;
+        it.raw = make_uint4(0u, 0u, 0u, 0u);
+        if (it.live) {
             // largest q with cum[q] <= item  (cum[0] == 0; interval [lo, hi) halves each step)
             int lo = 0, hi = n;
 #pragma unroll
@@ -207,47 +273,91 @@ __device__ __forceinline__ void for_each_window(const uint8_t* __restrict__ base
                 lo = right ? mid : lo;
                 hi = right ? hi : mid;
             }
-            q = lo;
-            const uint32_t c = (uint32_t)item - tb.cum[q];
-            const int64_t s = tb.start[q];
-            const int tend = tb.tend[q];
+            it.q = lo;
+            const uint32_t c = (uint32_t)item - tb.cum[lo];
+            const int64_t s = tb.start[lo];
             const int64_t blk = (s >> 4) + c;
-            const int t0 = (int)(blk * 16 - s);  // read-relative position of byte 0 of the block
-            first_block = (c == 0);
-            encode16<FMT>(ld_block(bases + blk * 16), codes, valid);
-            const int hi_pos = min(16, tend - t0);
-            const uint32_t upto = ~from_pos(hi_pos);
-            valid &= from_pos(max(0, -t0)) & upto;                    // bases of this read only
-            count_mask = from_pos(min(16, max(0, K - 1 - t0))) & upto;  // window ends that count
+            it.tend = tb.tend[lo];
+            it.extra = tb.extra[lo];
+            it.t0 = (int)(blk * 16 - s);
+            it.first_block = (c == 0);
+            it.raw = ld_block(bases + blk * 16);
         }
-        uint32_t pcodes = __shfl_up_sync(0xffffffffu, codes, 1);
-        uint32_t pvalid = __shfl_up_sync(0xffffffffu, valid, 1);
-        if (first_block) pvalid = 0;  // no context across a read start
-        const bool counting = live && lane != 0;  // lane 0 only feeds lane 1
-        if (!counting) count_mask = 0;
+        if constexpr (Sink::kCtaUniform) { if (iter == 0) sink.before_first_emit(); }
+        emit_item<K, FMT>(it, ncount, mode, sink);
+    }
+}
 
-        // bit b of `ok` <- bases b .. b+K-1 (this window) are all valid
-        const uint32_t v32 = (pvalid << 16) | valid;
-        uint32_t ok = v32;
+// ------------------------------------------------------------------------------------------
+// Warp-autonomous item loop: the read table of a small tile (n <= 32 reads, lane q holds read q)
+// lives in registers, lookups are shuffles, the next chunk's blocks are loaded before the current
+// chunk is processed.  No shared-memory table, no CTA barrier.
+struct LaneRead {      // read q = lane q of the warp
+    int64_t start;
+    int tend, extra;
+    uint32_t nblk, cum;  // 16-byte blocks of this read; exclusive prefix over the tile
+};
+
+template <int K>
+__device__ __forceinline__ LaneRead make_lane_read(bool have, int64_t s, int len, int mode, int64_t nN)
+{
+    LaneRead lr;
+    lr.start = s; lr.tend = 0; lr.extra = 0; lr.nblk = 0; lr.cum = 0;
+    if (have) {
+        read_extent<K>(mode, len, nN - s, lr.tend, lr.extra);
+        lr.nblk = lr.tend > 0 ? (uint32_t)(((s + lr.tend - 1) >> 4) - (s >> 4) + 1) : 0u;
+    }
+    uint32_t inc = lr.nblk;
+    const int lane = threadIdx.x & 31;
 #pragma unroll
-        for (int i = 1; i < K; i++) ok &= v32 >> i;
-        const uint32_t good = q < ncount ? (ok & count_mask) : 0u;
-        const uint32_t bad = ~ok & count_mask;
-        if constexpr (Sink::kCtaUniform) { if (it == 0) sink.before_first_emit(); }
-        if (mode == MODE_COMPAT) {
-            int nbad = __popc(bad) + ((counting && first_block) ? tb.extra[q] : 0);
-            if (nbad) sink.invalid(q, nbad);
-        }
-        if (good) {
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    lr.cum = inc - lr.nblk;
+    return lr;
+}
+
+template <int NREADS_MAX>
+__device__ __forceinline__ Item warp_fetch_item(const uint8_t* __restrict__ bases, const LaneRead& lr, int n,
+                                                uint32_t total, uint32_t chunk)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t item = (int64_t)chunk * 31 + lane - 1;
+    Item it;
+    it.live = item >= 0 && item < (int64_t)total;
+    // q = last read whose first item is <= item (reads without items share their successor's cum)
+    int q = 0;
 #pragma unroll
-            for (int j = 0; j < 16; j++) {
-                const int bit = 15 - j;
-                if (good & (1u << bit)) {
-                    uint32_t idx = __funnelshift_r(codes, pcodes, 2 * bit) & IDX_MASK;
-                    sink.kmer(q, idx);
-                }
-            }
-        }
+    for (int j = 1; j < NREADS_MAX; j++) {
+        const uint32_t cj = __shfl_sync(0xffffffffu, lr.cum, j);
+        if (j < n && cj <= (uint32_t)item) q = j;
+    }
+    const uint32_t cq = __shfl_sync(0xffffffffu, lr.cum, q);
+    const int64_t s = __shfl_sync(0xffffffffu, lr.start, q);
+    it.tend = __shfl_sync(0xffffffffu, lr.tend, q);
+    it.extra = __shfl_sync(0xffffffffu, lr.extra, q);
+    const uint32_t c = (uint32_t)item - cq;
+    const int64_t blk = (s >> 4) + c;
+    it.q = q;
+    it.t0 = (int)(blk * 16 - s);
+    it.first_block = (c == 0) || !it.live;
+    it.raw = it.live ? ld_block(bases + blk * 16) : make_uint4(0u, 0u, 0u, 0u);
+    return it;
+}
+
+template <int K, int FMT, int NREADS_MAX, class Sink>
+__device__ __forceinline__ void warp_for_each_window(const uint8_t* __restrict__ bases, const LaneRead& lr,
+                                                     int n, int ncount, int mode, Sink& sink)
+{
+    const uint32_t total = __shfl_sync(0xffffffffu, lr.cum + lr.nblk, 31);
+    const uint32_t nchunks = (total + 30u) / 31u;
+    if (nchunks == 0) return;
+    Item next = warp_fetch_item<NREADS_MAX>(bases, lr, n, total, 0);
+    for (uint32_t chunk = 0; chunk < nchunks; chunk++) {
+        const Item cur = next;
+        if (chunk + 1 < nchunks) next = warp_fetch_item<NREADS_MAX>(bases, lr, n, total, chunk + 1);
+        emit_item<K, FMT>(cur, ncount, mode, sink);
     }
 }
 

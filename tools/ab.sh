@@ -1,11 +1,8 @@
 #!/bin/bash
-run() { echo "== $1 k=$2"; env $1 python bench.py --steps 2 --warmup 1 --no-cpu --no-e2e --k $2 | python -c "
+run() { echo "== $1 k=$2"; env $1 python bench.py --steps 3 --warmup 1 --no-cpu --no-e2e --k $2 | python -c "
 import json,sys
 d=json.loads(sys.stdin.read())
-for x in d['per_k']: print('  ', x['k'], x['ms'], x['frac_of_peak'])"; }
-run "CFRK_BIGROW_MIN_K=5 CFRK_BIG_TILE_KB=64 CFRK_BIG_CTAS=3" 5,6
-run "CFRK_BIGROW_MIN_K=5 CFRK_BIG_TILE_KB=32 CFRK_BIG_CTAS=6" 5,6
-run "CFRK_BIGROW_MIN_K=5 CFRK_BIG_TILE_KB=128 CFRK_BIG_CTAS=2" 5,6
-run "CFRK_BIG_TILE_KB=64 CFRK_BIG_CTAS=3" 7,8
-run "CFRK_BIG_TILE_KB=64 CFRK_BIG_CTAS=3" 7,8
-run "CFRK_BIG_TILE_KB=32 CFRK_BIG_CTAS=5" 7,8
+for x in d['per_k']: print('  ', x['k'], x['ms'], x['gbases_s'], x['frac_of_peak'])"; }
+run "CFRK_K4=0 CFRK_K5=1" 4,5
+run "CFRK_K4=1 CFRK_K5=2" 4,5
+run "CFRK_K4=2 CFRK_K5=0" 4,5
