@@ -153,15 +153,22 @@ def make_reads_device(torch, nS, L, seed, n_frac, fmt, device):
 
 
 def make_reads_host(nS, L, seed, fmt):
+    """One reference chunk in the reference layout.  Read 0 is given length 1 (no visited window):
+    for k > 2 every read has windows that straddle its terminator, the reference adds those of
+    read 0 at Freq[-1] (src/kmer_kernel.cu:84-87), and with a multi-GB Freq that store is an
+    illegal memory access on a B200 (seen in round 1).  Both arms get the same chunk."""
     rng = np.random.default_rng(seed)
     c = rng.integers(0, 4, size=(nS, L + 1), dtype=np.uint8)
     if fmt == "ascii":
         c = np.array([65, 67, 71, 84], dtype=np.uint8)[c]
         c[:, L] = 10
+        c[0, 1] = 10
     else:
         c[:, L] = 0xFF
+        c[0, 1] = 0xFF
     start = np.arange(nS, dtype=np.int64) * (L + 1)
     length = np.full(nS, L, dtype=np.int32)
+    length[0] = 1
     return c.reshape(-1), start, length
 
 
@@ -182,7 +189,7 @@ def cpu_baseline(args, ks, L, budget_s):
             ob.count_dense_fast(data.view(np.int8), start, length, k, mode, nthreads=cores, out=outs[k])
         reps += 1
         dt = time.perf_counter() - t0
-        if dt >= budget_s or reps >= 50:
+        if dt >= budget_s or reps >= 2000:
             break
     bases = reps * len(ks) * nS * L
     return {"value": bases / dt / 1e9, "unit": UNIT, "cores": cores, "kind": "port",
@@ -393,14 +400,23 @@ def run_reference(args):
                 km(C.byref(rd), nN, cn, k, 0)
                 if rd.Freq:
                     lib.ref_free_host(rd.Freq)   # the reference never frees it (src/kmer_main.cu:115)
-        for _ in range(max(1, args.warmup)):
-            sweep()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        for _ in range(steps):
-            sweep()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
+        # the reference reports CUDA errors with printf on stdout (src/kmer_main.cu:59-63): keep
+        # stdout for the one JSON line by pointing fd 1 at stderr while its code runs
+        sys.stdout.flush()
+        saved_fd = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            for _ in range(max(1, args.warmup)):
+                sweep()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                sweep()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+        finally:
+            os.dup2(saved_fd, 1)
+            os.close(saved_fd)
         v = cn * L * len(ks) * steps / dt / 1e9
         line = {"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": 1,
                 "steps": steps, "warmup": args.warmup, "ms_per_step": round(dt / steps * 1e3, 2),

@@ -1,0 +1,124 @@
+"""GPU: the stand-alone stages of the pipeline (2-bit encode, whole-dataset histogram) and the
+device-resident operator with read ranges / chunk openers, against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+import cfrk_b200 as cf
+import fixtures as fx
+import oracle_binding as ob
+
+pytestmark = pytest.mark.gpu
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def padded_bases(raw, fill):
+    t = torch.full((len(raw) + 16,), fill, dtype=torch.uint8, device="cuda")
+    t[: len(raw)] = torch.from_numpy(np.ascontiguousarray(raw).view(np.uint8)).cuda()
+    return t
+
+
+@pytest.mark.parametrize("fmt", ["ascii", "codes"])
+def test_encode_2bit(fmt):
+    text = fx.fx_with_n() + fx.fx_multiline()
+    if fmt == "ascii":
+        raw = np.frombuffer(text.encode(), dtype=np.uint8)
+        want_code = np.array([ob.lib().oracle_encode_base(int(c)) for c in raw], dtype=np.int8)
+        bases = padded_bases(raw, 0)
+        f = cf.FMT_ASCII
+    else:
+        data, _, _ = ob.parse_fasta(text=text)
+        raw, want_code = data.view(np.uint8), data
+        bases = padded_bases(raw, 0xFF)
+        f = cf.FMT_CODES
+    n = len(raw)
+    nb = (n + 15) // 16
+    codes = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    valid = torch.zeros(nb, dtype=torch.int16, device="cuda")
+    cf.encode_2bit_device(bases.data_ptr(), n, codes.data_ptr(), valid.data_ptr(), fmt=f)
+    torch.cuda.synchronize()
+    c = codes.cpu().numpy().view(np.uint32)
+    v = valid.cpu().numpy().view(np.uint16)
+    pos = np.arange(n)
+    got_valid = (v[pos // 16] >> (15 - pos % 16)) & 1
+    got_code = (c[pos // 16] >> (2 * (15 - pos % 16))) & 3
+    np.testing.assert_array_equal(got_valid, (want_code >= 0).astype(np.uint16))
+    np.testing.assert_array_equal(got_code[want_code >= 0], want_code[want_code >= 0].astype(np.uint32))
+    assert (v[-1] & ((1 << (16 * nb - n)) - 1)) == 0   # nothing valid past the end of the buffer
+
+
+@pytest.mark.parametrize("k", [1, 2, 4, 6, 8, 10, 12, 13])
+def test_global_hist(k):
+    data, start, length = ob.parse_fasta(text=fx.fx_with_n() + fx.fx_ragged() + fx.fx_long())
+    want = ob.global_hist(data, start, length, k)
+    hist = torch.zeros(4 ** k, dtype=torch.int32, device="cuda")
+    b = padded_bases(data, 0xFF)
+    s, l = dev(start), dev(length)
+    cf.global_hist_device(b.data_ptr(), s.data_ptr(), l.data_ptr(), len(data), len(start), k, hist.data_ptr())
+    cf.global_hist_device(b.data_ptr(), s.data_ptr(), l.data_ptr(), len(data), len(start), k, hist.data_ptr())
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(hist.cpu().numpy().astype(np.uint64), 2 * want)   # accumulates
+
+
+@pytest.mark.parametrize("k", [2, 4, 5, 6, 8])
+def test_device_read_ranges_and_chunk_openers(k):
+    """one launch over many reference chunks == one kmer_main call per chunk (src/main.cu:222,294,300);
+    read ranges (multi-GPU shards, row rings) stitch together exactly"""
+    nS = 3000 if k <= 6 else 600
+    data, start, length = fx.synthetic_codes(nS, 97, seed=7 + k, n_frac=0.01)
+    chunk = 256
+    want = np.concatenate([
+        ob.count_dense(data[start[a]:], start[a:a + chunk] - start[a], length[a:a + chunk], k)
+        for a in range(0, nS, chunk)])
+    b, s, l = padded_bases(data, 0xFF), dev(start), dev(length)
+    out = torch.full((nS, 4 ** k), -1, dtype=torch.int32, device="cuda")
+    rpt = cf.dense_reads_per_tile(k)
+    cuts = [0, 512, 512 + 5 * rpt * 7, nS]
+    for a, e in zip(cuts, cuts[1:]):
+        cf.count_dense_device(b.data_ptr(), s.data_ptr(), l.data_ptr(), len(data), nS, k,
+                              out[a:].data_ptr(), read_begin=a, read_end=e, chunk_size=chunk)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy(), want)
+    # first_read_index shifts the chunk phase
+    want2 = np.concatenate([
+        ob.count_dense(data[start[a]:], start[a:e] - start[a], length[a:e], k)
+        for a, e in [(0, 56)] + [(x, min(nS, x + chunk)) for x in range(56, nS, chunk)]])
+    cf.count_dense_device(b.data_ptr(), s.data_ptr(), l.data_ptr(), len(data), nS, k, out.data_ptr(),
+                          chunk_size=chunk, first_read_index=200)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(out.cpu().numpy(), want2)
+
+
+def test_full_size_properties():
+    """BASELINE size (10 M x 150 bp is bench.py's job); here 2 M reads: conservation laws that do not
+    need the oracle: row sums, and a checksum against the CPU counter on a strided sample"""
+    nS, L, k = 2_000_000, 150, 4
+    g = torch.Generator(device="cuda"); g.manual_seed(5)
+    codes = torch.randint(0, 4, (nS, L + 1), dtype=torch.uint8, device="cuda", generator=g)
+    codes[:, L] = 0xFF
+    flat = torch.cat([codes.view(-1), torch.full((16,), 0xFF, dtype=torch.uint8, device="cuda")])
+    start = torch.arange(nS, dtype=torch.int64, device="cuda") * (L + 1)
+    length = torch.full((nS,), L, dtype=torch.int32, device="cuda")
+    out = torch.empty((nS, 4 ** k), dtype=torch.int32, device="cuda")
+    cf.count_dense_device(flat.data_ptr(), start.data_ptr(), length.data_ptr(), nS * (L + 1), nS, k, out.data_ptr())
+    torch.cuda.synchronize()
+    sums = out.sum(1)
+    # compat: L-k+1 valid windows + (k-2) spilled in from the next read (none for the last read)
+    assert int(sums[:-1].min()) == int(sums[:-1].max()) == (L - k + 1) + (k - 2)
+    assert int(sums[-1]) == L - k + 1
+    sel = np.arange(0, nS, 9973)
+    h = codes.cpu().numpy().view(np.int8)
+    for i in sel[:50]:
+        hi = min(nS, i + 2)
+        want = ob.count_dense(h[i:hi].reshape(-1), np.arange(hi - i) * (L + 1), np.full(hi - i, L), k)[0]
+        np.testing.assert_array_equal(out[i].cpu().numpy(), want)
+    # exact mode: global histogram == column sums of the rows
+    cf.count_dense_device(flat.data_ptr(), start.data_ptr(), length.data_ptr(), nS * (L + 1), nS, k, out.data_ptr(),
+                          mode=cf.MODE_EXACT)
+    hist = torch.zeros(4 ** k, dtype=torch.int32, device="cuda")
+    cf.global_hist_device(flat.data_ptr(), start.data_ptr(), length.data_ptr(), nS * (L + 1), nS, k, hist.data_ptr())
+    torch.cuda.synchronize()
+    assert torch.equal(out.sum(0, dtype=torch.int64), hist.to(torch.int64))
