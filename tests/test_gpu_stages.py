@@ -26,7 +26,10 @@ def test_encode_2bit(fmt):
     text = fx.fx_with_n() + fx.fx_multiline()
     if fmt == "ascii":
         raw = np.frombuffer(text.encode(), dtype=np.uint8)
-        want_code = np.array([ob.lib().oracle_encode_base(int(c)) for c in raw], dtype=np.int8)
+        lut = np.full(256, -1, dtype=np.int8)          # src/fastaIO.h:123-139
+        for ch, v in zip("ACGTacgt", [0, 1, 2, 3] * 2):
+            lut[ord(ch)] = v
+        want_code = lut[raw]
         bases = padded_bases(raw, 0)
         f = cf.FMT_ASCII
     else:
@@ -76,7 +79,7 @@ def test_device_read_ranges_and_chunk_openers(k):
     b, s, l = padded_bases(data, 0xFF), dev(start), dev(length)
     out = torch.full((nS, 4 ** k), -1, dtype=torch.int32, device="cuda")
     rpt = cf.dense_reads_per_tile(k)
-    cuts = [0, 512, 512 + 5 * rpt * 7, nS]
+    cuts = [0, 2 * rpt, 5 * rpt, nS]
     for a, e in zip(cuts, cuts[1:]):
         cf.count_dense_device(b.data_ptr(), s.data_ptr(), l.data_ptr(), len(data), nS, k,
                               out[a:].data_ptr(), read_begin=a, read_end=e, chunk_size=chunk)
