@@ -437,9 +437,36 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+class QuietStdout:
+    """Everything but the final JSON line goes to stderr: NCCL prints its version banner on stdout,
+    the reference prints its errors there."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
 if __name__ == "__main__":
     a = parse_args()
-    if a.impl == "reference":
-        run_reference(a)
-    else:
-        run_ours(a)
+    out_fd = os.dup(1)
+    with QuietStdout():
+        real_print = print
+
+        def emit(*args, **kw):          # the one JSON line goes to the real stdout
+            os.write(out_fd, (" ".join(str(x) for x in args) + "\n").encode())
+        import builtins
+        builtins.print = emit
+        try:
+            if a.impl == "reference":
+                run_reference(a)
+            else:
+                run_ours(a)
+        finally:
+            builtins.print = real_print
