@@ -46,6 +46,7 @@ struct DenseSink {
     using G = Geo<K, TILE_BINS_T>;
     static constexpr bool kCtaUniform = false;
     static constexpr bool kSharedRows = true;
+    static constexpr bool kRowsAligned = true;
     uint32_t hist_saddr;  // shared-window address of the tile buffer (aligned to the row size)
     int qb, period;       // table-local reads qb, qb+period, ... open a reference chunk (period 0: none)
     __device__ __forceinline__ uint32_t row_saddr(int q) const { return hist_saddr + (uint32_t)q * (G::BINS * 4); }
@@ -157,6 +158,7 @@ template <int K>
 struct WarpSink {
     static constexpr bool kCtaUniform = false;
     static constexpr bool kSharedRows = true;
+    static constexpr bool kRowsAligned = true;
     static constexpr int BINS = 1 << (2 * K);
     uint32_t hist_saddr;
     int qb, period;
@@ -169,22 +171,34 @@ struct WarpSink {
     }
 };
 
-template <int K, int FMT, int RW, int WARPS>
+// DIRECT = false: two buffers per warp, rows leave through the warp's own TMA bulk stores.
+// DIRECT = true : one buffer per warp; the warp reads its finished rows out of shared memory,
+//                 clears them in the same pass and writes them with coalesced 16-byte streaming
+//                 stores.  Half the shared memory per warp -> twice the resident warps, and no wait
+//                 for the TMA engine before the buffer can be reused.
+template <int K, int FMT, int RW, int WARPS, bool DIRECT>
 __global__ void __launch_bounds__(WARPS * 32) dense_warp_kernel(const DenseArgs a)
 {
     constexpr int BINS = 1 << (2 * K);
     constexpr int TILE_BINS = RW * BINS;
     constexpr int TILE_BYTES = TILE_BINS * 4;
+    constexpr int NBUF = DIRECT ? 1 : 2;
     static_assert(RW + 1 <= 32, "one lane per read of the tile (+ halo)");
     constexpr int ROW_ALIGN = BINS * 4 < 16 ? 16 : BINS * 4;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const uint32_t raw_saddr = (uint32_t)__cvta_generic_to_shared(smem_raw);
     unsigned char* smem = smem_raw + ((ROW_ALIGN - (raw_saddr & (ROW_ALIGN - 1))) & (ROW_ALIGN - 1));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t* bufs = reinterpret_cast<uint32_t*>(smem) + (size_t)warp * 2 * TILE_BINS;
+    uint32_t* bufs = reinterpret_cast<uint32_t*>(smem) + (size_t)warp * NBUF * TILE_BINS;
     const int64_t nwarps = (int64_t)gridDim.x * WARPS;
     int64_t tile = (int64_t)blockIdx.x * WARPS + warp;
     if (tile >= a.num_tiles) return;
+    if (DIRECT) {
+        uint4* h4 = reinterpret_cast<uint4*>(bufs);
+#pragma unroll
+        for (int i = lane; i < TILE_BYTES / 16; i += 32) h4[i] = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+    }
 
     // offsets of the first tile; afterwards always one tile ahead
     int64_t s = 0; int len = 0;
@@ -217,31 +231,46 @@ __global__ void __launch_bounds__(WARPS * 32) dense_warp_kernel(const DenseArgs 
             if (lane <= RW && r < a.nS) { s = a.start[r]; len = a.length[r]; }
         }
 
-        uint32_t* hist = bufs + (size_t)(it & 1) * TILE_BINS;
-        if (lane == 0) bulk_wait_read<1>();  // the store issued two tiles ago has read this buffer
-        __syncwarp();
-        {
+        uint32_t* hist = bufs + (DIRECT ? 0 : (size_t)(it & 1) * TILE_BINS);
+        if (!DIRECT) {
+            if (lane == 0) bulk_wait_read<1>();  // the store issued two tiles ago has read this buffer
+            __syncwarp();
             uint4* h4 = reinterpret_cast<uint4*>(hist);
-            const uint4 z = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
-            for (int i = lane; i < TILE_BYTES / 16; i += 32) h4[i] = z;
+            for (int i = lane; i < TILE_BYTES / 16; i += 32) h4[i] = make_uint4(0u, 0u, 0u, 0u);
+            __syncwarp();
         }
-        __syncwarp();
         WarpSink<K> sink{(uint32_t)__cvta_generic_to_shared(hist), qb, period};
         warp_for_each_window<K, FMT, RW + 1>(a.bases, lr, nreads, nrows, a.mode, sink);
-        fence_async_proxy_shared();
-        __syncwarp();
-        if (lane == 0) bulk_store_tile(a.out + (r0 - a.read_begin) * BINS, hist, (uint32_t)nrows * BINS * 4u);
+        uint32_t* dst = a.out + (r0 - a.read_begin) * BINS;
+        if (DIRECT) {
+            __syncwarp();
+            uint4* h4 = reinterpret_cast<uint4*>(hist);
+            uint4* d4 = reinterpret_cast<uint4*>(dst);
+            const int n16 = nrows * (BINS / 4);
+#pragma unroll 4
+            for (int i = lane; i < n16; i += 32) {
+                const uint4 v = h4[i];
+                h4[i] = make_uint4(0u, 0u, 0u, 0u);
+                asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};"
+                             :: "l"(d4 + i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+            }
+            __syncwarp();
+        } else {
+            fence_async_proxy_shared();
+            __syncwarp();
+            if (lane == 0) bulk_store_tile(dst, hist, (uint32_t)nrows * BINS * 4u);
+        }
         tile = next_tile;
     }
-    if (lane == 0) bulk_wait_all();
+    if (!DIRECT && lane == 0) bulk_wait_all();
 }
 
-template <int K, int FMT, int RW, int WARPS>
+template <int K, int FMT, int RW, int WARPS, bool DIRECT = false>
 static cudaError_t launch_warp_k(const DenseArgs& a0, cudaStream_t st)
 {
-    auto kern = dense_warp_kernel<K, FMT, RW, WARPS>;
-    constexpr int smem = WARPS * 2 * RW * (1 << (2 * K)) * 4 + ((1 << (2 * K)) * 4 < 16 ? 16 : (1 << (2 * K)) * 4);
+    auto kern = dense_warp_kernel<K, FMT, RW, WARPS, DIRECT>;
+    constexpr int smem = WARPS * (DIRECT ? 1 : 2) * RW * (1 << (2 * K)) * 4 + ((1 << (2 * K)) * 4 < 16 ? 16 : (1 << (2 * K)) * 4);
     static thread_local int configured_dev = -1;
     static thread_local int ctas_per_sm = 0, num_sms = 0;
     int dev = 0;
@@ -466,35 +495,49 @@ static cudaError_t launch_dense_k(const DenseArgs& a0, cudaStream_t st)
     return cudaGetLastError();
 }
 
-// k >= this uses dense_bigrow_kernel; CFRK_BIGROW_MIN_K overrides (tuning / A-B measurements)
-static int big_row_min_k()
-{
-    static const int v = [] {
-        const char* e = getenv("CFRK_BIGROW_MIN_K");
-        return e ? atoi(e) : 6;
-    }();
-    return v;
-}
-
 template <int FMT>
 static cudaError_t launch_dense_fmt(int k, const DenseArgs& a, cudaStream_t st)
 {
     // k <= CFRK_WARP_MAX_K: warp-autonomous tiles; else the CTA-cooperative tile kernel
     // tuning switches (A/B measurements, profiles/r1_notes.md); the defaults are the measured best
-    static const int k5_variant = env_int("CFRK_K5", 2);   // 0: CTA tiles, 1: warp tiles RW=2, 2: warp tiles RW=1
-    static const int k4_variant = env_int("CFRK_K4", 1);   // 0: CTA 16 KiB/256 thr, 1: 16 KiB/192, 2: 32 KiB/384, 3: warp RW=4
+    static const int k5_variant = env_int("CFRK_K5", 3);   // 0: CTA tiles, 1: warp tiles RW=2, 2: warp tiles RW=1
+    static const int k4_variant = env_int("CFRK_K4", 5);
+    static const int k123_variant = env_int("CFRK_K123", 0);  // 0: CTA tiles, 1: warp tiles (direct) RW=16, 2: RW=31
+    if (k <= 3 && k123_variant == 1) {
+        if (k == 1) return launch_warp_k<1, FMT, 16, 4, true>(a, st);
+        if (k == 2) return launch_warp_k<2, FMT, 16, 4, true>(a, st);
+        return launch_warp_k<3, FMT, 16, 4, true>(a, st);
+    }
+    if (k <= 3 && k123_variant == 2) {
+        if (k == 1) return launch_warp_k<1, FMT, 31, 4, true>(a, st);
+        if (k == 2) return launch_warp_k<2, FMT, 31, 4, true>(a, st);
+        return launch_warp_k<3, FMT, 31, 4, true>(a, st);
+    }
+    if (k == 4 && k4_variant == 6) return launch_warp_k<4, FMT, 16, 4, true>(a, st);
+    if (k == 4 && k4_variant == 7) return launch_warp_k<4, FMT, 8, 8, true>(a, st);
+    if (k == 5 && k5_variant == 5) return launch_warp_k<5, FMT, 1, 8, true>(a, st);   // 0: CTA 16 KiB/256 thr, 1: 16 KiB/192, 2: 32 KiB/384, 3: warp RW=4
     if (k == 5 && k5_variant == 1) return launch_warp_k<5, FMT, 2, 4>(a, st);
     if (k == 5 && k5_variant == 2) return launch_warp_k<5, FMT, 1, 4>(a, st);
     if (k == 4 && k4_variant == 1) return launch_dense_k<4, FMT, 4096, 192>(a, st);
     if (k == 4 && k4_variant == 2) return launch_dense_k<4, FMT, 8192, 384>(a, st);
     if (k == 4 && k4_variant == 3) return launch_warp_k<4, FMT, 4, 4>(a, st);
+    if (k == 4 && k4_variant == 4) return launch_warp_k<4, FMT, 4, 4, true>(a, st);
+    if (k == 4 && k4_variant == 5) return launch_warp_k<4, FMT, 8, 4, true>(a, st);
+    if (k == 5 && k5_variant == 3) return launch_warp_k<5, FMT, 1, 4, true>(a, st);
+    if (k == 5 && k5_variant == 4) return launch_warp_k<5, FMT, 2, 4, true>(a, st);
     switch (k) {
     case 1: return launch_dense_k<1, FMT>(a, st);
     case 2: return launch_dense_k<2, FMT>(a, st);
     case 3: return launch_dense_k<3, FMT>(a, st);
     case 4: return launch_dense_k<4, FMT>(a, st);
     case 5: return launch_dense_k<5, FMT>(a, st);
-    case 6: return big_row_min_k() <= 6 ? launch_bigrow_k<6, FMT>(a, st) : launch_dense_k<6, FMT>(a, st);
+    case 6: {
+        static const int k6_variant = env_int("CFRK_K6", 2);  // 0: big-row path, 1/2: warp tiles (direct), 3: CTA tiles
+        if (k6_variant == 1) return launch_warp_k<6, FMT, 1, 4, true>(a, st);
+        if (k6_variant == 2) return launch_warp_k<6, FMT, 1, 6, true>(a, st);
+        if (k6_variant == 3) return launch_dense_k<6, FMT>(a, st);
+        return launch_bigrow_k<6, FMT>(a, st);
+    }
     case 7: return launch_bigrow_k<7, FMT>(a, st);
     case 8: return launch_bigrow_k<8, FMT>(a, st);
     default: return cudaErrorInvalidValue;
@@ -528,7 +571,10 @@ cudaError_t launch_dense(const void* bases, int fmt, const int64_t* start, const
 }
 
 // ------------------------------------------------------------------------------------------
-// Whole-dataset histogram: same item loop, sink = one red.global per valid window.
+// Whole-dataset histogram: same item loop.  k <= 7: the CTA counts into a private shared-memory
+// histogram (red.shared) and adds it to the global one once at the end -- with 4^k <= 16384 bins a
+// direct red.global per window serialises in L2 (measured 4.4 Gbases/s at k=4).  k >= 8: one
+// red.global per valid window into the L2-resident histogram (186 G reductions/s at k=12).
 struct HistSink {
     static constexpr bool kCtaUniform = false;
     static constexpr bool kSharedRows = false;
@@ -536,9 +582,18 @@ struct HistSink {
     __device__ __forceinline__ void kmer(int, uint32_t idx) { atomicAdd(&hist[idx], 1u); }
     __device__ __forceinline__ void invalid(int, int) {}
 };
+struct HistSinkShared {
+    static constexpr bool kCtaUniform = false;
+    static constexpr bool kSharedRows = true;
+    static constexpr bool kRowsAligned = false;
+    uint32_t saddr;
+    __device__ __forceinline__ uint32_t row_saddr(int) const { return saddr; }
+    __device__ __forceinline__ void invalid(int, int) {}
+};
 
 constexpr int kHistGroup = 128;  // reads per work group
 constexpr int kHistThreads = 256;
+constexpr int kHistSharedMaxK = 7;
 
 template <int K, int FMT>
 __global__ void __launch_bounds__(kHistThreads) global_hist_kernel(const uint8_t* __restrict__ bases,
@@ -546,21 +601,36 @@ __global__ void __launch_bounds__(kHistThreads) global_hist_kernel(const uint8_t
                                                                  const int32_t* __restrict__ length,
                                                                  int64_t nS, uint32_t* hist)
 {
+    constexpr bool SHARED = K <= kHistSharedMaxK;
+    constexpr int BINS = 1 << (2 * K);
     __shared__ int64_t s_start[kHistGroup];
     __shared__ int32_t s_tend[kHistGroup], s_extra[kHistGroup];
     __shared__ uint32_t s_cum[kHistGroup + 1];
+    extern __shared__ __align__(16) uint32_t s_hist[];
     ReadTable tb{s_start, s_tend, s_extra, s_cum};
-    HistSink sink{hist};
+    if (SHARED) {
+        for (int i = threadIdx.x; i < BINS; i += kHistThreads) s_hist[i] = 0u;
+    }
+    HistSink gsink{hist};
+    HistSinkShared ssink{(uint32_t)__cvta_generic_to_shared(s_hist)};
     const int64_t groups = (nS + kHistGroup - 1) / kHistGroup;
     for (int64_t g = blockIdx.x; g < groups; g += gridDim.x) {
         const int64_t r0 = g * kHistGroup;
         const int n = (int)min((int64_t)kHistGroup, nS - r0);
-        __syncthreads();  // previous group's item loop is done with the table
+        __syncthreads();  // previous group's item loop is done with the table (and s_hist is zeroed)
         fill_read_table<K>(tb, start, length, r0, n, MODE_EXACT, INT64_MAX);
         __syncthreads();
         if (threadIdx.x < 32) scan_read_table(tb, n);
         __syncthreads();
-        for_each_window<K, FMT, kHistGroup>(bases, tb, n, n, MODE_EXACT, sink);
+        if constexpr (SHARED) for_each_window<K, FMT, kHistGroup>(bases, tb, n, n, MODE_EXACT, ssink);
+        else for_each_window<K, FMT, kHistGroup>(bases, tb, n, n, MODE_EXACT, gsink);
+    }
+    if (SHARED) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < BINS; i += kHistThreads) {
+            const uint32_t v = s_hist[i];
+            if (v) atomicAdd(&hist[i], v);
+        }
     }
 }
 
@@ -574,13 +644,18 @@ static cudaError_t launch_hist_k(const void* bases, const int64_t* start, const 
     if (e != cudaSuccess) return e;
     e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kHistThreads, 0);
+    const int smem = K <= kHistSharedMaxK ? (1 << (2 * K)) * 4 : 0;
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+    }
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kHistThreads, smem);
     if (e != cudaSuccess) return e;
     const int64_t groups = (nS + kHistGroup - 1) / kHistGroup;
     if (groups <= 0) return cudaSuccess;
     const int64_t resident = (int64_t)num_sms * (per_sm < 1 ? 1 : per_sm);
     const unsigned grid = (unsigned)(groups < resident ? groups : resident);
-    kern<<<grid, kHistThreads, 0, st>>>(static_cast<const uint8_t*>(bases), start, length, nS, hist);
+    kern<<<grid, kHistThreads, smem, st>>>(static_cast<const uint8_t*>(bases), start, length, nS, hist);
     g_launches.fetch_add(1);
     return cudaGetLastError();
 }

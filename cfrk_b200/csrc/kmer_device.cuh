@@ -209,9 +209,10 @@ __device__ __forceinline__ void emit_item(const Item& it, int ncount, int mode, 
         if (nbad) sink.invalid(it.q, nbad);
     }
     if constexpr (Sink::kSharedRows) {
-        // Rows live in shared memory, each aligned to its own size (4^K * 4 bytes): the address of
-        // a bin is row | (index << 2), so a window costs one funnel shift, one LOP3, one predicate
-        // and one predicated red.shared -- straight-line code, no branches.
+        // Rows live in shared memory; when each is aligned to its own size (4^K * 4 bytes,
+        // Sink::kRowsAligned) the address of a bin is row | (index << 2), so a window costs one
+        // funnel shift, one LOP3, one predicate and one predicated red.shared -- straight-line
+        // code, no branches.
         static_assert(2 * K + 2 <= 32, "shared rows are for k <= 8");
         if (good) {   // (warp-uniformly false only for halo-only chunks)
             const uint32_t row = sink.row_saddr(it.q);
@@ -219,7 +220,7 @@ __device__ __forceinline__ void emit_item(const Item& it, int ncount, int mode, 
             for (int j = 0; j < 16; j++) {
                 const int bit = 15 - j;
                 const uint32_t t = bit >= 1 ? __funnelshift_r(codes, pcodes, 2 * bit - 2) : (codes << 2);
-                const uint32_t addr = (t & (IDX_MASK << 2)) | row;
+                const uint32_t addr = Sink::kRowsAligned ? ((t & (IDX_MASK << 2)) | row) : ((t & (IDX_MASK << 2)) + row);
                 asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, 0;\n\t@p red.shared.add.u32 [%0], 1;\n\t}"
                              :: "r"(addr), "r"(good & (1u << bit)) : "memory");
             }
