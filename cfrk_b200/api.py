@@ -93,6 +93,16 @@ def global_hist_device(d_bases, d_start, d_length, nN, nS, k, d_hist, fmt=FMT_CO
            "cfrk_global_hist_device")
 
 
+def count_sparse_device(d_bases, d_start, d_length, nN, nS, k, d_row_begin, d_row_count, d_keys, d_counts,
+                        capacity, key_bytes=8, fmt=FMT_CODES, stream=0):
+    """Sparse per-read rows (exact semantics); returns the total number of windows."""
+    total = C.c_int64(0)
+    _check(lib().cfrk_count_sparse_device(d_bases, fmt, d_start, d_length, nN, nS, k, key_bytes, d_row_begin,
+                                          d_row_count, d_keys, d_counts, capacity, C.byref(total), stream),
+           "cfrk_count_sparse_device")
+    return total.value
+
+
 def run_file(fasta, out, k, nt=12, chunk_size=8192, flags=0, device=0):
     """cfrk <fasta> <out> <k> [nt] [chunkSize] (reference src/main.cu:232-305)."""
     _check(lib().cfrk_run_file(os.fsencode(fasta), os.fsencode(out), k, nt, chunk_size, flags, device),

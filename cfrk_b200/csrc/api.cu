@@ -238,6 +238,28 @@ int cfrk_encode_2bit_device(const void* d_bases, int fmt, int64_t n, uint32_t* d
     return CFRK_OK;
 }
 
+int cfrk_count_sparse_device(const void* d_bases, int fmt, const int64_t* d_start, const int32_t* d_length,
+                             int64_t nN, int64_t nS, int k, int key_bytes, int64_t* d_row_begin, int32_t* d_row_count,
+                             void* d_keys, uint32_t* d_counts, int64_t capacity, int64_t* total_windows, void* stream)
+{
+    int rc = check_common(fmt, k, CFRK_SPARSE_MAX_K, CFRK_MODE_EXACT);
+    if (rc) return rc;
+    if (key_bytes != 4 && key_bytes != 8) return fail(CFRK_EINVAL, "key_bytes must be 4 or 8");
+    if (key_bytes == 4 && k > 16) return fail(CFRK_EINVAL, "uint32 keys hold k <= 16");
+    if (nS < 0 || nN < 0 || capacity < 0) return fail(CFRK_EINVAL, "negative size");
+    if (!d_row_begin) return fail(CFRK_EINVAL, "null device pointer");
+    if (total_windows) *total_windows = 0;
+    if (nS == 0) return CFRK_OK;
+    if (!d_bases || !d_start || !d_length || !d_row_count || !d_keys || !d_counts)
+        return fail(CFRK_EINVAL, "null device pointer");
+    if (reinterpret_cast<uintptr_t>(d_bases) & 15) return fail(CFRK_EINVAL, "d_bases must be 16-byte aligned");
+    cudaError_t e = cfrk::launch_sparse(d_bases, fmt, d_start, d_length, nS, k, d_row_begin, d_row_count, d_keys,
+                                        key_bytes, d_counts, capacity, total_windows, static_cast<cudaStream_t>(stream));
+    if (e == cudaErrorInvalidValue) return fail(CFRK_EINVAL, "capacity smaller than the number of windows");
+    if (e != cudaSuccess) return fail_cuda(e, "sparse path");
+    return CFRK_OK;
+}
+
 int cfrk_global_hist_device(const void* d_bases, int fmt, const int64_t* d_start, const int32_t* d_length,
                             int64_t nN, int64_t nS, int k, uint32_t* d_hist, void* stream)
 {

@@ -16,6 +16,7 @@ namespace cfrk {
 
 static std::atomic<uint64_t> g_launches{0};
 uint64_t launch_count() { return g_launches.load(); }
+void count_launch() { g_launches.fetch_add(1); }
 
 static int env_int(const char* name, int dflt)
 {

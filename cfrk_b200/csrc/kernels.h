@@ -22,6 +22,12 @@ cudaError_t launch_global_hist(const void* bases, int fmt, const int64_t* start,
 cudaError_t launch_encode_2bit(const void* bases, int fmt, int64_t n, uint32_t* codes, uint16_t* valid,
                                cudaStream_t st);
 
+// Sparse per-read rows (exact semantics), k in 1..31; key_bytes 4 (k <= 16) or 8.  Synchronises
+// `st` internally (needs the total window count on the host).  cudaErrorInvalidValue = capacity.
+cudaError_t launch_sparse(const void* bases, int fmt, const int64_t* start, const int32_t* length, int64_t nS, int k,
+                          int64_t* row_begin, int32_t* row_count, void* keys, int key_bytes, uint32_t* counts,
+                          int64_t capacity, int64_t* total_windows, cudaStream_t st);
+
 uint64_t launch_count();
 
 }  // namespace cfrk

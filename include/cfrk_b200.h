@@ -49,6 +49,7 @@ extern "C" {
 
 #define CFRK_DENSE_MAX_K 8   /* shared-memory tile path (4^k int32 per read)            */
 #define CFRK_HIST_MAX_K  15  /* whole-dataset histogram, 4^k uint32 in HBM              */
+#define CFRK_SPARSE_MAX_K 31 /* sparse per-read rows, uint64 keys                       */
 #define CFRK_PAD         16  /* device bases buffers must be readable up to the next
                                 16-byte boundary and 16-byte aligned                    */
 
@@ -112,6 +113,24 @@ int cfrk_encode_2bit_device(const void *d_bases, int fmt, int64_t n, uint32_t *d
 int cfrk_global_hist_device(const void *d_bases, int fmt, const int64_t *d_start,
                             const int32_t *d_length, int64_t nN, int64_t nS, int k,
                             uint32_t *d_hist, void *stream);
+
+/*
+ * Sparse per-read counts, exact semantics, k = 1..31 (BASELINE configs 3 and 4; no reference
+ * counterpart: its dense rows end at k = 8 with the default chunk).
+ * Row r = the sorted distinct k-mers of read r and their multiplicities, stored at
+ *   d_keys/d_counts[d_row_begin[r] .. d_row_begin[r] + d_row_count[r])
+ * with d_row_begin[r] = sum_{j<r} max(0, length[j]-k+1) computed by the call (nS+1 entries; the
+ * last one is the total number of windows, also returned in *total_windows).  capacity = number
+ * of pairs d_keys/d_counts can hold; CFRK_EINVAL if the total exceeds it.  key_bytes = 4
+ * (uint32 keys, k <= 16) or 8 (uint64 keys).  Key = sum code_i * 4^(k-1-i), like the dense bin.
+ * Synchronises the stream (it needs the total on the host) and allocates scratch with
+ * cudaMallocAsync.
+ */
+int cfrk_count_sparse_device(const void *d_bases, int fmt, const int64_t *d_start,
+                             const int32_t *d_length, int64_t nN, int64_t nS, int k, int key_bytes,
+                             int64_t *d_row_begin, int32_t *d_row_count, void *d_keys,
+                             uint32_t *d_counts, int64_t capacity, int64_t *total_windows,
+                             void *stream);
 
 /* ---- file level: replaces main() of src/main.cu:232-305 ----------------------------- */
 

@@ -1,0 +1,99 @@
+"""GPU: sparse per-read rows (k up to 31) against the oracle's sort-based restatement."""
+import numpy as np
+import pytest
+import torch
+
+import cfrk_b200 as cf
+import fixtures as fx
+import oracle_binding as ob
+
+pytestmark = pytest.mark.gpu
+
+
+def run_sparse(data, start, length, k, key_bytes, fmt):
+    nS = len(start)
+    fill = 0xFF if fmt == cf.FMT_CODES else 0
+    b = torch.full((len(data) + 16,), fill, dtype=torch.uint8, device="cuda")
+    b[: len(data)] = torch.from_numpy(np.ascontiguousarray(data).view(np.uint8).copy()).cuda()
+    s = torch.from_numpy(np.ascontiguousarray(start, dtype=np.int64)).cuda()
+    l = torch.from_numpy(np.ascontiguousarray(length, dtype=np.int32)).cuda()
+    cap = int(np.maximum(np.asarray(length, dtype=np.int64) - k + 1, 0).sum()) + 8
+    rb = torch.zeros(nS + 1, dtype=torch.int64, device="cuda")
+    rc = torch.full((nS,), -7, dtype=torch.int32, device="cuda")
+    keys = torch.zeros(cap, dtype=torch.int32 if key_bytes == 4 else torch.int64, device="cuda")
+    cnt = torch.zeros(cap, dtype=torch.int32, device="cuda")
+    total = cf.count_sparse_device(b.data_ptr(), s.data_ptr(), l.data_ptr(), len(data), nS, k, rb.data_ptr(),
+                                   rc.data_ptr(), keys.data_ptr(), cnt.data_ptr(), cap, key_bytes=key_bytes, fmt=fmt)
+    torch.cuda.synchronize()
+    assert total == cap - 8
+    kdt = np.uint32 if key_bytes == 4 else np.uint64
+    return rb.cpu().numpy(), rc.cpu().numpy(), keys.cpu().numpy().view(kdt), cnt.cpu().numpy().view(np.uint32)
+
+
+def check(data, start, length, k, key_bytes, fmt=cf.FMT_CODES, odata=None):
+    rb, rc, keys, cnt = run_sparse(data, start, length, k, key_bytes, fmt)
+    orp, okeys, ocnt = ob.count_sparse(data if odata is None else odata, start, length, k, ascii=False)
+    nwin = np.maximum(np.asarray(length, dtype=np.int64) - k + 1, 0)
+    np.testing.assert_array_equal(rb, np.concatenate([[0], np.cumsum(nwin)]))
+    np.testing.assert_array_equal(rc, np.diff(orp))
+    for i in range(len(start)):
+        a, n = rb[i], rc[i]
+        np.testing.assert_array_equal(keys[a:a + n].astype(np.uint64), okeys[orp[i]:orp[i + 1]], err_msg=f"row {i}")
+        np.testing.assert_array_equal(cnt[a:a + n], ocnt[orp[i]:orp[i + 1]], err_msg=f"row {i}")
+
+
+@pytest.mark.parametrize("k,key_bytes", [(3, 4), (9, 4), (12, 4), (16, 4), (12, 8), (17, 8), (21, 8), (31, 8)])
+def test_short_reads(k, key_bytes):
+    data, start, length = ob.parse_fasta(text=fx.fx_with_n() + fx.fx_ragged() + fx.fx_multiline())
+    check(data, start, length, k, key_bytes)
+
+
+@pytest.mark.parametrize("k,key_bytes", [(12, 4), (31, 8)])
+def test_repeats_and_all_same(k, key_bytes):
+    """low-complexity reads: few distinct k-mers with large counts, incl. the all-T read (max key)"""
+    reads = ["T" * 150, "A" * 150, "AC" * 75, "ACGT" * 60, "T" * 40 + "N" + "T" * 60, "G" * 600, "TTTTTTTTTTTTTTTTTTTTTTTTTTTTTTT"]
+    text = "".join(f">r{i}\n{r}\n" for i, r in enumerate(reads))
+    data, start, length = ob.parse_fasta(text=text)
+    check(data, start, length, k, key_bytes)
+
+
+@pytest.mark.parametrize("k,key_bytes", [(12, 4), (16, 4), (21, 8), (31, 8)])
+def test_window_count_boundaries_and_long_reads(k, key_bytes):
+    """reads around the 128/256/512-window network sizes and long reads (radix-sort path)"""
+    import random
+    rng = random.Random(k)
+    lens = [k - 1, k, k + 1, 127 + k, 128 + k, 255 + k, 256 + k, 257 + k, 511 + k, 512 + k - 1, 512 + k, 513 + k,
+            3000, 20000, 70000]
+    reads = []
+    for L in lens:
+        s = [rng.choice("ACGT") for _ in range(L)]
+        if L > 40:
+            s[L // 3] = "N"
+        reads.append("".join(s))
+    reads.append(("ACGTTGCA" * 4000)[:30000])      # long AND repetitive
+    text = "".join(f">r{i}\n{r}\n" for i, r in enumerate(reads))
+    data, start, length = ob.parse_fasta(text=text)
+    check(data, start, length, k, key_bytes)
+
+
+def test_ascii_input_and_150bp_batch():
+    nS, L, k = 20000, 150, 12
+    data, start, length = fx.synthetic_codes(nS, L, seed=12, n_frac=0.001)
+    lut = np.array([65, 67, 71, 84], dtype=np.uint8)
+    raw = np.where(data >= 0, lut[np.clip(data, 0, 3)], 78).astype(np.uint8)
+    raw[start + length] = 10
+    check(raw, start, length, k, 4, fmt=cf.FMT_ASCII, odata=data)
+
+
+def test_capacity_error():
+    data, start, length = fx.synthetic_codes(10, 150, seed=1)
+    b = torch.from_numpy(np.concatenate([data.view(np.uint8), np.full(16, 255, np.uint8)])).cuda()
+    s, l = torch.from_numpy(start).cuda(), torch.from_numpy(length).cuda()
+    rb = torch.zeros(11, dtype=torch.int64, device="cuda")
+    rc = torch.zeros(10, dtype=torch.int32, device="cuda")
+    keys = torch.zeros(100, dtype=torch.int64, device="cuda")
+    cnt = torch.zeros(100, dtype=torch.int32, device="cuda")
+    with pytest.raises(cf.CfrkError) as e:
+        cf.count_sparse_device(b.data_ptr(), s.data_ptr(), l.data_ptr(), len(data), 10, 12, rb.data_ptr(), rc.data_ptr(),
+                               keys.data_ptr(), cnt.data_ptr(), 100)
+    assert e.value.code == -1 and "capacity" in str(e.value)
