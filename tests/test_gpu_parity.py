@@ -53,3 +53,35 @@ def test_empty_and_tiny():
     got = cf.kmer_main(data, np.array([0]), np.array([4]), 2)
     want = ob.count_dense(data, np.array([0]), np.array([4]), 2)
     np.testing.assert_array_equal(got, want)
+
+
+def test_concurrent_host_threads():
+    """the reference driver calls kmer_main from several pthreads at once (src/main.cu:279-289);
+    scratch buffers and streams are per host thread"""
+    import threading
+    data, start, length = fx.synthetic_codes(6000, 150, seed=77, n_frac=0.002)
+    wants = {k: ob.count_dense_fast(data, start, length, k, ob.MODE_COMPAT) for k in (3, 5, 6, 7)}
+    errs = []
+
+    def work(k):
+        try:
+            for _ in range(3):
+                got = cf.kmer_main(data, start, length, k)
+                if not np.array_equal(got, wants[k]):
+                    errs.append(f"k={k} mismatch")
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+    th = [threading.Thread(target=work, args=(k,)) for k in (3, 5, 6, 7) for _ in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+
+
+def test_pageable_and_unaligned_host_buffers():
+    """host buffers need no alignment or pinning (the device copy is ours)"""
+    data, start, length = fx.synthetic_codes(3000, 97, seed=5, n_frac=0.01)
+    buf = np.empty(len(data) + 3, dtype=np.int8)
+    view = buf[3:]           # misaligned host pointer
+    view[:] = data
+    for k in (2, 4, 8):
+        np.testing.assert_array_equal(cf.kmer_main(view, start, length, k), ob.count_dense_fast(data, start, length, k))
