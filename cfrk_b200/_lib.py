@@ -9,7 +9,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libcfrk_b200.so")
 SYMBOLS = [
     "cfrk_version", "cfrk_last_error", "cfrk_device_count", "cfrk_launch_count",
     "cfrk_count_dense_host", "cfrk_count_dense_device", "cfrk_dense_reads_per_tile",
-    "cfrk_encode_2bit_device", "cfrk_global_hist_device", "cfrk_count_sparse_device", "cfrk_run_file",
+    "cfrk_encode_2bit_device", "cfrk_global_hist_device", "cfrk_count_sparse_device", "cfrk_scan_fasta_device",
+    "cfrk_run_file",
 ]
 
 _lib = None
@@ -36,6 +37,7 @@ def load():
     L.cfrk_global_hist_device.argtypes = [vp, i32, vp, vp, i64, i64, i32, vp, vp]
     L.cfrk_count_sparse_device.argtypes = [vp, i32, vp, vp, i64, i64, i32, i32, vp, vp, vp, vp, i64,
                                            C.POINTER(C.c_int64), vp]
+    L.cfrk_scan_fasta_device.argtypes = [vp, i64, i32, vp, vp, vp, i64, C.POINTER(C.c_int64), vp]
     L.cfrk_run_file.argtypes = [C.c_char_p, C.c_char_p, i32, i32, i64, i32, i32]
     _lib = L
     return L

@@ -103,6 +103,14 @@ def count_sparse_device(d_bases, d_start, d_length, nN, nS, k, d_row_begin, d_ro
     return total.value
 
 
+def scan_fasta_device(d_bytes, n, is_final, d_header, d_start, d_length, capacity, stream=0):
+    """Record table of raw FASTA bytes on the GPU; returns the number of headers in the span."""
+    nh = C.c_int64(0)
+    _check(lib().cfrk_scan_fasta_device(d_bytes, n, int(is_final), d_header, d_start, d_length, capacity,
+                                        C.byref(nh), stream), "cfrk_scan_fasta_device")
+    return nh.value
+
+
 def run_file(fasta, out, k, nt=12, chunk_size=8192, flags=0, device=0):
     """cfrk <fasta> <out> <k> [nt] [chunkSize] (reference src/main.cu:232-305)."""
     _check(lib().cfrk_run_file(os.fsencode(fasta), os.fsencode(out), k, nt, chunk_size, flags, device),

@@ -260,6 +260,28 @@ int cfrk_count_sparse_device(const void* d_bases, int fmt, const int64_t* d_star
     return CFRK_OK;
 }
 
+int cfrk_scan_fasta_device(const void* d_bytes, int64_t n, int is_final, int64_t* d_header, int64_t* d_start,
+                           int32_t* d_length, int64_t capacity, int64_t* n_headers, void* stream)
+{
+    if (n_headers) *n_headers = 0;
+    if (n < 0 || capacity < 0) return fail(CFRK_EINVAL, "negative size");
+    if (n == 0) return CFRK_OK;
+    if (!d_bytes || !d_header || !d_start || !d_length) return fail(CFRK_EINVAL, "null device pointer");
+    if (reinterpret_cast<uintptr_t>(d_bytes) & 15) return fail(CFRK_EINVAL, "d_bytes must be 16-byte aligned");
+    int64_t out[2];
+    cudaError_t e = cfrk::launch_fasta_scan(static_cast<const uint8_t*>(d_bytes), n, is_final, d_header, d_start,
+                                            d_length, capacity, out, static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return fail_cuda(e, "fasta scan");
+    if (n_headers) *n_headers = out[0];
+    switch (out[1]) {
+    case 0: return CFRK_OK;
+    case 1: return fail(CFRK_EFORMAT, "'>' inside a line (grep -c over-counts nS in the reference, src/fastaIO.h:16)");
+    case 2: return fail(CFRK_EFORMAT, "sequence text before the first '>' header (undefined in the reference, src/fastaIO.h:49-52)");
+    case 3: return fail(CFRK_EFORMAT, "record longer than 2^31-1 bytes (length is int in the reference, src/tipos.h:26)");
+    default: return fail(CFRK_EINVAL, "capacity smaller than the number of headers");
+    }
+}
+
 int cfrk_global_hist_device(const void* d_bases, int fmt, const int64_t* d_start, const int32_t* d_length,
                             int64_t nN, int64_t nS, int k, uint32_t* d_hist, void* stream)
 {

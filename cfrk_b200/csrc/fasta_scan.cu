@@ -1,0 +1,161 @@
+// fasta_scan.cu -- record boundary detection on the GPU.
+//
+// Replaces, for the file pipeline, popen("grep -c '>'") + the getline loop of the reference
+// reader (src/fastaIO.h:12-69): the raw file bytes are already in HBM for the count kernel, so
+// the record table is derived there and the host never looks at a base.
+//   pass 1  every thread inspects 16 bytes: '>' at a line start = header; '>' anywhere else is
+//           where the reference is undefined (grep over-counts nS) -> error flag.  Headers are
+//           counted per 4 KiB chunk.
+//   scan    exclusive sum of the chunk counts (cub::DeviceScan: plumbing).
+//   pass 2  header positions written in file order.
+//   pass 3  one thread per record: walk to the end of the header line; the record text is
+//           everything up to the next header (or the end of the span), and
+//           length = max(0, text - 1)  (len = strlen - 1, src/fastaIO.h:53,65).
+#include "kernels.h"
+
+#include <cub/device/device_scan.cuh>
+
+namespace cfrk {
+
+extern void count_launch();
+
+constexpr int kScanThreads = 256;
+constexpr int kScanChunk = kScanThreads * 16;
+
+__device__ __forceinline__ uint32_t header_mask16(const uint8_t* __restrict__ buf, int64_t n, int64_t p0, int* err)
+{
+    // bit j set <=> byte p0+j is '>' starting a line
+    uint32_t m = 0;
+    if (p0 >= n) return 0;
+    const int cnt = (int)min((int64_t)16, n - p0);
+    const uint4 v = *reinterpret_cast<const uint4*>(buf + p0);   // buffer is padded to 16 bytes
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    uint8_t prev = p0 == 0 ? (uint8_t)'\n' : buf[p0 - 1];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+        const uint8_t c = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
+        if (j < cnt && c == '>') {
+            if (prev == '\n') m |= 1u << j;
+            else *err = 1;   // '>' inside a line: nS over-counted in the reference (src/fastaIO.h:16)
+        }
+        prev = c;
+    }
+    return m;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_count_kernel(const uint8_t* __restrict__ buf, int64_t n,
+                                                                 int64_t* __restrict__ chunk_count, int* __restrict__ err)
+{
+    const int64_t p0 = ((int64_t)blockIdx.x * kScanThreads + threadIdx.x) * 16;
+    int e = 0;
+    const int c = __popc(header_mask16(buf, n, p0, &e));
+    if (e) *err = 1;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && n > 0 && buf[0] != '>') *err = 2;  // text before the first header
+    __shared__ int s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    const int wsum = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(&s_sum, wsum);
+    __syncthreads();
+    if (threadIdx.x == 0) chunk_count[blockIdx.x] = s_sum;
+}
+
+__global__ void __launch_bounds__(kScanThreads) scan_write_kernel(const uint8_t* __restrict__ buf, int64_t n,
+                                                                 const int64_t* __restrict__ chunk_off,
+                                                                 int64_t* __restrict__ header, int64_t cap)
+{
+    const int64_t p0 = ((int64_t)blockIdx.x * kScanThreads + threadIdx.x) * 16;
+    int e = 0;
+    const uint32_t m = header_mask16(buf, n, p0, &e);
+    const int c = __popc(m);
+    // exclusive scan of c over the CTA
+    __shared__ int s_warp[kScanThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    int before = 0;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; w++) before += w < warp ? s_warp[w] : 0;
+    int64_t pos = chunk_off[blockIdx.x] + before + inc - c;
+    uint32_t mm = m;
+    while (mm) {
+        const int j = __ffs(mm) - 1;
+        mm &= mm - 1;
+        if (pos < cap) header[pos] = p0 + j;
+        pos++;
+    }
+}
+
+__global__ void records_kernel(const uint8_t* __restrict__ buf, int64_t n, const int64_t* __restrict__ header,
+                               int64_t n_headers, int final_span, int64_t* __restrict__ start,
+                               int32_t* __restrict__ length, int* __restrict__ err)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t complete = final_span ? n_headers : n_headers - 1;
+    if (i >= complete) return;
+    const int64_t h = header[i];
+    const int64_t end = i + 1 < n_headers ? header[i + 1] : n;
+    int64_t s = h;
+    while (s < end && buf[s] != '\n') s++;   // header lines are short
+    s = s < end ? s + 1 : end;
+    const int64_t text = end - s;
+    if (text > 2147483647ll) { *err = 3; return; }
+    start[i] = s;
+    length[i] = text > 0 ? (int32_t)(text - 1) : 0;
+}
+
+// d_header: cap entries; d_start/d_length: cap entries; h_out[0] = number of headers in the span,
+// h_out[1] = error (0 ok, 1 '>' inside a line, 2 text before the first header, 3 record too long,
+// 4 more headers than cap).  Synchronises the stream.
+cudaError_t launch_fasta_scan(const uint8_t* d_buf, int64_t n, int final_span, int64_t* d_header, int64_t* d_start,
+                              int32_t* d_length, int64_t cap, int64_t* h_out, cudaStream_t st)
+{
+    h_out[0] = 0; h_out[1] = 0;
+    if (n <= 0) return cudaSuccess;
+    cudaError_t e;
+    const int64_t nchunks = (n + kScanChunk - 1) / kScanChunk;
+    int64_t* chunk = nullptr;
+    int* d_err = nullptr;
+    if ((e = cudaMallocAsync(reinterpret_cast<void**>(&chunk), (size_t)(nchunks + 1) * 8, st)) != cudaSuccess) return e;
+    if ((e = cudaMallocAsync(reinterpret_cast<void**>(&d_err), 4, st)) != cudaSuccess) return e;
+    cudaMemsetAsync(d_err, 0, 4, st);
+    cudaMemsetAsync(chunk + nchunks, 0, 8, st);
+    scan_count_kernel<<<(unsigned)nchunks, kScanThreads, 0, st>>>(d_buf, n, chunk, d_err);
+    count_launch();
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, chunk, chunk, nchunks + 1, st);
+    void* tmp = nullptr;
+    if ((e = cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, st)) != cudaSuccess) return e;
+    if ((e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, chunk, chunk, nchunks + 1, st)) != cudaSuccess) return e;
+    int64_t n_headers = 0;
+    int err = 0;
+    cudaMemcpyAsync(&n_headers, chunk + nchunks, 8, cudaMemcpyDeviceToHost, st);
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    if (n_headers > cap) {
+        err = 4;
+    } else {
+        scan_write_kernel<<<(unsigned)nchunks, kScanThreads, 0, st>>>(d_buf, n, chunk, d_header, cap);
+        count_launch();
+        if (n_headers > 0) {
+            records_kernel<<<(unsigned)((n_headers + 255) / 256), 256, 0, st>>>(d_buf, n, d_header, n_headers, final_span,
+                                                                                d_start, d_length, d_err);
+            count_launch();
+        }
+        cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, st);
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    }
+    cudaFreeAsync(tmp, st);
+    cudaFreeAsync(chunk, st);
+    cudaFreeAsync(d_err, st);
+    h_out[0] = n_headers;
+    h_out[1] = err;
+    return cudaGetLastError();
+}
+
+}  // namespace cfrk

@@ -28,6 +28,12 @@ cudaError_t launch_sparse(const void* bases, int fmt, const int64_t* start, cons
                           int64_t* row_begin, int32_t* row_count, void* keys, int key_bytes, uint32_t* counts,
                           int64_t capacity, int64_t* total_windows, cudaStream_t st);
 
+// FASTA record table of a span of raw file bytes (16-byte aligned, padded): header positions,
+// and (start, length) of every record whose end is known (all when final_span, else all but the
+// last).  h_out[0] = headers found, h_out[1] = error code (fasta_scan.cu).  Synchronises `st`.
+cudaError_t launch_fasta_scan(const uint8_t* d_buf, int64_t n, int final_span, int64_t* d_header, int64_t* d_start,
+                              int32_t* d_length, int64_t cap, int64_t* h_out, cudaStream_t st);
+
 uint64_t launch_count();
 
 }  // namespace cfrk

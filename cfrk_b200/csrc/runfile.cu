@@ -9,8 +9,10 @@
 //            host -- newline-as-base, CRLF, missing final newline all fall out.
 //            Replaces popen("grep -c") + getline + 3 malloc/record + strcat + per-base switch
 //            + ProcessData + SelectChunk (src/fastaIO.h:12-148, src/main.cu:110-206).
-//   scan     the host only looks for '>' (memchr); a '>' that does not start a line, or text
-//            before the first header, is where the reference is undefined: CFRK_EFORMAT.
+//   scan     on the GPU (fasta_scan.cu): header positions, (start, length) per record; the host
+//            gets the small table back and never looks at a base.  A '>' that does not start a
+//            line, or text before the first header, is where the reference is undefined:
+//            CFRK_EFORMAT.
 //   count    dense_count_kernel over the buffer, rows through a two-slot device/pinned ring.
 //   writer   nt threads format rows ("bin:count ", src/main.cu:53-55) into private buffers
 //            that are written in order; "\n" before every row but the first, none at EOF.
@@ -24,6 +26,8 @@
 #include "internal.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
@@ -41,6 +45,23 @@ namespace {
 struct Err {
     int code = CFRK_OK;
     std::string msg;
+};
+
+// CFRK_TRACE=1: wall-clock trace of the file pipeline on stderr (the reference only has
+// commented-out time(NULL) probes, src/main.cu:259-268,302-306)
+struct Trace {
+    bool on = getenv("CFRK_TRACE") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), last = t0;
+    void mark(const char* what, size_t bytes = 0)
+    {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[cfrk trace] %9.3f ms (+%8.3f) %s", std::chrono::duration<double, std::milli>(now - t0).count(),
+                std::chrono::duration<double, std::milli>(now - last).count(), what);
+        if (bytes) fprintf(stderr, " %zu bytes", bytes);
+        fputc('\n', stderr);
+        last = now;
+    }
 };
 #define RF_CU(call)                                                                  \
     do {                                                                             \
@@ -145,45 +166,12 @@ private:
 };
 
 // ------------------------------------------------------------------------------------------
-// Header scan of data[0, n).  data[0] must be '>' (the caller cuts buffers at headers).
-// Appends (start, length) for every record whose end is known: all of them when `final`,
-// else all but the last.  Returns false on input the reference is undefined on.
+// Record table of a span, as fasta_scan.cu produces it on the device.
 struct RecordIndex {
-    std::vector<int64_t> start;
+    std::vector<int64_t> start;   // records whose end is known: all of them in a final span, else all but the last
     std::vector<int32_t> length;
-    std::vector<size_t> header;  // position of each header's '>'
+    std::vector<size_t> header;   // position of each header's '>'
 };
-
-bool scan_records(const char* data, size_t n, bool final, RecordIndex& ri, Err& err)
-{
-    ri.start.clear(); ri.length.clear(); ri.header.clear();
-    if (n == 0) return true;
-    if (data[0] != '>') { err.code = CFRK_EFORMAT; err.msg = "sequence text before the first '>' header (undefined in the reference, src/fastaIO.h:49-52)"; return false; }
-    size_t p = 0;
-    while (p < n) {
-        const char* g = static_cast<const char*>(memchr(data + p, '>', n - p));
-        if (!g) break;
-        size_t h = (size_t)(g - data);
-        if (h != 0 && data[h - 1] != '\n') { err.code = CFRK_EFORMAT; err.msg = "'>' inside a line (grep -c over-counts nS in the reference, src/fastaIO.h:16)"; return false; }
-        ri.header.push_back(h);
-        const char* nl = static_cast<const char*>(memchr(g, '\n', n - h));
-        p = nl ? (size_t)(nl - data) + 1 : n;
-        // (a second '>' inside the header line is fine: grep -c counts lines, not characters)
-    }
-    const size_t m = ri.header.size();
-    const size_t complete = final ? m : (m ? m - 1 : 0);
-    for (size_t i = 0; i < complete; i++) {
-        const size_t h = ri.header[i];
-        const size_t end = (i + 1 < m) ? ri.header[i + 1] : n;
-        const char* nl = static_cast<const char*>(memchr(data + h, '\n', end - h));
-        const size_t s = nl ? (size_t)(nl - data) + 1 : end;
-        const size_t text = end - s;
-        if (text > (size_t)INT32_MAX) { err.code = CFRK_EFORMAT; err.msg = "record longer than 2^31-1 bytes (length is int in the reference, src/tipos.h:26)"; return false; }
-        ri.start.push_back((int64_t)s);
-        ri.length.push_back(text > 0 ? (int32_t)(text - 1) : 0);  // len = strlen(text) - 1, src/fastaIO.h:53,65
-    }
-    return true;
-}
 
 // ------------------------------------------------------------------------------------------
 // .cfrk text writer
@@ -284,7 +272,7 @@ struct Pipeline {
     cudaStream_t compute = nullptr, copy = nullptr;
     cudaEvent_t done[2] = {}, drained[2] = {};
     char* d_in = nullptr; size_t cap_in = 0;
-    int64_t* d_start = nullptr; int32_t* d_length = nullptr; size_t cap_reads = 0;
+    int64_t* d_start = nullptr; int32_t* d_length = nullptr; int64_t* d_header = nullptr; size_t cap_reads = 0;
     int32_t* d_rows[2] = {}; int32_t* h_rows[2] = {}; size_t cap_rows = 0;
 
     bool init(Err& err)
@@ -299,19 +287,20 @@ struct Pipeline {
     }
     bool reserve(size_t in_bytes, size_t nreads, size_t row_bytes, Err& err)
     {
-        if (in_bytes + CFRK_PAD > cap_in) {
+        if (in_bytes && in_bytes + CFRK_PAD > cap_in) {
             cudaFree(d_in);
             cap_in = in_bytes + CFRK_PAD + in_bytes / 8;
             RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_in), cap_in));
         }
         if (nreads > cap_reads) {
-            cudaFree(d_start); cudaFree(d_length);
+            cudaFree(d_start); cudaFree(d_length); cudaFree(d_header);
             cap_reads = nreads + nreads / 4 + 64;
             RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_start), cap_reads * 8));
             RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_length), cap_reads * 4));
+            RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_header), cap_reads * 8));
         }
-        const size_t need = std::max(row_bytes, kSlotBytes);
-        if (need > cap_rows) {
+        const size_t need = row_bytes;
+        if (row_bytes && need > cap_rows) {
             for (int i = 0; i < 2; i++) {
                 cudaFree(d_rows[i]); if (h_rows[i]) cudaFreeHost(h_rows[i]);
                 RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_rows[i]), need));
@@ -321,7 +310,49 @@ struct Pipeline {
         }
         return true;
     }
-    // Count reads [0, nreads) of the span, produce rows [0, nrows) and hand them to the writer.
+    // Span of raw file bytes -> HBM, record table built THERE (fasta_scan.cu); the host gets the
+    // (small) table back for its bookkeeping and never looks at a base.
+    bool upload_and_scan(const char* h_in, size_t in_bytes, bool final_span, RecordIndex& ri, Err& err)
+    {
+        ri.start.clear(); ri.length.clear(); ri.header.clear();
+        if (in_bytes == 0) return true;
+        if (!reserve(in_bytes, std::max<size_t>(cap_reads, in_bytes / 64 + 64), 0, err)) return false;
+        RF_CU(cudaMemcpyAsync(d_in, h_in, in_bytes, cudaMemcpyHostToDevice, compute));
+        RF_CU(cudaMemsetAsync(d_in + in_bytes, 0, CFRK_PAD, compute));
+        int64_t out[2];
+        for (;;) {
+            cudaError_t e = cfrk::launch_fasta_scan(reinterpret_cast<const uint8_t*>(d_in), (int64_t)in_bytes, final_span,
+                                                    d_header, d_start, d_length, (int64_t)cap_reads, out, compute);
+            if (e != cudaSuccess) { err.code = CFRK_ECUDA; err.msg = std::string("fasta scan: ") + cudaGetErrorString(e); return false; }
+            if (out[1] != 4) break;
+            if (!reserve(in_bytes, (size_t)out[0], 0, err)) return false;   // more records than guessed: grow, rescan
+        }
+        if (out[1] == 1) { err.code = CFRK_EFORMAT; err.msg = "'>' inside a line (grep -c over-counts nS in the reference, src/fastaIO.h:16)"; return false; }
+        if (out[1] == 2) { err.code = CFRK_EFORMAT; err.msg = "sequence text before the first '>' header (undefined in the reference, src/fastaIO.h:49-52)"; return false; }
+        if (out[1] == 3) { err.code = CFRK_EFORMAT; err.msg = "record longer than 2^31-1 bytes (length is int in the reference, src/tipos.h:26)"; return false; }
+        const size_t nh = (size_t)out[0];
+        const size_t complete = final_span ? nh : (nh ? nh - 1 : 0);
+        ri.header.resize(nh); ri.start.resize(complete); ri.length.resize(complete);
+        std::vector<int64_t> hdr(nh);
+        if (nh) RF_CU(cudaMemcpyAsync(hdr.data(), d_header, nh * 8, cudaMemcpyDeviceToHost, compute));
+        if (complete) {
+            RF_CU(cudaMemcpyAsync(ri.start.data(), d_start, complete * 8, cudaMemcpyDeviceToHost, compute));
+            RF_CU(cudaMemcpyAsync(ri.length.data(), d_length, complete * 4, cudaMemcpyDeviceToHost, compute));
+        }
+        RF_CU(cudaStreamSynchronize(compute));
+        for (size_t i = 0; i < nh; i++) ri.header[i] = (size_t)hdr[i];
+        return true;
+    }
+    // Rows [0, nrows) of the span that upload_and_scan() left in HBM.
+    bool count_scanned(const char* h_in, size_t in_bytes, const RecordIndex& ri, size_t nrows, int k, int mode,
+                       int64_t chunk_size, int64_t index_base, CfrkWriter& w, Err& err)
+    {
+        if (nrows == 0) return true;
+        if (mode == CFRK_MODE_COMPAT && std::find(ri.length.begin(), ri.length.end(), 0) != ri.length.end())
+            return run(h_in, in_bytes, ri, nrows, k, mode, chunk_size, index_base, w, err);   // needs the packed layout
+        return count_rows(in_bytes, ri.start.size(), nrows, k, mode, chunk_size, index_base, w, err);
+    }
+    // Host-side record table (the rare packed layout): upload bytes + table, then count.
     bool run(const char* h_in, size_t in_bytes, const RecordIndex& ri_in, size_t nrows, int k, int mode,
              int64_t chunk_size, int64_t index_base, CfrkWriter& w, Err& err)
     {
@@ -352,16 +383,25 @@ struct Pipeline {
         }
         const RecordIndex& ri = *rip;
         const size_t nreads = ri.start.size();
-        const size_t bins = (size_t)1 << (2 * k), row_bytes = bins * 4;
-        if (!reserve(in_bytes, nreads, row_bytes, err)) return false;
-        const size_t rpt = (size_t)cfrk::dense_reads_per_tile(k);
-        size_t slice = std::max<size_t>(1, cap_rows / row_bytes);
-        slice = std::max(rpt, slice / rpt * rpt);
-
+        if (!reserve(in_bytes, nreads, 0, err)) return false;
         RF_CU(cudaMemcpyAsync(d_in, h_in, in_bytes, cudaMemcpyHostToDevice, compute));
         RF_CU(cudaMemsetAsync(d_in + in_bytes, 0, CFRK_PAD, compute));
         RF_CU(cudaMemcpyAsync(d_start, ri.start.data(), nreads * 8, cudaMemcpyHostToDevice, compute));
         RF_CU(cudaMemcpyAsync(d_length, ri.length.data(), nreads * 4, cudaMemcpyHostToDevice, compute));
+        const bool ok = count_rows(in_bytes, nreads, nrows, k, mode, chunk_size, index_base, w, err);
+        RF_CU(cudaStreamSynchronize(compute));   // pack_buf / ri must outlive the copies
+        return ok;
+    }
+    // d_in / d_start / d_length hold the span: kernels slice by slice, rows through the ring to the writer.
+    bool count_rows(size_t in_bytes, size_t nreads, size_t nrows, int k, int mode, int64_t chunk_size,
+                    int64_t index_base, CfrkWriter& w, Err& err)
+    {
+        const size_t bins = (size_t)1 << (2 * k), row_bytes = bins * 4;
+        // ring slots: as large as the span needs, at most kSlotBytes
+        if (!reserve(0, 0, std::max(row_bytes, std::min(kSlotBytes, nrows * row_bytes)), err)) return false;
+        const size_t rpt = (size_t)cfrk::dense_reads_per_tile(k);
+        size_t slice = std::max<size_t>(1, cap_rows / row_bytes);
+        slice = std::max(rpt, slice / rpt * rpt);
 
         const size_t nslices = (nrows + slice - 1) / slice;
         for (size_t s = 0; s <= nslices; s++) {
@@ -393,7 +433,7 @@ struct Pipeline {
     }
     ~Pipeline()
     {
-        cudaFree(d_in); cudaFree(d_start); cudaFree(d_length);
+        cudaFree(d_in); cudaFree(d_start); cudaFree(d_length); cudaFree(d_header);
         for (int i = 0; i < 2; i++) {
             cudaFree(d_rows[i]);
             if (h_rows[i]) cudaFreeHost(h_rows[i]);
@@ -412,13 +452,25 @@ bool run_file(const char* fasta, const char* out_path, int k, int nt, int64_t ch
     const int mode = (flags & CFRK_RUN_EXACT) ? CFRK_MODE_EXACT : CFRK_MODE_COMPAT;
     RF_CU(cudaSetDevice(device));
 
-    constexpr size_t kChunk = (size_t)64 << 20, kHeadroom = (size_t)64 << 20;
+    Trace tr;
+    tr.mark("cudaSetDevice");
+    // 64 MiB streaming window (+ as much headroom for carried records); small files get small
+    // pinned buffers: pinning costs ~0.5 ms/MiB and test-sized inputs should start instantly
+    size_t window = (size_t)64 << 20;
+    {
+        struct stat st0;
+        if (stat(fasta, &st0) == 0 && (size_t)st0.st_size < window)
+            window = std::max<size_t>((size_t)1 << 20, ((size_t)st0.st_size + 4095) & ~(size_t)4095);
+    }
+    const size_t kChunk = window, kHeadroom = window;
     FastaStreamer rd;
     if (!rd.open(fasta, kChunk, kHeadroom, err)) return false;
+    tr.mark("streamer open (pinned ring)");
     CfrkWriter w;
     if (!w.open(out_path, k, nt, flags & CFRK_RUN_SPARSE, err)) return false;
     Pipeline gpu;
     if (!gpu.init(err)) return false;
+    tr.mark("pipeline init");
 
     RecordIndex ri;
     size_t carry = 0;            // bytes of unfinished records prepended to the current buffer
@@ -429,7 +481,9 @@ bool run_file(const char* fasta, const char* out_path, int k, int nt, int64_t ch
         FastaStreamer::Buf* b = rd.acquire(i);
         char* data = b->base + rd.headroom() - carry;
         const size_t n = carry + b->n;
-        if (!scan_records(data, n, b->eof, ri, err)) return false;
+        tr.mark("buffer acquired", n);
+        if (!gpu.upload_and_scan(data, n, b->eof, ri, err)) return false;
+        tr.mark("uploaded + scanned on device");
         const size_t m = ri.start.size();  // records whose end is known
 
         size_t keep_from;  // data[keep_from, n) goes in front of the next buffer
@@ -446,8 +500,9 @@ bool run_file(const char* fasta, const char* out_path, int k, int nt, int64_t ch
                     held += (size_t)ri.length[nrows] + 1;
                 }
             }
-            if (!gpu.run(data, n, ri, nrows, k, mode, chunk_size, reads_done, w, err)) return false;
+            if (!gpu.count_scanned(data, n, ri, nrows, k, mode, chunk_size, reads_done, w, err)) return false;
             reads_done += (int64_t)nrows;
+            tr.mark("rows counted + written");
             keep_from = b->eof ? n : (m ? ri.header[nrows] : 0);
         } else {
             for (size_t r = 0; r < m; r++)
@@ -459,7 +514,7 @@ bool run_file(const char* fasta, const char* out_path, int k, int nt, int64_t ch
         carry = n - keep_from;
         if (carry > rd.headroom()) {
             err.code = CFRK_EFORMAT;
-            err.msg = "a single FASTA record (plus its predecessor) exceeds the 64 MiB streaming window";
+            err.msg = "a single FASTA record (plus the records held back with it) exceeds the streaming window";
             return false;
         }
         memcpy(rd.next_base(i) + rd.headroom() - carry, data + keep_from, carry);
@@ -483,9 +538,11 @@ bool run_file(const char* fasta, const char* out_path, int k, int nt, int64_t ch
                 if (r <= 0) break;
                 got += (size_t)r;
             }
-            bool ok = got == bytes && scan_records(h, bytes, true, ri, err);
+            bool ok = got == bytes && gpu.upload_and_scan(h, bytes, true, ri, err);
             if (got != bytes) { err.code = CFRK_EIO; err.msg = "short read of the tail chunk"; }
-            if (ok) ok = gpu.run(h, bytes, ri, ri.start.size(), k, mode, chunk_size, (nS / chunk_size) * chunk_size, w, err);
+            tr.mark("tail chunk scanned", bytes);
+            if (ok) ok = gpu.count_scanned(h, bytes, ri, ri.start.size(), k, mode, chunk_size, (nS / chunk_size) * chunk_size, w, err);
+            tr.mark("tail rows counted + written");
             cudaFreeHost(h);
             if (!ok) return false;
         }

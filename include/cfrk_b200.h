@@ -132,6 +132,21 @@ int cfrk_count_sparse_device(const void *d_bases, int fmt, const int64_t *d_star
                              uint32_t *d_counts, int64_t capacity, int64_t *total_windows,
                              void *stream);
 
+/*
+ * FASTA record table on the GPU (replaces popen("grep -c") + the getline loop of
+ * src/fastaIO.h:12-69 for bytes that are already in HBM).  d_bytes: n raw file bytes, 16-byte
+ * aligned and readable to the next 16-byte boundary; the span must begin with a header line.
+ * Writes the position of every header's '>' to d_header, and (start, length) -- reference
+ * semantics: text = all lines after the header up to the next header, length = text - 1 -- of
+ * every record whose end is known: all of them if is_final, else all but the last.
+ * *n_headers = headers found (records described = n_headers or n_headers - 1).
+ * CFRK_EFORMAT where the reference is undefined ('>' inside a line, text before the first
+ * header), CFRK_EINVAL if capacity is too small.  Synchronises the stream.
+ */
+int cfrk_scan_fasta_device(const void *d_bytes, int64_t n, int is_final, int64_t *d_header,
+                           int64_t *d_start, int32_t *d_length, int64_t capacity,
+                           int64_t *n_headers, void *stream);
+
 /* ---- file level: replaces main() of src/main.cu:232-305 ----------------------------- */
 
 #define CFRK_RUN_ALL_ROWS   1  /* print every read (chunk by chunk) instead of only the

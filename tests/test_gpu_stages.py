@@ -125,3 +125,44 @@ def test_full_size_properties():
     cf.global_hist_device(flat.data_ptr(), start.data_ptr(), length.data_ptr(), nS * (L + 1), nS, k, hist.data_ptr())
     torch.cuda.synchronize()
     assert torch.equal(out.sum(0, dtype=torch.int64), hist.to(torch.int64))
+
+
+@pytest.mark.parametrize("name", ["A_basic", "C_multiline", "F_crlf", "F_noeol", "F_blank", "G_short", "R_ragged"])
+@pytest.mark.parametrize("final", [True, False])
+def test_scan_fasta_device(name, final):
+    """record table built on the GPU == the table the reference parser implies (fixtures.ascii_batch)"""
+    text = dict((n, t) for n, t, _ in fx.EDGE_SET)[name]
+    raw, start, length = fx.ascii_batch(text)
+    n = len(raw)
+    buf = padded_bases(raw, 0)
+    cap = len(start) + 4
+    hdr = torch.zeros(cap, dtype=torch.int64, device="cuda")
+    st = torch.zeros(cap, dtype=torch.int64, device="cuda")
+    ln = torch.zeros(cap, dtype=torch.int32, device="cuda")
+    nh = cf.scan_fasta_device(buf.data_ptr(), n, final, hdr.data_ptr(), st.data_ptr(), ln.data_ptr(), cap)
+    torch.cuda.synchronize()
+    assert nh == len(start)
+    want_hdr = [i for i in range(n) if raw[i] == ord(">") and (i == 0 or raw[i - 1] == 10)]
+    np.testing.assert_array_equal(hdr.cpu().numpy()[:nh], want_hdr)
+    m = nh if final else nh - 1
+    np.testing.assert_array_equal(st.cpu().numpy()[:m], start[:m])
+    np.testing.assert_array_equal(ln.cpu().numpy()[:m], length[:m])
+
+
+def test_scan_fasta_device_errors():
+    for bad, frag in ((b"ACGT\n>a\nAC\n", "before the first"), (b">a\nAC>GT\n", "inside a line")):
+        raw = np.frombuffer(bad, dtype=np.uint8)
+        buf = padded_bases(raw, 0)
+        z = torch.zeros(8, dtype=torch.int64, device="cuda")
+        l = torch.zeros(8, dtype=torch.int32, device="cuda")
+        with pytest.raises(cf.CfrkError) as e:
+            cf.scan_fasta_device(buf.data_ptr(), len(raw), True, z.data_ptr(), z.clone().data_ptr(), l.data_ptr(), 8)
+        assert e.value.code == -5 and frag in str(e.value)
+    # capacity too small
+    raw = np.frombuffer(b">a\nA\n>b\nC\n>c\nG\n", dtype=np.uint8)
+    buf = padded_bases(raw, 0)
+    z = torch.zeros(2, dtype=torch.int64, device="cuda")
+    with pytest.raises(cf.CfrkError) as e:
+        cf.scan_fasta_device(buf.data_ptr(), len(raw), True, z.data_ptr(), z.clone().data_ptr(),
+                             torch.zeros(2, dtype=torch.int32, device="cuda").data_ptr(), 2)
+    assert e.value.code == -1
