@@ -321,7 +321,7 @@ __device__ __forceinline__ LaneRead make_lane_read(bool have, int64_t s, int len
 
 template <int NREADS_MAX>
 __device__ __forceinline__ Item warp_fetch_item(const uint8_t* __restrict__ bases, const LaneRead& lr, int n,
-                                                uint32_t total, uint32_t chunk)
+                                                uint32_t total, uint32_t chunk, bool any_empty)
 {
     const int lane = threadIdx.x & 31;
     const int64_t item = (int64_t)chunk * 31 + lane - 1;
@@ -329,10 +329,21 @@ __device__ __forceinline__ Item warp_fetch_item(const uint8_t* __restrict__ base
     it.live = item >= 0 && item < (int64_t)total;
     // q = last read whose first item is <= item (reads without items share their successor's cum)
     int q = 0;
+    if (NREADS_MAX > 4 && !any_empty) {
+        // every read has items, so cum is strictly increasing: q(lane) = q(lane 0) + number of
+        // reads that begin at items item0+1 .. item0+lane  -- one ballot + one warp OR-reduction
+        const int64_t item0 = (int64_t)chunk * 31 - 1;
+        const int cnt0 = __popc(__ballot_sync(0xffffffffu, lane < n && (int64_t)lr.cum <= item0));
+        const int64_t d = (int64_t)lr.cum - item0;
+        const uint32_t bit = (lane < n && d >= 1 && d <= 31) ? (1u << (int)d) : 0u;
+        const uint32_t begins = __reduce_or_sync(0xffffffffu, bit);
+        q = max(0, cnt0 - 1 + __popc(begins & ((2u << lane) - 1u)));
+    } else {
 #pragma unroll
-    for (int j = 1; j < NREADS_MAX; j++) {
-        const uint32_t cj = __shfl_sync(0xffffffffu, lr.cum, j);
-        if (j < n && cj <= (uint32_t)item) q = j;
+        for (int j = 1; j < NREADS_MAX; j++) {
+            const uint32_t cj = __shfl_sync(0xffffffffu, lr.cum, j);
+            if (j < n && cj <= (uint32_t)item) q = j;
+        }
     }
     const uint32_t cq = __shfl_sync(0xffffffffu, lr.cum, q);
     const int64_t s = __shfl_sync(0xffffffffu, lr.start, q);
@@ -354,10 +365,11 @@ __device__ __forceinline__ void warp_for_each_window(const uint8_t* __restrict__
     const uint32_t total = __shfl_sync(0xffffffffu, lr.cum + lr.nblk, 31);
     const uint32_t nchunks = (total + 30u) / 31u;
     if (nchunks == 0) return;
-    Item next = warp_fetch_item<NREADS_MAX>(bases, lr, n, total, 0);
+    const bool any_empty = __ballot_sync(0xffffffffu, (threadIdx.x & 31) < n && lr.nblk == 0) != 0u;
+    Item next = warp_fetch_item<NREADS_MAX>(bases, lr, n, total, 0, any_empty);
     for (uint32_t chunk = 0; chunk < nchunks; chunk++) {
         const Item cur = next;
-        if (chunk + 1 < nchunks) next = warp_fetch_item<NREADS_MAX>(bases, lr, n, total, chunk + 1);
+        if (chunk + 1 < nchunks) next = warp_fetch_item<NREADS_MAX>(bases, lr, n, total, chunk + 1, any_empty);
         emit_item<K, FMT>(cur, ncount, mode, sink);
     }
 }

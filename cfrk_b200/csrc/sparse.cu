@@ -42,35 +42,64 @@ __global__ void nwin_kernel(const int32_t* __restrict__ length, int64_t nS, int 
 }
 
 // ------------------------------------------------------------------------------------------
+// keep min(mine, other) if take_min else max: min ^ ((mine ^ other) & mask), mask = take_min ? 0 : ~0
+template <typename KeyT>
+__device__ __forceinline__ KeyT keep_minmax(KeyT mine, KeyT other, KeyT mask)
+{
+    const KeyT mn = mine < other ? mine : other;
+    return mn ^ ((mine ^ other) & mask);
+}
+
+// Bitonic network over 32*E keys in blocked layout (lane L holds elements L*E .. L*E+E-1), in the
+// direction-free form: every merge starts with a MIRRORED compare (i with i ^ (size-1)) and goes on
+// with the usual strides, and every comparator leaves the minimum at the lower index.  In-lane
+// comparators are then pure min/max on compile-time registers; cross-lane ones need one per-lane
+// mask per stage.
 template <typename KeyT, int E>
 __device__ __forceinline__ void bitonic_sort_blocked(KeyT (&key)[E])
 {
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int size = 2; size <= 32 * E; size <<= 1) {
+        // mirrored step
+        if (size <= E) {
 #pragma unroll
-        for (int stride = size >> 1; stride >= 1; stride >>= 1) {
+            for (int e = 0; e < E; e++) {
+                const int p = e ^ (size - 1);
+                if (p > e) {
+                    const KeyT a = key[e], b = key[p];
+                    key[e] = a < b ? a : b;
+                    key[p] = a < b ? b : a;
+                }
+            }
+        } else {
+            const int lm = size / E - 1;
+            const KeyT mask = (lane & (size / (2 * E))) == 0 ? (KeyT)0 : ~(KeyT)0;
+            KeyT other[E];
+#pragma unroll
+            for (int e = 0; e < E; e++) other[e] = __shfl_xor_sync(0xffffffffu, key[E - 1 - e], lm);
+#pragma unroll
+            for (int e = 0; e < E; e++) key[e] = keep_minmax<KeyT>(key[e], other[e], mask);
+        }
+        // remaining strides
+#pragma unroll
+        for (int stride = size >> 2; stride >= 1; stride >>= 1) {
             if (stride >= E) {
                 const int ls = stride / E;
-                const bool lower = (lane & ls) == 0;
+                const KeyT mask = (lane & ls) == 0 ? (KeyT)0 : ~(KeyT)0;
 #pragma unroll
                 for (int e = 0; e < E; e++) {
                     const KeyT other = __shfl_xor_sync(0xffffffffu, key[e], ls);
-                    const bool asc = ((lane * E + e) & size) == 0;
-                    const KeyT mn = key[e] < other ? key[e] : other;
-                    const KeyT mx = key[e] < other ? other : key[e];
-                    key[e] = (lower == asc) ? mn : mx;
+                    key[e] = keep_minmax<KeyT>(key[e], other, mask);
                 }
             } else {
 #pragma unroll
                 for (int e = 0; e < E; e++) {
                     const int p = e ^ stride;
                     if (p > e) {
-                        const bool asc = ((lane * E + e) & size) == 0;
                         const KeyT a = key[e], b = key[p];
-                        const KeyT mn = a < b ? a : b, mx = a < b ? b : a;
-                        key[e] = asc ? mn : mx;
-                        key[p] = asc ? mx : mn;
+                        key[e] = a < b ? a : b;
+                        key[p] = a < b ? b : a;
                     }
                 }
             }
@@ -81,7 +110,8 @@ __device__ __forceinline__ void bitonic_sort_blocked(KeyT (&key)[E])
 // keys sorted ascending in blocked layout, the first nvalid of them real -> (key, count) pairs
 template <typename KeyT, int E>
 __device__ __forceinline__ int warp_rle_store(const KeyT (&key)[E], int nvalid, KeyT* __restrict__ keys_out,
-                                              uint32_t* __restrict__ counts_out)
+                                              uint32_t* __restrict__ counts_out, KeyT* __restrict__ stage_k,
+                                              uint32_t* __restrict__ stage_c)
 {
     const int lane = threadIdx.x & 31;
     KeyT prev = __shfl_up_sync(0xffffffffu, key[E - 1], 1);
@@ -121,14 +151,21 @@ __device__ __forceinline__ int warp_rle_store(const KeyT (&key)[E], int nvalid, 
         cnt[e] = (uint32_t)(nxt - g);
         if (heads & (1u << e)) nxt = g;
     }
+    // stage the pairs in shared memory, then write the row with coalesced stores
 #pragma unroll
     for (int e = 0; e < E; e++) {
         if (heads & (1u << e)) {
-            keys_out[off] = key[e];
-            counts_out[off] = cnt[e];
+            stage_k[off] = key[e];
+            stage_c[off] = cnt[e];
             off++;
         }
     }
+    __syncwarp();
+    for (int i = lane; i < total; i += 32) {
+        keys_out[i] = stage_k[i];
+        counts_out[i] = stage_c[i];
+    }
+    __syncwarp();
     return total;
 }
 
@@ -159,7 +196,8 @@ __device__ __forceinline__ bool stream_window(const WarpStream& st, int P, int k
 
 template <typename KeyT, int E>
 __device__ __forceinline__ int warp_count_read(const WarpStream& st, int a, int nwin, int k,
-                                               KeyT* __restrict__ keys_out, uint32_t* __restrict__ counts_out)
+                                               KeyT* __restrict__ keys_out, uint32_t* __restrict__ counts_out,
+                                               KeyT* __restrict__ stage_k, uint32_t* __restrict__ stage_c)
 {
     const int lane = threadIdx.x & 31;
     KeyT key[E];
@@ -178,25 +216,33 @@ __device__ __forceinline__ int warp_count_read(const WarpStream& st, int a, int 
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, d);
     bitonic_sort_blocked<KeyT, E>(key);
-    return warp_rle_store<KeyT, E>(key, nvalid, keys_out, counts_out);
+    return warp_rle_store<KeyT, E>(key, nvalid, keys_out, counts_out, stage_k, stage_c);
 }
 
-template <typename KeyT, int FMT>
-__global__ void __launch_bounds__(kSparseWarps * 32) sparse_short_kernel(
+// E = keys per lane: the kernel handles the reads whose window count falls in its class
+// ((E == 4: 1..128, E == 8: 129..256, E == 16: 257..512) and leaves the others to its siblings, so
+// that the common short-read case is not compiled with the register budget of the largest network.
+template <int E> struct SparseCta { static constexpr int WARPS = E == 16 ? 4 : kSparseWarps; };
+
+template <typename KeyT, int FMT, int E>
+__global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) sparse_short_kernel(
     const uint8_t* __restrict__ bases, const int64_t* __restrict__ start, const int32_t* __restrict__ length,
     int64_t nS, int k, const int64_t* __restrict__ row_begin, int32_t* __restrict__ row_count,
     KeyT* __restrict__ keys, uint32_t* __restrict__ counts)
 {
-    __shared__ uint32_t s_cw[kSparseWarps][kStreamBlocks];
-    __shared__ __align__(4) uint16_t s_vh[kSparseWarps][2 * ((kStreamBlocks + 1) / 2) + 2];
+    constexpr int WARPS = SparseCta<E>::WARPS;
+    __shared__ uint32_t s_cw[WARPS][kStreamBlocks];
+    __shared__ __align__(4) uint16_t s_vh[WARPS][2 * ((kStreamBlocks + 1) / 2) + 2];
+    __shared__ KeyT s_stage_k[WARPS][32 * E];
+    __shared__ uint32_t s_stage_c[WARPS][32 * E];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpStream st{s_cw[warp], s_vh[warp]};
-    const int64_t nwarps = (int64_t)gridDim.x * kSparseWarps;
-    for (int64_t r = (int64_t)blockIdx.x * kSparseWarps + warp; r < nS; r += nwarps) {
+    const int64_t nwarps = (int64_t)gridDim.x * WARPS;
+    for (int64_t r = (int64_t)blockIdx.x * WARPS + warp; r < nS; r += nwarps) {
         const int len = length[r];
         const int nwin = len - k + 1;
-        if (nwin <= 0) { if (lane == 0) row_count[r] = 0; continue; }
-        if (nwin > kShortMaxWindows) continue;  // long path
+        if (nwin <= 0) { if (E == 4 && lane == 0) row_count[r] = 0; continue; }
+        if (nwin > 32 * E || (E > 4 && nwin <= 16 * E)) continue;  // another class, or the long path
         const int64_t s = start[r];
         const int a = (int)(s & 15);
         const int nblocks = (a + len + 15) >> 4;
@@ -213,10 +259,7 @@ __global__ void __launch_bounds__(kSparseWarps * 32) sparse_short_kernel(
         __syncwarp();
         KeyT* ko = keys + row_begin[r];
         uint32_t* co = counts + row_begin[r];
-        int nd;
-        if (nwin <= 128) nd = warp_count_read<KeyT, 4>(st, a, nwin, k, ko, co);
-        else if (nwin <= 256) nd = warp_count_read<KeyT, 8>(st, a, nwin, k, ko, co);
-        else nd = warp_count_read<KeyT, 16>(st, a, nwin, k, ko, co);
+        const int nd = warp_count_read<KeyT, E>(st, a, nwin, k, ko, co, s_stage_k[warp], s_stage_c[warp]);
         if (lane == 0) row_count[r] = nd;
     }
 }
@@ -384,9 +427,13 @@ static cudaError_t sparse_impl(const void* bases, const int64_t* start, const in
     {
         const int64_t ctas = (nS + kSparseWarps - 1) / kSparseWarps;
         const unsigned grid = (unsigned)(ctas < (int64_t)num_sms * 8 ? ctas : (int64_t)num_sms * 8);
-        sparse_short_kernel<KeyT, FMT><<<grid, kSparseWarps * 32, 0, st>>>(
-            static_cast<const uint8_t*>(bases), start, length, nS, k, row_begin, row_count, keys, counts);
-        count_launch();
+        // which classes occur is not known on the host without a pass over the lengths: launch all
+        // three; a class without reads costs one pass over length[] (4 B/read)
+        const uint8_t* b8 = static_cast<const uint8_t*>(bases);
+        sparse_short_kernel<KeyT, FMT, 4><<<grid, SparseCta<4>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts);
+        sparse_short_kernel<KeyT, FMT, 8><<<grid, SparseCta<8>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts);
+        sparse_short_kernel<KeyT, FMT, 16><<<grid, SparseCta<16>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts);
+        count_launch(); count_launch(); count_launch();
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
 

@@ -85,3 +85,28 @@ def test_pageable_and_unaligned_host_buffers():
     view[:] = data
     for k in (2, 4, 8):
         np.testing.assert_array_equal(cf.kmer_main(view, start, length, k), ob.count_dense_fast(data, start, length, k))
+
+
+@pytest.mark.parametrize("k", [1, 3, 4, 5, 6, 7, 8])
+def test_long_sequences_dense(k):
+    """sequences far beyond the reference's 1024-window cap: exact mode counts every window,
+    compat mode stops at 1024; mixed with short reads so tiles hold both"""
+    import random
+    rng = random.Random(100 + k)
+    lens = [200_000, 150, 1500, 0, 70_000, 3, 150, 150, 33_333]
+    reads = []
+    for L in lens:
+        s = [rng.choice("ACGT") for _ in range(L)]
+        for _ in range(L // 5000):
+            s[rng.randrange(L)] = "N"
+        reads.append("".join(s))
+    reads += ["ACGT" * 40] * 20      # clean tail so the empty read's walk stays inside the buffer
+    text = "".join(f">r{i}\n{r}\n" for i, r in enumerate(reads))
+    data, start, length = ob.parse_fasta(text=text)
+    for mode in (cf.MODE_EXACT, cf.MODE_COMPAT):
+        want = ob.count_dense_fast(data, start, length, k, mode)
+        got = cf.count_dense_host(data, start, length, k, mode)
+        np.testing.assert_array_equal(got, want, err_msg=f"k={k} mode={mode}")
+    if k <= 6:
+        np.testing.assert_array_equal(ob.count_dense(data, start, length, k, cf.MODE_EXACT),
+                                      ob.count_dense_fast(data, start, length, k, cf.MODE_EXACT))

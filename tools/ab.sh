@@ -3,6 +3,4 @@ run() { echo "== $1 k=$2"; env $1 python bench.py --steps 3 --warmup 1 --no-cpu 
 import json,sys
 d=json.loads(sys.stdin.read())
 for x in d['per_k']: print('  ', x['k'], x['ms'], x['gbases_s'], x['frac_of_peak'])"; }
-run "CFRK_K6=0" 6
-run "CFRK_K6=1" 6
-run "CFRK_K6=2" 6
+run "X=1" 4,5,6
