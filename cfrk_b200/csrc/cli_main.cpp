@@ -9,6 +9,7 @@
 //     --all-rows   print every read, not only the last nS mod chunkSize
 //     --exact      intended semantics instead of the reference's quirks
 //     --sparse     omit zero bins (the filter commented out at src/main.cu:51,56)
+//                  k = 9..31 needs --sparse --exact: rows of "kmer_index:count " for the k-mers present
 //     --device=N
 // Legacy Swift form (swift/cfrk.swf:5): `cfrk <dataset> <k> <chunkSize>` with numeric 2nd/3rd
 // arguments writes the rows to stdout.

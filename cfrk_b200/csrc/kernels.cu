@@ -177,8 +177,8 @@ struct WarpSink {
 //                 clears them in the same pass and writes them with coalesced 16-byte streaming
 //                 stores.  Half the shared memory per warp -> twice the resident warps, and no wait
 //                 for the TMA engine before the buffer can be reused.
-template <int K, int FMT, int RW, int WARPS, bool DIRECT>
-__global__ void __launch_bounds__(WARPS * 32) dense_warp_kernel(const DenseArgs a)
+template <int K, int FMT, int RW, int WARPS, bool DIRECT, int MINB = 1>
+__global__ void __launch_bounds__(WARPS * 32, MINB) dense_warp_kernel(const DenseArgs a)
 {
     constexpr int BINS = 1 << (2 * K);
     constexpr int TILE_BINS = RW * BINS;
@@ -267,10 +267,10 @@ __global__ void __launch_bounds__(WARPS * 32) dense_warp_kernel(const DenseArgs 
     if (!DIRECT && lane == 0) bulk_wait_all();
 }
 
-template <int K, int FMT, int RW, int WARPS, bool DIRECT = false>
+template <int K, int FMT, int RW, int WARPS, bool DIRECT = false, int MINB = 1>
 static cudaError_t launch_warp_k(const DenseArgs& a0, cudaStream_t st)
 {
-    auto kern = dense_warp_kernel<K, FMT, RW, WARPS, DIRECT>;
+    auto kern = dense_warp_kernel<K, FMT, RW, WARPS, DIRECT, MINB>;
     constexpr int smem = WARPS * (DIRECT ? 1 : 2) * RW * (1 << (2 * K)) * 4 + ((1 << (2 * K)) * 4 < 16 ? 16 : (1 << (2 * K)) * 4);
     static thread_local int configured_dev = -1;
     static thread_local int ctas_per_sm = 0, num_sms = 0;
@@ -516,7 +516,11 @@ static cudaError_t launch_dense_fmt(int k, const DenseArgs& a, cudaStream_t st)
     }
     if (k == 4 && k4_variant == 6) return launch_warp_k<4, FMT, 16, 4, true>(a, st);
     if (k == 4 && k4_variant == 7) return launch_warp_k<4, FMT, 8, 8, true>(a, st);
-    if (k == 5 && k5_variant == 5) return launch_warp_k<5, FMT, 1, 8, true>(a, st);   // 0: CTA 16 KiB/256 thr, 1: 16 KiB/192, 2: 32 KiB/384, 3: warp RW=4
+    if (k == 5 && k5_variant == 5) return launch_warp_k<5, FMT, 1, 8, true>(a, st);
+    if (k == 5 && k5_variant == 6) return launch_warp_k<5, FMT, 1, 4, true, 10>(a, st);
+    if (k == 5 && k5_variant == 7) return launch_warp_k<5, FMT, 1, 4, true, 12>(a, st);
+    if (k == 4 && k4_variant == 8) return launch_warp_k<4, FMT, 4, 4, true, 10>(a, st);
+    if (k == 4 && k4_variant == 9) return launch_warp_k<4, FMT, 4, 4, true, 12>(a, st);   // 0: CTA 16 KiB/256 thr, 1: 16 KiB/192, 2: 32 KiB/384, 3: warp RW=4
     if (k == 5 && k5_variant == 1) return launch_warp_k<5, FMT, 2, 4>(a, st);
     if (k == 5 && k5_variant == 2) return launch_warp_k<5, FMT, 1, 4>(a, st);
     if (k == 4 && k4_variant == 1) return launch_dense_k<4, FMT, 4096, 192>(a, st);

@@ -230,8 +230,8 @@ public:
     {
         f_ = fopen(path, "w");
         if (!f_) { err.code = CFRK_EIO; err.msg = std::string("cannot open output ") + path; return false; }
-        bins_ = (size_t)1 << (2 * k);
-        labels_.reset(new BinLabels(bins_));
+        bins_ = k <= CFRK_DENSE_MAX_K ? (size_t)1 << (2 * k) : 0;
+        if (bins_) labels_.reset(new BinLabels(bins_));
         nt_ = std::max(1, std::min(nt, 64));
         sparse_ = sparse;
         return true;
@@ -246,6 +246,49 @@ public:
             const size_t a = nrows * t / nt, b = nrows * (t + 1) / nt;
             const bool first = first_ && a == 0;
             th.emplace_back([=, &parts] { format_rows(rows + a * bins_, b - a, bins_, *labels_, sparse_, first, parts[t]); });
+        }
+        for (auto& x : th) x.join();
+        first_ = false;
+        for (auto& part : parts)
+            if (!part.empty() && fwrite(part.data(), 1, part.size(), f_) != part.size()) {
+                err.code = CFRK_EIO; err.msg = "short write"; return false;
+            }
+        return true;
+    }
+    // rows given as (key, count) pairs: the same "bin:count " tokens, non-zero bins only
+    bool write_pairs(const int64_t* row_begin, const int32_t* row_count, const uint64_t* keys,
+                     const uint32_t* counts, size_t nrows, Err& err)
+    {
+        if (!nrows) return true;
+        const int nt = (int)std::min<size_t>((size_t)nt_, nrows);
+        std::vector<std::vector<char>> parts(nt);
+        std::vector<std::thread> th;
+        for (int t = 0; t < nt; t++) {
+            const size_t a = nrows * t / nt, b = nrows * (t + 1) / nt;
+            const bool first = first_ && a == 0;
+            th.emplace_back([=, &parts] {
+                size_t npairs = 0;
+                for (size_t r = a; r < b; r++) npairs += (size_t)row_count[r];
+                std::vector<char>& out = parts[t];
+                out.resize(npairs * 33 + (b - a) + 1);   // 20 + 1 + 10 + 1 per token, '\n' per row
+                char* p = out.data();
+                for (size_t r = a; r < b; r++) {
+                    if (!(first && r == a)) *p++ = '\n';
+                    const uint64_t* kk = keys + row_begin[r];
+                    const uint32_t* cc = counts + row_begin[r];
+                    for (int32_t i = 0; i < row_count[r]; i++) {
+                        char tmp[24];
+                        int l = 0;
+                        uint64_t u = kk[i];
+                        do { tmp[l++] = (char)('0' + u % 10); u /= 10; } while (u);
+                        while (l) *p++ = tmp[--l];
+                        *p++ = ':';
+                        p = put_int(p, (int32_t)cc[i]);
+                        *p++ = ' ';
+                    }
+                }
+                out.resize((size_t)(p - out.data()));
+            });
         }
         for (auto& x : th) x.join();
         first_ = false;
@@ -351,6 +394,41 @@ struct Pipeline {
         if (mode == CFRK_MODE_COMPAT && std::find(ri.length.begin(), ri.length.end(), 0) != ri.length.end())
             return run(h_in, in_bytes, ri, nrows, k, mode, chunk_size, index_base, w, err);   // needs the packed layout
         return count_rows(in_bytes, ri.start.size(), nrows, k, mode, chunk_size, index_base, w, err);
+    }
+    // k > 8: sparse rows (exact semantics) of the span that upload_and_scan() left in HBM
+    bool count_scanned_sparse(size_t in_bytes, const RecordIndex& ri, size_t nrows, int k, CfrkWriter& w, Err& err)
+    {
+        if (nrows == 0) return true;
+        const size_t nreads = ri.start.size();
+        int64_t cap = 0;
+        for (int32_t l : ri.length) cap += std::max(0, l - k + 1);
+        int64_t* d_rb = nullptr; int32_t* d_rc = nullptr; uint64_t* d_k = nullptr; uint32_t* d_c = nullptr;
+        RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_rb), (nreads + 1) * 8));
+        RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_rc), nreads * 4));
+        RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_k), (size_t)std::max<int64_t>(cap, 1) * 8));
+        RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_c), (size_t)std::max<int64_t>(cap, 1) * 4));
+        int64_t total = 0;
+        cudaError_t e = cfrk::launch_sparse(d_in, cfrk::FMT_ASCII, d_start, d_length, (int64_t)nreads, k, d_rb, d_rc, d_k, 8,
+                                            d_c, cap, &total, compute);
+        bool ok = e == cudaSuccess;
+        if (!ok) { err.code = CFRK_ECUDA; err.msg = std::string("sparse path: ") + cudaGetErrorString(e); }
+        std::vector<int64_t> rb(nrows + 1);
+        std::vector<int32_t> rc(nrows);
+        std::vector<uint64_t> kk;
+        std::vector<uint32_t> cc;
+        if (ok) {
+            ok = cudaMemcpyAsync(rb.data(), d_rb, (nrows + 1) * 8, cudaMemcpyDeviceToHost, compute) == cudaSuccess &&
+                 cudaMemcpyAsync(rc.data(), d_rc, nrows * 4, cudaMemcpyDeviceToHost, compute) == cudaSuccess &&
+                 cudaStreamSynchronize(compute) == cudaSuccess;
+            const size_t used = (size_t)rb[nrows];
+            kk.resize(std::max<size_t>(used, 1)); cc.resize(std::max<size_t>(used, 1));
+            ok = ok && cudaMemcpy(kk.data(), d_k, used * 8, cudaMemcpyDeviceToHost) == cudaSuccess &&
+                 cudaMemcpy(cc.data(), d_c, used * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
+            if (!ok) { err.code = CFRK_ECUDA; err.msg = "sparse path: device to host copy failed"; }
+        }
+        cudaFree(d_rb); cudaFree(d_rc); cudaFree(d_k); cudaFree(d_c);
+        (void)in_bytes;
+        return ok && w.write_pairs(rb.data(), rc.data(), kk.data(), cc.data(), nrows, err);
     }
     // Host-side record table (the rare packed layout): upload bytes + table, then count.
     bool run(const char* h_in, size_t in_bytes, const RecordIndex& ri_in, size_t nrows, int k, int mode,
@@ -500,7 +578,8 @@ bool run_file(const char* fasta, const char* out_path, int k, int nt, int64_t ch
                     held += (size_t)ri.length[nrows] + 1;
                 }
             }
-            if (!gpu.count_scanned(data, n, ri, nrows, k, mode, chunk_size, reads_done, w, err)) return false;
+            if (k > CFRK_DENSE_MAX_K ? !gpu.count_scanned_sparse(n, ri, nrows, k, w, err)
+                                     : !gpu.count_scanned(data, n, ri, nrows, k, mode, chunk_size, reads_done, w, err)) return false;
             reads_done += (int64_t)nrows;
             tr.mark("rows counted + written");
             keep_from = b->eof ? n : (m ? ri.header[nrows] : 0);
@@ -541,7 +620,9 @@ bool run_file(const char* fasta, const char* out_path, int k, int nt, int64_t ch
             bool ok = got == bytes && gpu.upload_and_scan(h, bytes, true, ri, err);
             if (got != bytes) { err.code = CFRK_EIO; err.msg = "short read of the tail chunk"; }
             tr.mark("tail chunk scanned", bytes);
-            if (ok) ok = gpu.count_scanned(h, bytes, ri, ri.start.size(), k, mode, chunk_size, (nS / chunk_size) * chunk_size, w, err);
+            if (ok) ok = k > CFRK_DENSE_MAX_K
+                             ? gpu.count_scanned_sparse(bytes, ri, ri.start.size(), k, w, err)
+                             : gpu.count_scanned(h, bytes, ri, ri.start.size(), k, mode, chunk_size, (nS / chunk_size) * chunk_size, w, err);
             tr.mark("tail rows counted + written");
             cudaFreeHost(h);
             if (!ok) return false;
@@ -557,7 +638,11 @@ extern "C" int cfrk_run_file(const char* fasta_path, const char* out_path, int k
 {
     Err err;
     if (!fasta_path || !out_path) { err.code = CFRK_EINVAL; err.msg = "null path"; }
-    else if (k < 1 || k > CFRK_DENSE_MAX_K) { err.code = CFRK_EINVAL; err.msg = "k must be in 1..8 for dense .cfrk output"; }
+    else if (k < 1 || k > CFRK_SPARSE_MAX_K) { err.code = CFRK_EINVAL; err.msg = "k must be in 1..31"; }
+    else if (k > CFRK_DENSE_MAX_K && (flags & (CFRK_RUN_SPARSE | CFRK_RUN_EXACT)) != (CFRK_RUN_SPARSE | CFRK_RUN_EXACT)) {
+        err.code = CFRK_EINVAL;
+        err.msg = "k > 8: rows have 4^k bins; pass --sparse --exact (non-zero bins only, intended semantics)";
+    }
     else if (chunk_size <= 0) { err.code = CFRK_EINVAL; err.msg = "chunkSize must be positive"; }
     else {
         int ndev = 0;

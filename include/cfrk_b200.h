@@ -157,7 +157,9 @@ int cfrk_scan_fasta_device(const void *d_bytes, int64_t n, int is_final, int64_t
 
 /*
  * cfrk <fasta> <out> <k> [nt] [chunkSize] as a function: pinned double-buffered FASTA
- * streamer -> GPU count -> multi-threaded .cfrk writer.  nt = host writer threads.
+ * streamer -> GPU record scan + count -> multi-threaded .cfrk writer.  nt = host writer threads.
+ * k <= 8: dense rows (reference format).  k = 9..31 needs CFRK_RUN_SPARSE | CFRK_RUN_EXACT:
+ * each row lists "kmer_index:count " for the k-mers that occur, in increasing index order.
  */
 int cfrk_run_file(const char *fasta_path, const char *out_path, int k, int nt,
                   int64_t chunk_size, int flags, int device);

@@ -116,3 +116,22 @@ def test_swift_legacy_form(tmp_path):
     want = tmp_path / "want"
     ob.run_cli(str(fa), str(want), 2, 4096)
     assert r.stdout == want.read_bytes()
+
+
+@pytest.mark.parametrize("k", [9, 12, 21, 31])
+def test_sparse_rows_for_large_k(tmp_path, k):
+    """k > 8: --sparse --exact rows = the oracle's sorted (k-mer, count) pairs"""
+    fa = tmp_path / "in.fa"
+    text = fx.fx_with_n() + fx.fx_long() + fx.fx_short()
+    fa.write_text(text)
+    out = tmp_path / "out.cfrk"
+    run_cfrk(fa, out, k, 4, 8192, "--all-rows", "--sparse", "--exact")
+    data, start, length = ob.parse_fasta(text=text)
+    rp, keys, cnt = ob.count_sparse(data, start, length, k)
+    lines = out.read_bytes().split(b"\n")
+    assert len(lines) == len(start)
+    for i, line in enumerate(lines):
+        toks = [tuple(map(int, t.split(b":"))) for t in line.split()]
+        assert toks == list(zip(keys[rp[i]:rp[i + 1]].tolist(), cnt[rp[i]:rp[i + 1]].tolist())), f"row {i}"
+    r = subprocess.run([CFRK, str(fa), str(out), str(k)], capture_output=True)     # dense k > 8 is refused
+    assert r.returncode == 1 and b"--sparse --exact" in r.stderr
