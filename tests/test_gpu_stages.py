@@ -166,3 +166,31 @@ def test_scan_fasta_device_errors():
         cf.scan_fasta_device(buf.data_ptr(), len(raw), True, z.data_ptr(), z.clone().data_ptr(),
                              torch.zeros(2, dtype=torch.int32, device="cuda").data_ptr(), 2)
     assert e.value.code == -1
+
+
+@pytest.mark.parametrize("k,nS", [(6, 400_000), (7, 150_000), (8, 40_000)])
+def test_big_rows_under_load(k, nS):
+    """~10 GB of rows per launch: every TMA zero store must land before the reductions of its tile
+    (a lost or clobbered count shows up in the row sums), and a strided sample equals the oracle"""
+    L = 150
+    g = torch.Generator(device="cuda"); g.manual_seed(k)
+    codes = torch.randint(0, 4, (nS, L + 1), dtype=torch.uint8, device="cuda", generator=g)
+    codes[:, L] = 0xFF
+    flat = torch.cat([codes.view(-1), torch.full((16,), 0xFF, dtype=torch.uint8, device="cuda")])
+    start = torch.arange(nS, dtype=torch.int64, device="cuda") * (L + 1)
+    length = torch.full((nS,), L, dtype=torch.int32, device="cuda")
+    out = torch.full((nS, 4 ** k), 7, dtype=torch.int32, device="cuda")     # poisoned
+    for rep in range(2):
+        cf.count_dense_device(flat.data_ptr(), start.data_ptr(), length.data_ptr(), nS * (L + 1), nS, k, out.data_ptr())
+    torch.cuda.synchronize()
+    sums = torch.empty(nS, dtype=torch.int64, device="cuda")
+    for a in range(0, nS, 8192):
+        sums[a:a + 8192] = out[a:a + 8192].sum(1, dtype=torch.int64)
+    assert int(sums[:-1].min()) == int(sums[:-1].max()) == (L - k + 1) + (k - 2)
+    assert int(sums[-1]) == L - k + 1
+    assert int(out.min()) == 0
+    h = codes.cpu().numpy().view(np.int8)
+    for i in list(range(0, nS, nS // 23))[:23]:
+        hi = min(nS, i + 2)
+        want = ob.count_dense(h[i:hi].reshape(-1), np.arange(hi - i) * (L + 1), np.full(hi - i, L), k)[0]
+        np.testing.assert_array_equal(out[i].cpu().numpy(), want)
