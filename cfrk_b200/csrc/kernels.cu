@@ -75,6 +75,7 @@ struct DenseArgs {
     int64_t num_tiles;
     int64_t chunk_size;   // compat: reads with (index_base + i) % chunk_size == 0 start a reference
     int64_t index_base;   //         chunk (their spill is dropped); 0 = only read 0 does
+    int flags;            // bit 0: big-row path zeroes with plain stores instead of TMA (A/B switch)
 };
 
 template <int K, int FMT, int TILE_BINS_T, int NTHREADS, int NBUF>
@@ -327,14 +328,15 @@ struct BigRowSink {
     using G = BigGeo<K, TILE_BYTES>;
     static constexpr bool kCtaUniform = true;
     static constexpr bool kSharedRows = false;
+    bool tma;         // zeros were streamed by TMA (wait for the bulk group) or by plain stores
     uint32_t* rows;   // row of table-local read 0
     int sub;          // which slice of the row this tile covers (SUB > 1)
     bool has_last;
     int qb, period;   // chunk openers (see DenseSink)
     __device__ __forceinline__ void before_first_emit()
     {
-        if (threadIdx.x == 0) { bulk_wait_all(); fence_async_proxy_global(); }
-        __syncthreads();
+        if (tma && threadIdx.x == 0) { bulk_wait_all(); fence_async_proxy_global(); }
+        __syncthreads();   // plain stores: the barrier orders them before the CTA's reductions
     }
     __device__ __forceinline__ void kmer(int q, uint32_t idx)
     {
@@ -390,7 +392,13 @@ __global__ void __launch_bounds__(kBigThreads) dense_bigrow_kernel(const DenseAr
         const int nreads = nrows + (halo ? 1 : 0);
         uint32_t* rows = a.out + (r0 - a.read_begin) * G::BINS;
 
-        if (threadIdx.x == 0) {  // 1. zero stream
+        if (a.flags & 1) {       // 1'. zero stream by plain 16-byte stores from every thread
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(rows) + (int64_t)sub * TILE_BYTES);
+            const int n16 = (int)((G::SUB > 1 ? (int64_t)TILE_BYTES : (int64_t)nrows * G::ROW_BYTES) / 16);
+#pragma unroll 4
+            for (int i = threadIdx.x; i < n16; i += kBigThreads)
+                asm volatile("st.global.v4.u32 [%0], {%1,%1,%1,%1};" :: "l"(dst + i), "r"(0u) : "memory");
+        } else if (threadIdx.x == 0) {  // 1. zero stream by TMA
             unsigned char* dst = reinterpret_cast<unsigned char*>(rows) + (int64_t)sub * TILE_BYTES;
             int64_t left = G::SUB > 1 ? (int64_t)TILE_BYTES : (int64_t)nrows * G::ROW_BYTES;
             while (left > 0) {
@@ -404,7 +412,7 @@ __global__ void __launch_bounds__(kBigThreads) dense_bigrow_kernel(const DenseAr
         __syncthreads();
         if (threadIdx.x < 32) scan_read_table(tb, nreads);
         __syncthreads();
-        BigRowSink<K, TILE_BYTES> sink{rows, sub, has_last, qb, period};
+        BigRowSink<K, TILE_BYTES> sink{(a.flags & 1) == 0, rows, sub, has_last, qb, period};
         for_each_window<K, FMT, G::TABLE_READS>(a.bases, tb, nreads, nrows, a.mode, sink);  // 2. + 3.
         __syncthreads();  // table is reused by the next tile
     }
@@ -572,6 +580,8 @@ cudaError_t launch_dense(const void* bases, int fmt, const int64_t* start, const
     a.out = reinterpret_cast<uint32_t*>(out);
     a.mode = mode; a.num_tiles = 0;
     a.chunk_size = chunk_size; a.index_base = index_base;
+    static const int big_plain = env_int("CFRK_BIG_PLAIN", 0);
+    a.flags = big_plain ? 1 : 0;
     return fmt == FMT_ASCII ? launch_dense_fmt<FMT_ASCII>(k, a, st) : launch_dense_fmt<FMT_CODES>(k, a, st);
 }
 

@@ -1,5 +1,5 @@
 import os, subprocess, sys
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import fixtures as fx, oracle_binding as ob
 out = os.path.join(ROOT, "gpurun_out", "dbg"); os.makedirs(out, exist_ok=True)
