@@ -11,6 +11,7 @@
 
 #include <atomic>
 #include <cstdlib>
+#include <vector>
 
 namespace cfrk {
 
@@ -22,6 +23,37 @@ static int env_int(const char* name, int dflt)
 {
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
+}
+
+// Small device scratch that survives between launches: one buffer per (host thread, device, stream),
+// grown on demand.  Launches of one stream are ordered, so they can share it; different streams
+// and different host threads get their own.  (cudaMallocAsync per launch stalled the host for
+// about a millisecond per launch -- visible at k=4, where a whole sweep takes 2.6 ms.)
+static cudaError_t stream_scratch(cudaStream_t st, size_t bytes, void** out)
+{
+    struct Slot { int dev; cudaStream_t st; void* p; size_t cap; };
+    static thread_local std::vector<Slot> slots;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    for (Slot& s : slots) {
+        if (s.dev == dev && s.st == st) {
+            if (s.cap < bytes) {
+                if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;   // last user may still run
+                cudaFree(s.p);
+                s.p = nullptr; s.cap = 0;
+                if ((e = cudaMalloc(&s.p, bytes + bytes / 4)) != cudaSuccess) return e;
+                s.cap = bytes + bytes / 4;
+            }
+            *out = s.p;
+            return cudaSuccess;
+        }
+    }
+    Slot s{dev, st, nullptr, bytes + bytes / 4};
+    if ((e = cudaMalloc(&s.p, s.cap)) != cudaSuccess) return e;
+    slots.push_back(s);
+    *out = s.p;
+    return cudaSuccess;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -54,11 +86,11 @@ struct DenseSink {
     // the reference adds at Freq[4^k*i + (-1)]: last bin of read i-1 (src/kmer_kernel.cu:84-87);
     // q == 0 belongs to the previous tile (counted there through its halo read); for the first
     // read of a reference chunk (a separate kmer_main call) it is the lost Freq[-1] store.
-    __device__ __forceinline__ void invalid(int q, int n)
+    __device__ __forceinline__ void invalid(int q, int in_read, int extra)
     {
         if (period > 0 && q >= qb && (q - qb) % period == 0) return;
         if (q >= 1)
-            asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(row_saddr(q) - 4u), "r"((uint32_t)n) : "memory");
+            asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(row_saddr(q) - 4u), "r"((uint32_t)(in_read + extra)) : "memory");
     }
 };
 
@@ -76,6 +108,7 @@ struct DenseArgs {
     int64_t chunk_size;   // compat: reads with (index_base + i) % chunk_size == 0 start a reference
     int64_t index_base;   //         chunk (their spill is dropped); 0 = only read 0 does
     int flags;            // bit 0: big-row path zeroes with plain stores instead of TMA (A/B switch)
+    uint32_t* handoff;    // warp tiles, compat: one word per tile boundary (zeroed), or null
 };
 
 template <int K, int FMT, int TILE_BINS_T, int NTHREADS, int NBUF>
@@ -164,12 +197,15 @@ struct WarpSink {
     static constexpr int BINS = 1 << (2 * K);
     uint32_t hist_saddr;
     int qb, period;
+    int carry0;   // per lane: data-dependent invalid windows of the tile's FIRST read (owed to the previous tile)
     __device__ __forceinline__ uint32_t row_saddr(int q) const { return hist_saddr + (uint32_t)q * (BINS * 4); }
-    __device__ __forceinline__ void invalid(int q, int n)
+    __device__ __forceinline__ void invalid(int q, int in_read, int extra)
     {
         if (period > 0 && q >= qb && (q - qb) % period == 0) return;
         if (q >= 1)
-            asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(row_saddr(q) - 4u), "r"((uint32_t)n) : "memory");
+            asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(row_saddr(q) - 4u), "r"((uint32_t)(in_read + extra)) : "memory");
+        else
+            carry0 += in_read;   // its `extra` was added by the previous tile from the read length alone
     }
 };
 
@@ -224,8 +260,17 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dense_warp_kernel(const Dens
         }
         const bool next_opens_chunk = period > 0 && nrows >= qb && (nrows - qb) % period == 0;
         const bool halo = a.mode == MODE_COMPAT && (r0 + nrows < a.nS) && !next_opens_chunk;
-        const int nreads = nrows + (halo ? 1 : 0);
-        const LaneRead lr = make_lane_read<K>(lane < nreads, s, len, a.mode, a.nN);
+        // The spill of the read after the tile (read r0+nrows) into the tile's last row:
+        //   * its length-only part (`extra`) is added here from length[] alone;
+        //   * its data-dependent part (windows holding a non-ACGT byte; zero for clean reads) is
+        //     recorded by the tile that owns that read in a.handoff[this tile] and added by
+        //     spill_fixup_kernel after this kernel -- the kernel boundary is the only ordering
+        //     needed (a fence + atomic handshake inside the kernel cost 3x the run time at k=4).
+        // Without a.handoff, and for the last tile of a launch (the owner is another launch), the
+        // read is scanned here as a halo read instead.
+        const bool scan_halo = halo && (a.handoff == nullptr || tile == a.num_tiles - 1);
+        const int nreads = nrows + (scan_halo ? 1 : 0);
+        const LaneRead lr = make_lane_read<K>(lane < nrows + (halo ? 1 : 0), lane < nreads, s, len, a.mode, a.nN);
 
         const int64_t next_tile = tile + nwarps;
         if (next_tile < a.num_tiles) {  // prefetch the next tile's offsets
@@ -242,9 +287,14 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dense_warp_kernel(const Dens
             for (int i = lane; i < TILE_BYTES / 16; i += 32) h4[i] = make_uint4(0u, 0u, 0u, 0u);
             __syncwarp();
         }
-        WarpSink<K> sink{(uint32_t)__cvta_generic_to_shared(hist), qb, period};
+        WarpSink<K> sink{(uint32_t)__cvta_generic_to_shared(hist), qb, period, 0};
         warp_for_each_window<K, FMT, RW + 1>(a.bases, lr, nreads, nrows, a.mode, sink);
         uint32_t* dst = a.out + (r0 - a.read_begin) * BINS;
+        if (halo && !scan_halo) {   // length-only part of the next read's spill
+            const int ex = __shfl_sync(0xffffffffu, lr.extra, nrows);
+            __syncwarp();
+            if (lane == 0 && ex > 0) hist[nrows * BINS - 1] += (uint32_t)ex;
+        }
         if (DIRECT) {
             __syncwarp();
             uint4* h4 = reinterpret_cast<uint4*>(hist);
@@ -263,9 +313,27 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dense_warp_kernel(const Dens
             __syncwarp();
             if (lane == 0) bulk_store_tile(dst, hist, (uint32_t)nrows * BINS * 4u);
         }
+        if (DIRECT && a.handoff != nullptr && a.mode == MODE_COMPAT) {
+            int c0 = sink.carry0;
+#pragma unroll
+            for (int d = 16; d >= 1; d >>= 1) c0 += __shfl_xor_sync(0xffffffffu, c0, d);
+            const bool q0_opens_chunk = period > 0 && qb == 0;
+            if (lane == 0 && c0 > 0 && tile != 0 && !q0_opens_chunk) a.handoff[tile - 1] = (uint32_t)c0;
+        }
         tile = next_tile;
     }
     if (!DIRECT && lane == 0) bulk_wait_all();
+}
+
+// handoff[t] != 0: the first read of tile t+1 had that many invalid windows -> last bin of the
+// last row of tile t (rows_per_tile * bins int32 per tile)
+__global__ void spill_fixup_kernel(const uint32_t* __restrict__ handoff, int64_t ntiles, uint32_t* __restrict__ out,
+                                   int64_t tile_bins)
+{
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ntiles - 1; t += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t v = handoff[t];
+        if (v) out[(t + 1) * tile_bins - 1] += v;
+    }
 }
 
 template <int K, int FMT, int RW, int WARPS, bool DIRECT = false, int MINB = 1>
@@ -294,9 +362,23 @@ static cudaError_t launch_warp_k(const DenseArgs& a0, cudaStream_t st)
     const int64_t ctas_needed = (a.num_tiles + WARPS - 1) / WARPS;
     const int64_t resident = (int64_t)num_sms * ctas_per_sm;
     const unsigned grid = (unsigned)(ctas_needed < resident ? ctas_needed : resident);
+    static const int use_handoff = env_int("CFRK_HANDOFF", 1);
+    if (DIRECT && use_handoff && a.mode == MODE_COMPAT && a.num_tiles > 1) {
+        // one word per tile boundary, zeroed for this launch
+        if ((e = stream_scratch(st, (size_t)a.num_tiles * 4, reinterpret_cast<void**>(&a.handoff))) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(a.handoff, 0, (size_t)a.num_tiles * 4, st)) != cudaSuccess) return e;
+    }
     kern<<<grid, WARPS * 32, smem, st>>>(a);
     g_launches.fetch_add(1);
-    return cudaGetLastError();
+    e = cudaGetLastError();
+    if (a.handoff) {
+        const int64_t blocks = (a.num_tiles + 255) / 256;
+        spill_fixup_kernel<<<(unsigned)(blocks < 2368 ? blocks : 2368), 256, 0, st>>>(
+            a.handoff, a.num_tiles, a.out, (int64_t)RW * (1 << (2 * K)));
+        g_launches.fetch_add(1);
+        if (e == cudaSuccess) e = cudaGetLastError();
+    }
+    return e;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -343,10 +425,10 @@ struct BigRowSink {
         if (G::SUB > 1 && (int)(idx / G::TILE_BINS) != sub) return;
         atomicAdd(rows + (int64_t)q * G::BINS + idx, 1u);
     }
-    __device__ __forceinline__ void invalid(int q, int n)
+    __device__ __forceinline__ void invalid(int q, int in_read, int extra)
     {
         if (period > 0 && q >= qb && (q - qb) % period == 0) return;
-        if (q >= 1 && has_last) atomicAdd(rows + (int64_t)q * G::BINS - 1, (uint32_t)n);
+        if (q >= 1 && has_last) atomicAdd(rows + (int64_t)q * G::BINS - 1, (uint32_t)(in_read + extra));
     }
 };
 
@@ -507,43 +589,36 @@ static cudaError_t launch_dense_k(const DenseArgs& a0, cudaStream_t st)
 template <int FMT>
 static cudaError_t launch_dense_fmt(int k, const DenseArgs& a, cudaStream_t st)
 {
-    // k <= CFRK_WARP_MAX_K: warp-autonomous tiles; else the CTA-cooperative tile kernel
-    // tuning switches (A/B measurements, profiles/r1_notes.md); the defaults are the measured best
-    static const int k5_variant = env_int("CFRK_K5", 3);   // 0: CTA tiles, 1: warp tiles RW=2, 2: warp tiles RW=1
-    static const int k4_variant = env_int("CFRK_K4", 5);
-    static const int k123_variant = env_int("CFRK_K123", 0);  // 0: CTA tiles, 1: warp tiles (direct) RW=16, 2: RW=31
-    if (k <= 3 && k123_variant == 1) {
-        if (k == 1) return launch_warp_k<1, FMT, 16, 4, true>(a, st);
-        if (k == 2) return launch_warp_k<2, FMT, 16, 4, true>(a, st);
-        return launch_warp_k<3, FMT, 16, 4, true>(a, st);
+    // Which kernel serves which k is a measured choice (profiles/r1_notes.md).  The environment
+    // switches below exist to re-run those A/B measurements; the defaults are the winners.
+    //   launch_warp_k<K, FMT, RW, WARPS, DIRECT>: warp tiles of RW rows, WARPS warps per CTA,
+    //   DIRECT = read-clear-store (one buffer) instead of TMA stores (two buffers).
+    static const int k4_variant = env_int("CFRK_K4", 0);
+    static const int k5_variant = env_int("CFRK_K5", 0);
+    if (k == 4) {
+        switch (k4_variant) {
+        case 1: return launch_dense_k<4, FMT, 4096, 256>(a, st);      // CTA tiles 16 KiB            0.64
+        case 2: return launch_dense_k<4, FMT, 4096, 192>(a, st);      // CTA tiles, 6 warps          0.66
+        case 3: return launch_warp_k<4, FMT, 4, 4, false>(a, st);     // warp tiles + TMA, RW=4      0.60
+        case 4: return launch_warp_k<4, FMT, 8, 4, true>(a, st);      // direct, RW=8 (93 items)     0.69-0.75
+        case 5: return launch_warp_k<4, FMT, 16, 4, true>(a, st);     // direct, RW=16               0.53
+        default: return launch_warp_k<4, FMT, 9, 4, true>(a, st);     // direct, RW=9 (93 items, no halo scan) +2.5 %
+        }
     }
-    if (k <= 3 && k123_variant == 2) {
-        if (k == 1) return launch_warp_k<1, FMT, 31, 4, true>(a, st);
-        if (k == 2) return launch_warp_k<2, FMT, 31, 4, true>(a, st);
-        return launch_warp_k<3, FMT, 31, 4, true>(a, st);
+    if (k == 5) {
+        switch (k5_variant) {
+        case 1: return launch_dense_k<5, FMT>(a, st);                 // CTA tiles                   0.70
+        case 2: return launch_warp_k<5, FMT, 1, 4, false>(a, st);     // warp tiles + TMA, RW=1      0.79
+        case 3: return launch_warp_k<5, FMT, 1, 4, true>(a, st);      // direct, RW=1                0.77-0.87
+        case 4: return launch_warp_k<5, FMT, 2, 4, true>(a, st);      // direct, RW=2                0.89
+        case 5: return launch_warp_k<5, FMT, 3, 4, true>(a, st);      // direct, RW=3, 4 warps       0.85
+        default: return launch_warp_k<5, FMT, 3, 3, true>(a, st);     // direct, RW=3 (31 items = one full chunk), 3 warps  0.91
+        }
     }
-    if (k == 4 && k4_variant == 6) return launch_warp_k<4, FMT, 16, 4, true>(a, st);
-    if (k == 4 && k4_variant == 7) return launch_warp_k<4, FMT, 8, 8, true>(a, st);
-    if (k == 5 && k5_variant == 5) return launch_warp_k<5, FMT, 1, 8, true>(a, st);
-    if (k == 5 && k5_variant == 6) return launch_warp_k<5, FMT, 1, 4, true, 10>(a, st);
-    if (k == 5 && k5_variant == 7) return launch_warp_k<5, FMT, 1, 4, true, 12>(a, st);
-    if (k == 4 && k4_variant == 8) return launch_warp_k<4, FMT, 4, 4, true, 10>(a, st);
-    if (k == 4 && k4_variant == 9) return launch_warp_k<4, FMT, 4, 4, true, 12>(a, st);   // 0: CTA 16 KiB/256 thr, 1: 16 KiB/192, 2: 32 KiB/384, 3: warp RW=4
-    if (k == 5 && k5_variant == 1) return launch_warp_k<5, FMT, 2, 4>(a, st);
-    if (k == 5 && k5_variant == 2) return launch_warp_k<5, FMT, 1, 4>(a, st);
-    if (k == 4 && k4_variant == 1) return launch_dense_k<4, FMT, 4096, 192>(a, st);
-    if (k == 4 && k4_variant == 2) return launch_dense_k<4, FMT, 8192, 384>(a, st);
-    if (k == 4 && k4_variant == 3) return launch_warp_k<4, FMT, 4, 4>(a, st);
-    if (k == 4 && k4_variant == 4) return launch_warp_k<4, FMT, 4, 4, true>(a, st);
-    if (k == 4 && k4_variant == 5) return launch_warp_k<4, FMT, 8, 4, true>(a, st);
-    if (k == 5 && k5_variant == 3) return launch_warp_k<5, FMT, 1, 4, true>(a, st);
-    if (k == 5 && k5_variant == 4) return launch_warp_k<5, FMT, 2, 4, true>(a, st);
     switch (k) {
     case 1: return launch_dense_k<1, FMT>(a, st);
     case 2: return launch_dense_k<2, FMT>(a, st);
     case 3: return launch_dense_k<3, FMT>(a, st);
-    case 4: return launch_dense_k<4, FMT>(a, st);
-    case 5: return launch_dense_k<5, FMT>(a, st);
     case 6: {
         static const int k6_variant = env_int("CFRK_K6", 2);  // 0: big-row path, 1/2: warp tiles (direct), 3: CTA tiles
         if (k6_variant == 1) return launch_warp_k<6, FMT, 1, 4, true>(a, st);
@@ -582,6 +657,7 @@ cudaError_t launch_dense(const void* bases, int fmt, const int64_t* start, const
     a.chunk_size = chunk_size; a.index_base = index_base;
     static const int big_plain = env_int("CFRK_BIG_PLAIN", 0);
     a.flags = big_plain ? 1 : 0;
+    a.handoff = nullptr;
     return fmt == FMT_ASCII ? launch_dense_fmt<FMT_ASCII>(k, a, st) : launch_dense_fmt<FMT_CODES>(k, a, st);
 }
 
@@ -595,7 +671,7 @@ struct HistSink {
     static constexpr bool kSharedRows = false;
     uint32_t* hist;
     __device__ __forceinline__ void kmer(int, uint32_t idx) { atomicAdd(&hist[idx], 1u); }
-    __device__ __forceinline__ void invalid(int, int) {}
+    __device__ __forceinline__ void invalid(int, int, int) {}
 };
 struct HistSinkShared {
     static constexpr bool kCtaUniform = false;
@@ -603,7 +679,7 @@ struct HistSinkShared {
     static constexpr bool kRowsAligned = false;
     uint32_t saddr;
     __device__ __forceinline__ uint32_t row_saddr(int) const { return saddr; }
-    __device__ __forceinline__ void invalid(int, int) {}
+    __device__ __forceinline__ void invalid(int, int, int) {}
 };
 
 constexpr int kHistGroup = 128;  // reads per work group

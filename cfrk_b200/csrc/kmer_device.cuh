@@ -176,8 +176,9 @@ struct Item {
 // Everything that follows the load of an item: encode, context from the previous lane, window
 // validity, emission.  Must be called by all 32 lanes (shuffles).  Lane 0 only feeds lane 1.
 //   sink.kmer(q, idx)        one valid window of read q with index idx
-//   sink.invalid(q, count)   compat only: `count` visited windows of read q held a non-ACGT byte
-//                            or the terminator
+//   sink.invalid(q, in_read, extra)   compat only: visited windows of read q that held a non-ACGT
+//                            byte (`in_read`, data dependent) or reached the terminator (`extra`,
+//                            a function of the read length alone, reported with the first block)
 // Reads q >= ncount (the halo read of a compat tile) only report invalid windows.
 template <int K, int FMT, class Sink>
 __device__ __forceinline__ void emit_item(const Item& it, int ncount, int mode, Sink& sink)
@@ -205,8 +206,9 @@ __device__ __forceinline__ void emit_item(const Item& it, int ncount, int mode, 
     for (int i = 1; i < K; i++) ok &= v32 >> i;
     const uint32_t good = it.q < ncount ? (ok & count_mask) : 0u;
     if (mode == MODE_COMPAT) {
-        const int nbad = __popc(~ok & count_mask) + ((counting && it.first_block) ? it.extra : 0);
-        if (nbad) sink.invalid(it.q, nbad);
+        const int nbad = __popc(~ok & count_mask);
+        const int nextra = (counting && it.first_block) ? it.extra : 0;
+        if (nbad | nextra) sink.invalid(it.q, nbad, nextra);
     }
     if constexpr (Sink::kSharedRows) {
         // Rows live in shared memory; when each is aligned to its own size (4^K * 4 bytes,
@@ -299,14 +301,15 @@ struct LaneRead {      // read q = lane q of the warp
     uint32_t nblk, cum;  // 16-byte blocks of this read; exclusive prefix over the tile
 };
 
+// have: the lane describes a read (tend / extra are computed); items: its blocks are enumerated
 template <int K>
-__device__ __forceinline__ LaneRead make_lane_read(bool have, int64_t s, int len, int mode, int64_t nN)
+__device__ __forceinline__ LaneRead make_lane_read(bool have, bool items, int64_t s, int len, int mode, int64_t nN)
 {
     LaneRead lr;
     lr.start = s; lr.tend = 0; lr.extra = 0; lr.nblk = 0; lr.cum = 0;
     if (have) {
         read_extent<K>(mode, len, nN - s, lr.tend, lr.extra);
-        lr.nblk = lr.tend > 0 ? (uint32_t)(((s + lr.tend - 1) >> 4) - (s >> 4) + 1) : 0u;
+        lr.nblk = (items && lr.tend > 0) ? (uint32_t)(((s + lr.tend - 1) >> 4) - (s >> 4) + 1) : 0u;
     }
     uint32_t inc = lr.nblk;
     const int lane = threadIdx.x & 31;
