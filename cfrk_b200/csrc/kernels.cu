@@ -382,6 +382,86 @@ static cudaError_t launch_warp_k(const DenseArgs& a0, cudaStream_t st)
 }
 
 // ------------------------------------------------------------------------------------------
+// One row per CTA (k = 7: 64 KiB rows): the CTA counts one read into a shared-memory row, then all
+// 256 threads read the row out, clear it in the same pass and write it with 16-byte streaming
+// stores.  Same idea as the DIRECT warp tiles, at CTA granularity: no TMA, no L2 reductions, no
+// dependence on the row staying L2-resident.  The spill of the next read is handled like there:
+// length-only part from length[], data part through the hand-off words + spill_fixup_kernel.
+template <int K>
+struct RowSink {
+    static constexpr bool kCtaUniform = false;
+    static constexpr bool kSharedRows = true;
+    static constexpr bool kRowsAligned = false;
+    static constexpr int BINS = 1 << (2 * K);
+    uint32_t hist_saddr;
+    bool drop0;     // read 0 of the table opens a chunk / the launch: its spill is dropped
+    bool scan;      // read 1 of the table is a halo read scanned here (last row of a launch)
+    int carry0;
+    __device__ __forceinline__ uint32_t row_saddr(int) const { return hist_saddr; }
+    __device__ __forceinline__ void invalid(int q, int in_read, int extra)
+    {
+        if (q == 0) { carry0 += in_read; return; }
+        // q == 1: halo read scanned here -> last bin of this row
+        asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(hist_saddr + (uint32_t)(BINS * 4 - 4)), "r"((uint32_t)(in_read + extra)) : "memory");
+    }
+};
+
+constexpr int kRowThreads = 256;
+
+template <int K, int FMT>
+__global__ void __launch_bounds__(kRowThreads) dense_row_kernel(const DenseArgs a)
+{
+    constexpr int BINS = 1 << (2 * K);
+    extern __shared__ __align__(128) unsigned char smem[];
+    uint32_t* hist = reinterpret_cast<uint32_t*>(smem);
+    unsigned char* tp = smem + (size_t)BINS * 4;
+    ReadTable tb;
+    tb.start = reinterpret_cast<int64_t*>(tp);
+    tb.tend = reinterpret_cast<int32_t*>(tp + 2 * 8);
+    tb.extra = reinterpret_cast<int32_t*>(tp + 2 * 12);
+    tb.cum = reinterpret_cast<uint32_t*>(tp + 2 * 16);
+    __shared__ int s_carry;
+
+    for (int i = threadIdx.x; i < BINS / 4; i += kRowThreads) reinterpret_cast<uint4*>(hist)[i] = make_uint4(0u, 0u, 0u, 0u);
+    const int64_t nrows_total = a.read_end - a.read_begin;
+    for (int64_t row = blockIdx.x; row < nrows_total; row += gridDim.x) {
+        const int64_t r = a.read_begin + row;
+        const bool compat = a.mode == MODE_COMPAT;
+        const bool opens = a.chunk_size > 0 ? ((a.index_base + r) % a.chunk_size == 0) : (r == 0);
+        const bool next_opens = a.chunk_size > 0 ? ((a.index_base + r + 1) % a.chunk_size == 0) : false;
+        const bool halo = compat && (r + 1 < a.nS) && !next_opens;
+        const bool scan_halo = halo && (a.handoff == nullptr || row == nrows_total - 1);
+        const int nreads = 1 + (scan_halo ? 1 : 0);
+        if (threadIdx.x == 0) s_carry = 0;
+        fill_read_table<K>(tb, a.start, a.length, r, 1 + (halo ? 1 : 0), a.mode, a.nN);
+        __syncthreads();
+        if (threadIdx.x == 0) {   // 2-entry "scan"
+            const uint32_t n0 = tb.cum[0], n1 = scan_halo ? tb.cum[1] : 0u;
+            tb.cum[0] = 0u; tb.cum[1] = n0; tb.cum[2] = n0 + n1;
+        }
+        __syncthreads();
+        RowSink<K> sink{(uint32_t)__cvta_generic_to_shared(hist), opens, scan_halo, 0};
+        for_each_window<K, FMT, 2>(a.bases, tb, nreads, 1, a.mode, sink);
+        if (sink.carry0) atomicAdd(&s_carry, sink.carry0);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (halo && !scan_halo && tb.extra[1] > 0) hist[BINS - 1] += (uint32_t)tb.extra[1];
+            if (compat && a.handoff != nullptr && s_carry > 0 && row != 0 && !opens) a.handoff[row - 1] = (uint32_t)s_carry;
+        }
+        __syncthreads();
+        uint4* h4 = reinterpret_cast<uint4*>(hist);
+        uint4* d4 = reinterpret_cast<uint4*>(a.out + row * BINS);
+#pragma unroll 4
+        for (int i = threadIdx.x; i < BINS / 4; i += kRowThreads) {
+            const uint4 v = h4[i];
+            h4[i] = make_uint4(0u, 0u, 0u, 0u);
+            asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" :: "l"(d4 + i), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // Big rows (k >= 6: 16 / 64 / 256 KiB per read, of which a read touches <= 1024+1 bins).
 // The row write IS the roofline, so the kernel is a streaming zero-writer with sparse patches:
 //   1. one thread streams the rows of a group of reads as zeros with TMA bulk stores whose source
@@ -395,6 +475,48 @@ static cudaError_t launch_warp_k(const DenseArgs& a0, cudaStream_t st)
 // far below the 126 MB L2: measured on B200 (profiles/r1_notes.md) 888 CTAs x 256 KiB = 227 MB gave
 // 3 % L2 hits for the reductions and 0.65-0.79 of the HBM roofline; 444 x 64 KiB = 28 MB gives 0.91
 // (k=7) and 1.06 (k=8) of the measured copy bandwidth.
+template <int K, int FMT>
+static cudaError_t launch_row_k(const DenseArgs& a0, cudaStream_t st)
+{
+    auto kern = dense_row_kernel<K, FMT>;
+    constexpr int smem = (1 << (2 * K)) * 4 + 2 * 16 + 3 * 4 + 16;
+    static thread_local int configured_dev = -1;
+    static thread_local int ctas_per_sm = 0, num_sms = 0;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (configured_dev != dev) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, kRowThreads, smem);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+        configured_dev = dev;
+    }
+    DenseArgs a = a0;
+    a.num_tiles = a.read_end - a.read_begin;
+    if (a.num_tiles <= 0) return cudaSuccess;
+    const int64_t resident = (int64_t)num_sms * ctas_per_sm;
+    const unsigned grid = (unsigned)(a.num_tiles < resident ? a.num_tiles : resident);
+    if (a.mode == MODE_COMPAT && a.num_tiles > 1) {
+        if ((e = stream_scratch(st, (size_t)a.num_tiles * 4, reinterpret_cast<void**>(&a.handoff))) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(a.handoff, 0, (size_t)a.num_tiles * 4, st)) != cudaSuccess) return e;
+    }
+    kern<<<grid, kRowThreads, smem, st>>>(a);
+    g_launches.fetch_add(1);
+    e = cudaGetLastError();
+    if (a.handoff) {
+        const int64_t blocks = (a.num_tiles + 255) / 256;
+        spill_fixup_kernel<<<(unsigned)(blocks < 2368 ? blocks : 2368), 256, 0, st>>>(a.handoff, a.num_tiles, a.out,
+                                                                                        (int64_t)(1 << (2 * K)));
+        g_launches.fetch_add(1);
+        if (e == cudaSuccess) e = cudaGetLastError();
+    }
+    return e;
+}
+
 template <int K, int TILE_BYTES>
 struct BigGeo {
     static constexpr int BINS = 1 << (2 * K);
@@ -538,8 +660,10 @@ static cudaError_t launch_bigrow_t(const DenseArgs& a0, cudaStream_t st, int cta
 template <int K, int FMT>
 static cudaError_t launch_bigrow_k(const DenseArgs& a, cudaStream_t st)
 {
-    static const int tile_kb = env_int("CFRK_BIG_TILE_KB", 64);
-    static const int ctas = env_int("CFRK_BIG_CTAS", 3);
+    // measured optimum (profiles/r1_notes.md): k=7 32 KiB x 5 CTAs/SM (23.7 MB in flight) 0.965,
+    // k=8 64 KiB x 3 (28.4 MB) 1.06; the curve is sharp (k=7: 32x4 0.81, 32x6 0.92, 64x3 0.93)
+    static const int tile_kb = env_int("CFRK_BIG_TILE_KB", K == 7 ? 32 : 64);
+    static const int ctas = env_int("CFRK_BIG_CTAS", K == 7 ? 5 : 3);
     switch (tile_kb) {
     case 16: return launch_bigrow_t<K, FMT, (16 << 10)>(a, st, ctas);
     case 32: return launch_bigrow_t<K, FMT, (32 << 10)>(a, st, ctas);
@@ -626,7 +750,10 @@ static cudaError_t launch_dense_fmt(int k, const DenseArgs& a, cudaStream_t st)
         if (k6_variant == 3) return launch_dense_k<6, FMT>(a, st);
         return launch_bigrow_k<6, FMT>(a, st);
     }
-    case 7: return launch_bigrow_k<7, FMT>(a, st);
+    case 7: {
+        static const int k7_variant = env_int("CFRK_K7", 0);  // 0: big-row path (TMA zeros + L2 reductions) 0.965, 1: one row per CTA 0.92
+        return k7_variant == 1 ? launch_row_k<7, FMT>(a, st) : launch_bigrow_k<7, FMT>(a, st);
+    }
     case 8: return launch_bigrow_k<8, FMT>(a, st);
     default: return cudaErrorInvalidValue;
     }
