@@ -175,61 +175,82 @@ struct RecordIndex {
 
 // ------------------------------------------------------------------------------------------
 // .cfrk text writer
+// "bin:" labels as fixed 8-byte records (bins < 65536 -> at most "65535:"): one 64-bit store per token
 struct BinLabels {
-    std::vector<char> text;      // "0:" "1:" ...
-    std::vector<uint32_t> off;   // offsets, size bins+1
-    explicit BinLabels(size_t bins)
+    std::vector<uint64_t> rec;
+    std::vector<uint8_t> len;
+    explicit BinLabels(size_t bins) : rec(bins), len(bins)
     {
-        off.resize(bins + 1);
         char tmp[16];
         for (size_t b = 0; b < bins; b++) {
-            off[b] = (uint32_t)text.size();
-            int l = snprintf(tmp, sizeof tmp, "%zu:", b);
-            text.insert(text.end(), tmp, tmp + l);
+            memset(tmp, 0, sizeof tmp);
+            len[b] = (uint8_t)snprintf(tmp, sizeof tmp, "%zu:", b);
+            memcpy(&rec[b], tmp, 8);
         }
-        off[bins] = (uint32_t)text.size();
     }
+};
+
+// output scratch that is NOT value-initialised (a std::vector would zero-fill the worst-case size
+// of every slice: measured as most of the writer's time) and is kept between slices
+struct RawBuf {
+    char* data = nullptr;
+    size_t size = 0, cap = 0;
+    void reserve(size_t n)
+    {
+        if (n > cap) {
+            free(data);
+            data = static_cast<char*>(malloc(n));
+            cap = data ? n : 0;
+        }
+        size = 0;
+    }
+    RawBuf() = default;
+    RawBuf(const RawBuf&) = delete;
+    RawBuf& operator=(const RawBuf&) = delete;
+    ~RawBuf() { free(data); }
 };
 
 inline char* put_int(char* p, int32_t v)
 {
-    if (v < 0) { *p++ = '-'; v = -v; }  // cannot happen (counts), kept for "%d" fidelity
+    uint32_t u = (uint32_t)v;
+    if (v < 0) { *p++ = '-'; u = (uint32_t)(-(int64_t)v); }  // cannot happen (counts), kept for "%d" fidelity
+    if (u < 10) { *p++ = (char)('0' + u); return p; }
+    if (u < 100) { *p++ = (char)('0' + u / 10); *p++ = (char)('0' + u % 10); return p; }
     char tmp[12];
     int l = 0;
-    uint32_t u = (uint32_t)v;
     do { tmp[l++] = (char)('0' + u % 10); u /= 10; } while (u);
     while (l) *p++ = tmp[--l];
     return p;
 }
 
 void format_rows(const int32_t* rows, size_t nrows, size_t bins, const BinLabels& lab, bool sparse,
-                 bool first_row_of_file, std::vector<char>& out)
+                 bool first_row_of_file, RawBuf& out)
 {
-    // worst case per token: label + 11 digits + space
-    const size_t worst_row = lab.text.size() + bins * 12 + 1;
-    out.resize(nrows * worst_row);
-    char* p = out.data();
+    // worst case per token: 8-byte label store + 11 digits + space
+    out.reserve(nrows * (bins * 20 + 1) + 16);
+    char* p = out.data;
     for (size_t r = 0; r < nrows; r++) {
         if (!(first_row_of_file && r == 0)) *p++ = '\n';
         const int32_t* row = rows + r * bins;
         for (size_t b = 0; b < bins; b++) {
-            if (sparse && row[b] == 0) continue;
-            const uint32_t l0 = lab.off[b], l1 = lab.off[b + 1];
-            memcpy(p, lab.text.data() + l0, l1 - l0);
-            p += l1 - l0;
-            p = put_int(p, row[b]);
+            const int32_t v = row[b];
+            if (sparse && v == 0) continue;
+            memcpy(p, &lab.rec[b], 8);
+            p += lab.len[b];
+            p = put_int(p, v);
             *p++ = ' ';
         }
     }
-    out.resize((size_t)(p - out.data()));
+    out.size = (size_t)(p - out.data);
 }
 
 class CfrkWriter {
 public:
     bool open(const char* path, int k, int nt, bool sparse, Err& err)
     {
-        f_ = fopen(path, "w");
-        if (!f_) { err.code = CFRK_EIO; err.msg = std::string("cannot open output ") + path; return false; }
+        fd_ = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);   // fopen(path, "w"), src/main.cu:34
+        if (fd_ < 0) { err.code = CFRK_EIO; err.msg = std::string("cannot open output ") + path; return false; }
+        seekable_ = lseek(fd_, 0, SEEK_CUR) != (off_t)-1;
         bins_ = k <= CFRK_DENSE_MAX_K ? (size_t)1 << (2 * k) : 0;
         if (bins_) labels_.reset(new BinLabels(bins_));
         nt_ = std::max(1, std::min(nt, 64));
@@ -240,20 +261,16 @@ public:
     {
         if (!nrows) return true;
         const int nt = (int)std::min<size_t>((size_t)nt_, nrows);
-        std::vector<std::vector<char>> parts(nt);
+        if (parts_.size() < (size_t)nt_) parts_ = std::vector<RawBuf>(nt_);
         std::vector<std::thread> th;
         for (int t = 0; t < nt; t++) {
             const size_t a = nrows * t / nt, b = nrows * (t + 1) / nt;
             const bool first = first_ && a == 0;
-            th.emplace_back([=, &parts] { format_rows(rows + a * bins_, b - a, bins_, *labels_, sparse_, first, parts[t]); });
+            th.emplace_back([=] { format_rows(rows + a * bins_, b - a, bins_, *labels_, sparse_, first, parts_[t]); });
         }
         for (auto& x : th) x.join();
         first_ = false;
-        for (auto& part : parts)
-            if (!part.empty() && fwrite(part.data(), 1, part.size(), f_) != part.size()) {
-                err.code = CFRK_EIO; err.msg = "short write"; return false;
-            }
-        return true;
+        return flush_parts(nt, err);
     }
     // rows given as (key, count) pairs: the same "bin:count " tokens, non-zero bins only
     bool write_pairs(const int64_t* row_begin, const int32_t* row_count, const uint64_t* keys,
@@ -261,17 +278,17 @@ public:
     {
         if (!nrows) return true;
         const int nt = (int)std::min<size_t>((size_t)nt_, nrows);
-        std::vector<std::vector<char>> parts(nt);
+        if (parts_.size() < (size_t)nt_) parts_ = std::vector<RawBuf>(nt_);
         std::vector<std::thread> th;
         for (int t = 0; t < nt; t++) {
             const size_t a = nrows * t / nt, b = nrows * (t + 1) / nt;
             const bool first = first_ && a == 0;
-            th.emplace_back([=, &parts] {
+            th.emplace_back([=] {
                 size_t npairs = 0;
                 for (size_t r = a; r < b; r++) npairs += (size_t)row_count[r];
-                std::vector<char>& out = parts[t];
-                out.resize(npairs * 33 + (b - a) + 1);   // 20 + 1 + 10 + 1 per token, '\n' per row
-                char* p = out.data();
+                RawBuf& out = parts_[t];
+                out.reserve(npairs * 33 + (b - a) + 1);   // 20 + 1 + 10 + 1 per token, '\n' per row
+                char* p = out.data;
                 for (size_t r = a; r < b; r++) {
                     if (!(first && r == a)) *p++ = '\n';
                     const uint64_t* kk = keys + row_begin[r];
@@ -287,21 +304,53 @@ public:
                         *p++ = ' ';
                     }
                 }
-                out.resize((size_t)(p - out.data()));
+                out.size = (size_t)(p - out.data);
             });
         }
         for (auto& x : th) x.join();
         first_ = false;
-        for (auto& part : parts)
-            if (!part.empty() && fwrite(part.data(), 1, part.size(), f_) != part.size()) {
-                err.code = CFRK_EIO; err.msg = "short write"; return false;
-            }
-        return true;
+        return flush_parts(nt, err);
     }
-    ~CfrkWriter() { if (f_) fclose(f_); }
+    ~CfrkWriter() { if (fd_ >= 0) ::close(fd_); }
 
 private:
-    FILE* f_ = nullptr;
+    // formatted parts -> file, in order.  Regular files: every part is written at its own offset
+    // by its own thread (pwrite); pipes (the Swift stdout form): sequential write.
+    bool flush_parts(int nparts, Err& err)
+    {
+        bool ok = true;
+        if (seekable_) {
+            std::vector<off_t> at(nparts);
+            for (int i = 0; i < nparts; i++) { at[i] = off_; off_ += (off_t)parts_[i].size; }
+            std::vector<std::thread> th;
+            std::vector<char> good(nparts, 1);
+            for (int i = 0; i < nparts; i++)
+                th.emplace_back([&, i] {
+                    size_t done = 0;
+                    while (done < parts_[i].size) {
+                        ssize_t w = pwrite(fd_, parts_[i].data + done, parts_[i].size - done, at[i] + (off_t)done);
+                        if (w <= 0) { good[i] = 0; break; }
+                        done += (size_t)w;
+                    }
+                });
+            for (auto& x : th) x.join();
+            for (char g : good) ok = ok && g;
+        } else {
+            for (int i = 0; i < nparts; i++) {
+                size_t done = 0;
+                while (ok && done < parts_[i].size) {
+                    ssize_t w = ::write(fd_, parts_[i].data + done, parts_[i].size - done);
+                    if (w <= 0) ok = false; else done += (size_t)w;
+                }
+            }
+        }
+        if (!ok) { err.code = CFRK_EIO; err.msg = "short write"; }
+        return ok;
+    }
+    std::vector<RawBuf> parts_;
+    int fd_ = -1;
+    bool seekable_ = false;
+    off_t off_ = 0;
     size_t bins_ = 0;
     std::unique_ptr<BinLabels> labels_;
     int nt_ = 1;
