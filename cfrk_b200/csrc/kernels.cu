@@ -1,9 +1,16 @@
 // kernels.cu -- sm_100a kernels of the CFRK hot path and their launchers.
 //
-//   dense_count_kernel   per-read dense int32 rows, k <= 8   (replaces SetMatrix x2 + ComputeIndex +
-//                        ComputeFreqNew, reference src/kmer_kernel.cu:6-90, src/kmer_main.cu:107-111)
+// Per-read dense int32 rows (replace SetMatrix x2 + ComputeIndex + ComputeFreqNew, reference
+// src/kmer_kernel.cu:6-90 as launched by src/kmer_main.cu:107-111), one kernel family per row size:
+//   dense_count_kernel   k = 1..3  CTA-cooperative 16 KiB tiles, TMA bulk store
+//   dense_warp_kernel    k = 4..6  warp-autonomous tiles, read-clear-store, spill hand-off
+//   dense_bigrow_kernel  k = 7, 8  TMA zero stream + L2 reductions on L2-resident tiles
+//   dense_row_kernel     k = 7     measured alternative (one shared-memory row per CTA)
+//   spill_fixup_kernel             data-dependent part of the cross-tile spill (compat mode)
+// Other stages:
 //   global_hist_kernel   whole-dataset histogram, k <= 15    (no reference counterpart; config C5)
 //   encode_2bit_kernel   bases -> packed 2-bit + validity    (replaces src/fastaIO.h:123-139)
+// Which kernel serves which k, and every tile size, is a measured choice: profiles/r1_notes.md.
 //
 // Compile: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo
 #include "kernels.h"
@@ -57,9 +64,10 @@ static cudaError_t stream_scratch(cudaStream_t st, size_t bytes, void** out)
 }
 
 // ------------------------------------------------------------------------------------------
-// Tile geometry.  A tile is TILE_BINS consecutive int32 of the output, i.e. a contiguous
-// TILE_BINS*4-byte span of HBM that one CTA builds in shared memory and ships with one TMA
-// bulk store:  k <= 6: RPT whole rows (reads) per tile;  k = 7, 8: one row = SUB tiles.
+// Tile geometry of the CTA-cooperative kernel.  A tile is TILE_BINS consecutive int32 of the
+// output, i.e. a contiguous TILE_BINS*4-byte span of HBM that one CTA builds in shared memory and
+// ships with one TMA bulk store: RPT whole rows (reads) per tile.  (SUB > 1, rows larger than a
+// tile, is the big-row kernel's business.)
 template <int K, int TILE_BINS_T>
 struct Geo {
     static constexpr int BINS = 1 << (2 * K);
