@@ -7,7 +7,8 @@
 // Like the reference: fewer than 3 arguments prints the usage line (no newline) and returns 1;
 // success prints nothing; a missing input exits 1.  Extensions (ignored by positional counting):
 //     --all-rows   print every read, not only the last nS mod chunkSize
-//     --exact      intended semantics instead of the reference's quirks
+//     --exact      intended semantics instead of the reference's quirks (all windows, no spill,
+//                  wrapped FASTA lines joined, last base kept)
 //     --sparse     omit zero bins (the filter commented out at src/main.cu:51,56)
 //                  k = 9..31 needs --sparse --exact: rows of "kmer_index:count " for the k-mers present
 //     --device=N

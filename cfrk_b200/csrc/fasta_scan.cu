@@ -110,6 +110,77 @@ __global__ void records_kernel(const uint8_t* __restrict__ buf, int64_t n, const
     length[i] = text > 0 ? (int32_t)(text - 1) : 0;
 }
 
+// ------------------------------------------------------------------------------------------
+// Exact mode at file level reads FASTA the intended way: line terminators are not bases and the
+// last base is kept (the reference keeps the newlines and drops the last byte, src/fastaIO.h:49-67).
+// One warp per record copies the record text without '\n' / '\r' into a packed buffer.
+__global__ void unwrap_count_kernel(const uint8_t* __restrict__ buf, int64_t n, const int64_t* __restrict__ header,
+                                    int64_t n_headers, const int64_t* __restrict__ start, int64_t nrec,
+                                    int64_t* __restrict__ kept)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r <= nrec; r += warps) {
+        if (r == nrec) { if (lane == 0) kept[r] = 0; continue; }
+        const int64_t s = start[r], e = r + 1 < n_headers ? header[r + 1] : n;
+        int c = 0;
+        for (int64_t i = s + lane; i < e; i += 32) {
+            const uint8_t b = buf[i];
+            c += (b != '\n' && b != '\r');
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        if (lane == 0) kept[r] = c;
+    }
+}
+
+__global__ void unwrap_copy_kernel(const uint8_t* __restrict__ buf, int64_t n, const int64_t* __restrict__ header,
+                                   int64_t n_headers, const int64_t* __restrict__ start, int64_t nrec,
+                                   const int64_t* __restrict__ new_start, uint8_t* __restrict__ out,
+                                   int32_t* __restrict__ new_length)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrec; r += warps) {
+        const int64_t s = start[r], e = r + 1 < n_headers ? header[r + 1] : n;
+        uint8_t* dst = out + new_start[r];
+        int64_t base = 0;
+        for (int64_t i0 = s; i0 < e; i0 += 32) {
+            const int64_t i = i0 + lane;
+            const uint8_t b = i < e ? buf[i] : (uint8_t)'\n';
+            const bool keep = b != '\n' && b != '\r';
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            if (keep) dst[base + __popc(m & ((1u << lane) - 1u))] = b;
+            base += __popc(m);
+        }
+        if (lane == 0) new_length[r] = (int32_t)base;
+    }
+}
+
+// records [0, nrec) of a scanned span -> packed bases + (new_start, new_length); d_new_start has
+// nrec + 1 entries (the last = packed size).  Asynchronous on st.
+cudaError_t launch_unwrap(const uint8_t* d_buf, int64_t n, const int64_t* d_header, int64_t n_headers,
+                          const int64_t* d_start, int64_t nrec, uint8_t* d_out, int64_t* d_new_start,
+                          int32_t* d_new_length, cudaStream_t st)
+{
+    if (nrec <= 0) return cudaSuccess;
+    const int64_t blocks = (nrec + 1 + 7) / 8;
+    const unsigned grid = (unsigned)(blocks < 148 * 8 ? blocks : 148 * 8);
+    unwrap_count_kernel<<<grid, 256, 0, st>>>(d_buf, n, d_header, n_headers, d_start, nrec, d_new_start);
+    count_launch();
+    size_t tmp_bytes = 0;
+    cudaError_t e = cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, d_new_start, d_new_start, nrec + 1, st);
+    if (e != cudaSuccess) return e;
+    void* tmp = nullptr;
+    if ((e = cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, st)) != cudaSuccess) return e;
+    e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, d_new_start, d_new_start, nrec + 1, st);
+    cudaFreeAsync(tmp, st);
+    if (e != cudaSuccess) return e;
+    unwrap_copy_kernel<<<grid, 256, 0, st>>>(d_buf, n, d_header, n_headers, d_start, nrec, d_new_start, d_out, d_new_length);
+    count_launch();
+    return cudaGetLastError();
+}
+
 // d_header: cap entries; d_start/d_length: cap entries; h_out[0] = number of headers in the span,
 // h_out[1] = error (0 ok, 1 '>' inside a line, 2 text before the first header, 3 record too long,
 // 4 more headers than cap).  Synchronises the stream.

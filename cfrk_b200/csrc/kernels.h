@@ -34,6 +34,11 @@ cudaError_t launch_sparse(const void* bases, int fmt, const int64_t* start, cons
 cudaError_t launch_fasta_scan(const uint8_t* d_buf, int64_t n, int final_span, int64_t* d_header, int64_t* d_start,
                               int32_t* d_length, int64_t cap, int64_t* h_out, cudaStream_t st);
 
+// Exact mode at file level: record text without line terminators, last base kept (fasta_scan.cu).
+cudaError_t launch_unwrap(const uint8_t* d_buf, int64_t n, const int64_t* d_header, int64_t n_headers,
+                          const int64_t* d_start, int64_t nrec, uint8_t* d_out, int64_t* d_new_start,
+                          int32_t* d_new_length, cudaStream_t st);
+
 uint64_t launch_count();
 
 }  // namespace cfrk

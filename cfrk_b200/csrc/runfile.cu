@@ -365,6 +365,12 @@ struct Pipeline {
     cudaEvent_t done[2] = {}, drained[2] = {};
     char* d_in = nullptr; size_t cap_in = 0;
     int64_t* d_start = nullptr; int32_t* d_length = nullptr; int64_t* d_header = nullptr; size_t cap_reads = 0;
+    // exact mode: unwrapped copy of the span (fasta_scan.cu launch_unwrap)
+    char* d_packed = nullptr; size_t cap_packed = 0;
+    int64_t* d_start2 = nullptr; int32_t* d_length2 = nullptr; size_t cap_reads2 = 0;
+    // what the count kernels read: the raw span or its unwrapped copy
+    const char* cur_bases = nullptr; const int64_t* cur_start = nullptr; const int32_t* cur_length = nullptr;
+    size_t n_headers = 0;
     int32_t* d_rows[2] = {}; int32_t* h_rows[2] = {}; size_t cap_rows = 0;
 
     bool init(Err& err)
@@ -423,6 +429,8 @@ struct Pipeline {
         if (out[1] == 2) { err.code = CFRK_EFORMAT; err.msg = "sequence text before the first '>' header (undefined in the reference, src/fastaIO.h:49-52)"; return false; }
         if (out[1] == 3) { err.code = CFRK_EFORMAT; err.msg = "record longer than 2^31-1 bytes (length is int in the reference, src/tipos.h:26)"; return false; }
         const size_t nh = (size_t)out[0];
+        n_headers = nh;
+        cur_bases = d_in; cur_start = d_start; cur_length = d_length;
         const size_t complete = final_span ? nh : (nh ? nh - 1 : 0);
         ri.header.resize(nh); ri.start.resize(complete); ri.length.resize(complete);
         std::vector<int64_t> hdr(nh);
@@ -435,6 +443,29 @@ struct Pipeline {
         for (size_t i = 0; i < nh; i++) ri.header[i] = (size_t)hdr[i];
         return true;
     }
+    // Exact mode: k-mers do not stop at line ends.  Replace the span by its unwrapped copy.
+    bool unwrap_scanned(size_t in_bytes, size_t nreads, Err& err)
+    {
+        if (nreads == 0) return true;
+        if (in_bytes + CFRK_PAD > cap_packed) {
+            cudaFree(d_packed);
+            cap_packed = in_bytes + CFRK_PAD + in_bytes / 8;
+            RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_packed), cap_packed));
+        }
+        if (nreads + 1 > cap_reads2) {
+            cudaFree(d_start2); cudaFree(d_length2);
+            cap_reads2 = nreads + nreads / 4 + 64;
+            RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_start2), cap_reads2 * 8));
+            RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_length2), cap_reads2 * 4));
+        }
+        RF_CU(cudaMemsetAsync(d_packed, 0, in_bytes + CFRK_PAD, compute));
+        cudaError_t e = cfrk::launch_unwrap(reinterpret_cast<const uint8_t*>(d_in), (int64_t)in_bytes, d_header,
+                                            (int64_t)n_headers, d_start, (int64_t)nreads,
+                                            reinterpret_cast<uint8_t*>(d_packed), d_start2, d_length2, compute);
+        if (e != cudaSuccess) { err.code = CFRK_ECUDA; err.msg = std::string("unwrap: ") + cudaGetErrorString(e); return false; }
+        cur_bases = d_packed; cur_start = d_start2; cur_length = d_length2;
+        return true;
+    }
     // Rows [0, nrows) of the span that upload_and_scan() left in HBM.
     bool count_scanned(const char* h_in, size_t in_bytes, const RecordIndex& ri, size_t nrows, int k, int mode,
                        int64_t chunk_size, int64_t index_base, CfrkWriter& w, Err& err)
@@ -442,6 +473,7 @@ struct Pipeline {
         if (nrows == 0) return true;
         if (mode == CFRK_MODE_COMPAT && std::find(ri.length.begin(), ri.length.end(), 0) != ri.length.end())
             return run(h_in, in_bytes, ri, nrows, k, mode, chunk_size, index_base, w, err);   // needs the packed layout
+        if (mode == CFRK_MODE_EXACT && !unwrap_scanned(in_bytes, ri.start.size(), err)) return false;
         return count_rows(in_bytes, ri.start.size(), nrows, k, mode, chunk_size, index_base, w, err);
     }
     // k > 8: sparse rows (exact semantics) of the span that upload_and_scan() left in HBM
@@ -449,15 +481,16 @@ struct Pipeline {
     {
         if (nrows == 0) return true;
         const size_t nreads = ri.start.size();
+        if (!unwrap_scanned(in_bytes, nreads, err)) return false;   // k > 8 is exact mode only
         int64_t cap = 0;
-        for (int32_t l : ri.length) cap += std::max(0, l - k + 1);
+        for (int32_t l : ri.length) cap += std::max(0, l + 1 - k + 1);   // unwrapped text <= raw length + 1
         int64_t* d_rb = nullptr; int32_t* d_rc = nullptr; uint64_t* d_k = nullptr; uint32_t* d_c = nullptr;
         RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_rb), (nreads + 1) * 8));
         RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_rc), nreads * 4));
         RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_k), (size_t)std::max<int64_t>(cap, 1) * 8));
         RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_c), (size_t)std::max<int64_t>(cap, 1) * 4));
         int64_t total = 0;
-        cudaError_t e = cfrk::launch_sparse(d_in, cfrk::FMT_ASCII, d_start, d_length, (int64_t)nreads, k, d_rb, d_rc, d_k, 8,
+        cudaError_t e = cfrk::launch_sparse(cur_bases, cfrk::FMT_ASCII, cur_start, cur_length, (int64_t)nreads, k, d_rb, d_rc, d_k, 8,
                                             d_c, cap, &total, compute);
         bool ok = e == cudaSuccess;
         if (!ok) { err.code = CFRK_ECUDA; err.msg = std::string("sparse path: ") + cudaGetErrorString(e); }
@@ -476,7 +509,6 @@ struct Pipeline {
             if (!ok) { err.code = CFRK_ECUDA; err.msg = "sparse path: device to host copy failed"; }
         }
         cudaFree(d_rb); cudaFree(d_rc); cudaFree(d_k); cudaFree(d_c);
-        (void)in_bytes;
         return ok && w.write_pairs(rb.data(), rc.data(), kk.data(), cc.data(), nrows, err);
     }
     // Host-side record table (the rare packed layout): upload bytes + table, then count.
@@ -515,6 +547,7 @@ struct Pipeline {
         RF_CU(cudaMemsetAsync(d_in + in_bytes, 0, CFRK_PAD, compute));
         RF_CU(cudaMemcpyAsync(d_start, ri.start.data(), nreads * 8, cudaMemcpyHostToDevice, compute));
         RF_CU(cudaMemcpyAsync(d_length, ri.length.data(), nreads * 4, cudaMemcpyHostToDevice, compute));
+        cur_bases = d_in; cur_start = d_start; cur_length = d_length;
         const bool ok = count_rows(in_bytes, nreads, nrows, k, mode, chunk_size, index_base, w, err);
         RF_CU(cudaStreamSynchronize(compute));   // pack_buf / ri must outlive the copies
         return ok;
@@ -538,7 +571,7 @@ struct Pipeline {
                 // slot reuse: the host finished formatting slice s-2 before we get here (below);
                 // the kernel must not overwrite d_rows[slot] before the D2H of slice s-2 is done
                 if (s >= 2) RF_CU(cudaStreamWaitEvent(compute, drained[slot], 0));
-                cudaError_t e = cfrk::launch_dense(d_in, cfrk::FMT_ASCII, d_start, d_length, (int64_t)in_bytes, (int64_t)nreads,
+                cudaError_t e = cfrk::launch_dense(cur_bases, cfrk::FMT_ASCII, cur_start, cur_length, (int64_t)in_bytes, (int64_t)nreads,
                                                    (int64_t)r0, (int64_t)r1, k, mode, chunk_size, index_base,
                                                    d_rows[slot], compute);
                 if (e != cudaSuccess) { err.code = CFRK_ECUDA; err.msg = std::string("dense_count_kernel: ") + cudaGetErrorString(e); return false; }
@@ -561,6 +594,7 @@ struct Pipeline {
     ~Pipeline()
     {
         cudaFree(d_in); cudaFree(d_start); cudaFree(d_length); cudaFree(d_header);
+        cudaFree(d_packed); cudaFree(d_start2); cudaFree(d_length2);
         for (int i = 0; i < 2; i++) {
             cudaFree(d_rows[i]);
             if (h_rows[i]) cudaFreeHost(h_rows[i]);

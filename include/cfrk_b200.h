@@ -151,7 +151,9 @@ int cfrk_scan_fasta_device(const void *d_bytes, int64_t n, int is_final, int64_t
 
 #define CFRK_RUN_ALL_ROWS   1  /* print every read (chunk by chunk) instead of only the
                                   last nS mod chunkSize reads (src/main.cu:303-305)     */
-#define CFRK_RUN_EXACT      2  /* CFRK_MODE_EXACT instead of compat                     */
+#define CFRK_RUN_EXACT      2  /* CFRK_MODE_EXACT instead of compat, and the file is read the
+                                  intended way: line terminators are not bases (k-mers span
+                                  wrapped lines) and the last base is kept                 */
 #define CFRK_RUN_SPARSE     4  /* write only non-zero bins (the filter commented out at
                                   src/main.cu:51,56)                                    */
 

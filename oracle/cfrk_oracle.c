@@ -52,6 +52,11 @@ void oracle_free_reads(oracle_reads *r)
  */
 int oracle_parse_fasta_mem(const char *buf, size_t n, oracle_reads *out)
 {
+    return oracle_parse_fasta_mem_ex(buf, n, 0, out);
+}
+
+int oracle_parse_fasta_mem_ex(const char *buf, size_t n, int unwrap, oracle_reads *out)
+{
     memset(out, 0, sizeof *out);
     /* pass 1: count lines with '>' (grep) and header lines, bound the text size */
     int64_t grep_count = 0, headers = 0;
@@ -85,7 +90,7 @@ int oracle_parse_fasta_mem(const char *buf, size_t n, oracle_reads *out)
         /* len = strlen(text) - 1, never below 0 (a header with no sequence line is      \
          * undefined in the reference; defined here as a read of length 0) */            \
         int64_t tlen = w - text_begin;                                                   \
-        int64_t len = tlen > 0 ? tlen - 1 : 0;                                           \
+        int64_t len = unwrap ? tlen : (tlen > 0 ? tlen - 1 : 0);                         \
         w = text_begin + len;                                                            \
         out->length[rec] = (int32_t)len;                                                 \
         out->start[rec] = text_begin;                                                    \
@@ -103,8 +108,10 @@ int oracle_parse_fasta_mem(const char *buf, size_t n, oracle_reads *out)
             /* strcat copies up to the first NUL of the line */
             const char *z = memchr(buf + pos, '\0', end - pos);
             size_t cpy = z ? (size_t)(z - (buf + pos)) : end - pos;
-            for (size_t j = 0; j < cpy; j++)
+            for (size_t j = 0; j < cpy; j++) {
+                if (unwrap && (buf[pos + j] == '\n' || buf[pos + j] == '\r')) continue;
                 out->data[w++] = oracle_encode_base((unsigned char)buf[pos + j]);
+            }
         }
         pos = end;
     }
@@ -114,7 +121,9 @@ int oracle_parse_fasta_mem(const char *buf, size_t n, oracle_reads *out)
     return 0;
 }
 
-int oracle_parse_fasta(const char *path, oracle_reads *out)
+int oracle_parse_fasta(const char *path, oracle_reads *out) { return oracle_parse_fasta_ex(path, 0, out); }
+
+int oracle_parse_fasta_ex(const char *path, int unwrap, oracle_reads *out)
 {
     FILE *f = fopen(path, "rb");
     if (!f) return -1; /* src/fastaIO.h:36 exit(EXIT_FAILURE) */
@@ -125,7 +134,7 @@ int oracle_parse_fasta(const char *path, oracle_reads *out)
     if (!buf) { fclose(f); return -4; }
     size_t got = fread(buf, 1, (size_t)sz, f);
     fclose(f);
-    int rc = oracle_parse_fasta_mem(buf, got, out);
+    int rc = oracle_parse_fasta_mem_ex(buf, got, unwrap, out);
     free(buf);
     return rc;
 }
@@ -400,7 +409,8 @@ int oracle_run_cli(const char *fasta, const char *out, int k, int64_t chunk_size
 {
     if (chunk_size <= 0 || k < 1 || k > 12) return -5;
     oracle_reads rd;
-    int rc = oracle_parse_fasta(fasta, &rd);
+    /* exact mode reads the file the intended way: lines unwrapped, last base kept */
+    int rc = oracle_parse_fasta_ex(fasta, mode == ORACLE_MODE_EXACT, &rd);
     if (rc) return rc;
     const int64_t fourk = four_pow(k);
     FILE *f = fopen(out, "w");

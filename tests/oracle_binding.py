@@ -41,6 +41,8 @@ def lib():
         p8, p32, p64 = C.c_void_p, C.c_void_p, C.c_void_p
         L.oracle_parse_fasta.argtypes = [C.c_char_p, C.POINTER(_Reads)]
         L.oracle_parse_fasta_mem.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(_Reads)]
+        L.oracle_parse_fasta_ex.argtypes = [C.c_char_p, C.c_int, C.POINTER(_Reads)]
+        L.oracle_parse_fasta_mem_ex.argtypes = [C.c_char_p, C.c_size_t, C.c_int, C.POINTER(_Reads)]
         L.oracle_free_reads.argtypes = [C.POINTER(_Reads)]
         for name in ("oracle_count_compat", "oracle_count_exact"):
             getattr(L, name).argtypes = [p8, p64, p32, C.c_int64, C.c_int64, C.c_int, p32]
@@ -64,15 +66,16 @@ def _ptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def parse_fasta(path=None, text=None):
-    """-> (data int8[nN], start int64[nS], length int32[nS]); raises ValueError on rc<0."""
+def parse_fasta(path=None, text=None, unwrap=False):
+    """-> (data int8[nN], start int64[nS], length int32[nS]); raises ValueError on rc<0.
+    unwrap: the intended reading (line terminators are not bases, last base kept)."""
     r = _Reads()
     if text is not None:
         if isinstance(text, str):
             text = text.encode()
-        rc = lib().oracle_parse_fasta_mem(text, len(text), C.byref(r))
+        rc = lib().oracle_parse_fasta_mem_ex(text, len(text), int(unwrap), C.byref(r))
     else:
-        rc = lib().oracle_parse_fasta(os.fsencode(path), C.byref(r))
+        rc = lib().oracle_parse_fasta_ex(os.fsencode(path), int(unwrap), C.byref(r))
     if rc != 0:
         raise ValueError(f"oracle_parse_fasta rc={rc}")
     nS, nN = r.nS, r.nN

@@ -135,3 +135,41 @@ def test_sparse_rows_for_large_k(tmp_path, k):
         assert toks == list(zip(keys[rp[i]:rp[i + 1]].tolist(), cnt[rp[i]:rp[i + 1]].tolist())), f"row {i}"
     r = subprocess.run([CFRK, str(fa), str(out), str(k)], capture_output=True)     # dense k > 8 is refused
     assert r.returncode == 1 and b"--sparse --exact" in r.stderr
+
+
+@pytest.mark.parametrize("name", ["C_multiline", "F_crlf", "F_noeol", "F_blank", "B_withN", "R_ragged"])
+@pytest.mark.parametrize("k", [3, 6, 11])
+def test_exact_mode_unwraps_lines(tmp_path, name, k):
+    """--exact reads FASTA the intended way (line terminators are not bases, last base kept):
+    equals the oracle's unwrapped reading, dense (k <= 8) and sparse (k > 8)"""
+    text = dict((n, t) for n, t, _ in fx.EDGE_SET)[name]
+    fa, out = tmp_path / "in.fa", tmp_path / "out.cfrk"
+    fa.write_text(text, newline="")
+    data, start, length = ob.parse_fasta(text=text, unwrap=True)
+    if k <= 8:
+        run_cfrk(fa, out, k, 4, 8192, "--all-rows", "--exact")
+        want = tmp_path / "want.cfrk"
+        ob.write_cfrk(str(want), ob.count_dense(data, start, length, k, ob.MODE_EXACT), k)
+        assert out.read_bytes() == want.read_bytes()
+    else:
+        run_cfrk(fa, out, k, 4, 8192, "--all-rows", "--exact", "--sparse")
+        rp, keys, cnt = ob.count_sparse(data, start, length, k)
+        lines = out.read_bytes().split(b"\n")
+        assert len(lines) == len(start)
+        for i, line in enumerate(lines):
+            toks = [tuple(map(int, t.split(b":"))) for t in line.split()]
+            assert toks == list(zip(keys[rp[i]:rp[i + 1]].tolist(), cnt[rp[i]:rp[i + 1]].tolist())), f"row {i}"
+
+
+def test_wrapped_equals_single_line_in_exact_mode(tmp_path):
+    import random
+    rng = random.Random(4)
+    seqs = ["".join(rng.choice("ACGTN" if rng.random() < 0.02 else "ACGT") for _ in range(rng.randint(1, 900))) for _ in range(200)]
+    one = tmp_path / "one.fa"; wrapped = tmp_path / "wrapped.fa"
+    one.write_text("".join(f">s{i}\n{s}\n" for i, s in enumerate(seqs)))
+    wrapped.write_text("".join(f">s{i}\n" + "\n".join(s[j:j + 60] for j in range(0, len(s), 60)) + "\n" for i, s in enumerate(seqs)))
+    a, b = tmp_path / "a", tmp_path / "b"
+    for k in (4, 7):
+        run_cfrk(one, a, k, 4, 8192, "--all-rows", "--exact")
+        run_cfrk(wrapped, b, k, 4, 8192, "--all-rows", "--exact")
+        assert a.read_bytes() == b.read_bytes()
