@@ -763,6 +763,12 @@ static cudaError_t launch_dense_fmt(int k, const DenseArgs& a, cudaStream_t st)
         return k7_variant == 1 ? launch_row_k<7, FMT>(a, st) : launch_bigrow_k<7, FMT>(a, st);
     }
     case 8: return launch_bigrow_k<8, FMT>(a, st);
+    // k = 9..12: 1 MiB .. 64 MiB per read.  Only the reference's operator can ask for these (its
+    // own driver overflows beyond k = 8); same path, 256 KiB tiles, 2 CTAs/SM.
+    case 9: return launch_bigrow_t<9, FMT, (256 << 10)>(a, st, 2);
+    case 10: return launch_bigrow_t<10, FMT, (256 << 10)>(a, st, 2);
+    case 11: return launch_bigrow_t<11, FMT, (256 << 10)>(a, st, 2);
+    case 12: return launch_bigrow_t<12, FMT, (256 << 10)>(a, st, 2);
     default: return cudaErrorInvalidValue;
     }
 }

@@ -251,7 +251,7 @@ public:
         fd_ = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);   // fopen(path, "w"), src/main.cu:34
         if (fd_ < 0) { err.code = CFRK_EIO; err.msg = std::string("cannot open output ") + path; return false; }
         seekable_ = lseek(fd_, 0, SEEK_CUR) != (off_t)-1;
-        bins_ = k <= CFRK_DENSE_MAX_K ? (size_t)1 << (2 * k) : 0;
+        bins_ = k <= CFRK_CLI_DENSE_MAX_K ? (size_t)1 << (2 * k) : 0;
         if (bins_) labels_.reset(new BinLabels(bins_));
         nt_ = std::max(1, std::min(nt, 64));
         sparse_ = sparse;
@@ -661,7 +661,7 @@ bool run_file(const char* fasta, const char* out_path, int k, int nt, int64_t ch
                     held += (size_t)ri.length[nrows] + 1;
                 }
             }
-            if (k > CFRK_DENSE_MAX_K ? !gpu.count_scanned_sparse(n, ri, nrows, k, w, err)
+            if (k > CFRK_CLI_DENSE_MAX_K ? !gpu.count_scanned_sparse(n, ri, nrows, k, w, err)
                                      : !gpu.count_scanned(data, n, ri, nrows, k, mode, chunk_size, reads_done, w, err)) return false;
             reads_done += (int64_t)nrows;
             tr.mark("rows counted + written");
@@ -703,7 +703,7 @@ bool run_file(const char* fasta, const char* out_path, int k, int nt, int64_t ch
             bool ok = got == bytes && gpu.upload_and_scan(h, bytes, true, ri, err);
             if (got != bytes) { err.code = CFRK_EIO; err.msg = "short read of the tail chunk"; }
             tr.mark("tail chunk scanned", bytes);
-            if (ok) ok = k > CFRK_DENSE_MAX_K
+            if (ok) ok = k > CFRK_CLI_DENSE_MAX_K
                              ? gpu.count_scanned_sparse(bytes, ri, ri.start.size(), k, w, err)
                              : gpu.count_scanned(h, bytes, ri, ri.start.size(), k, mode, chunk_size, (nS / chunk_size) * chunk_size, w, err);
             tr.mark("tail rows counted + written");
@@ -722,7 +722,7 @@ extern "C" int cfrk_run_file(const char* fasta_path, const char* out_path, int k
     Err err;
     if (!fasta_path || !out_path) { err.code = CFRK_EINVAL; err.msg = "null path"; }
     else if (k < 1 || k > CFRK_SPARSE_MAX_K) { err.code = CFRK_EINVAL; err.msg = "k must be in 1..31"; }
-    else if (k > CFRK_DENSE_MAX_K && (flags & (CFRK_RUN_SPARSE | CFRK_RUN_EXACT)) != (CFRK_RUN_SPARSE | CFRK_RUN_EXACT)) {
+    else if (k > CFRK_CLI_DENSE_MAX_K && (flags & (CFRK_RUN_SPARSE | CFRK_RUN_EXACT)) != (CFRK_RUN_SPARSE | CFRK_RUN_EXACT)) {
         err.code = CFRK_EINVAL;
         err.msg = "k > 8: rows have 4^k bins; pass --sparse --exact (non-zero bins only, intended semantics)";
     }

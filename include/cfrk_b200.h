@@ -47,7 +47,9 @@ extern "C" {
 #define CFRK_FMT_ASCII 1   /* FASTA letters as read from the file (upper or lower case);
                               one separator byte (any non-ACGT byte) after each read    */
 
-#define CFRK_DENSE_MAX_K 8   /* shared-memory tile path (4^k int32 per read)            */
+#define CFRK_DENSE_MAX_K 12  /* dense rows, 4^k int32 per read (the reference's float32 index
+                                is exact up to k = 12); k <= 8 is the tuned range */
+#define CFRK_CLI_DENSE_MAX_K 8 /* dense TEXT rows of the cfrk command                    */
 #define CFRK_HIST_MAX_K  15  /* whole-dataset histogram, 4^k uint32 in HBM              */
 #define CFRK_SPARSE_MAX_K 31 /* sparse per-read rows, uint64 keys                       */
 #define CFRK_PAD         16  /* device bases buffers must be readable up to the next

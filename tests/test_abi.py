@@ -49,7 +49,7 @@ def test_argument_validation_needs_no_gpu():
     z8, z64, z32 = np.zeros(16, np.int8), np.zeros(1, np.int64), np.ones(1, np.int32)
     L = cf.lib()
     p8, p64, p32 = z8.ctypes.data, z64.ctypes.data, z32.ctypes.data
-    for k in (0, 9, -1):   # dense path is k = 1..8
+    for k in (0, 13, -1):   # dense path is k = 1..12
         assert L.cfrk_count_dense_host(p8, 0, p64, p32, 16, 1, k, 0, 0, p8) == -1
         assert b"k out of range" in L.cfrk_last_error()
     assert L.cfrk_count_dense_host(p8, 7, p64, p32, 16, 1, 2, 0, 0, p8) == -1        # bad fmt

@@ -110,3 +110,14 @@ def test_long_sequences_dense(k):
     if k <= 6:
         np.testing.assert_array_equal(ob.count_dense(data, start, length, k, cf.MODE_EXACT),
                                       ob.count_dense_fast(data, start, length, k, cf.MODE_EXACT))
+
+
+@pytest.mark.parametrize("k", [9, 10, 12])
+def test_dense_rows_up_to_k12(k):
+    """the reference's operator accepts k up to 12 when nS * 4^k < 2^31"""
+    nS = {9: 300, 10: 80, 12: 6}[k]
+    data, start, length = fx.synthetic_codes(nS, 150, seed=k, n_frac=0.003)
+    for mode in (cf.MODE_COMPAT, cf.MODE_EXACT):
+        got = cf.count_dense_host(data, start, length, k, mode)
+        want = ob.count_dense_fast(data, start, length, k, mode)
+        np.testing.assert_array_equal(got, want)
