@@ -734,6 +734,8 @@ static cudaError_t launch_dense_fmt(int k, const DenseArgs& a, cudaStream_t st)
         case 3: return launch_warp_k<4, FMT, 4, 4, false>(a, st);     // warp tiles + TMA, RW=4      0.60
         case 4: return launch_warp_k<4, FMT, 8, 4, true>(a, st);      // direct, RW=8 (93 items)     0.69-0.75
         case 5: return launch_warp_k<4, FMT, 16, 4, true>(a, st);     // direct, RW=16               0.53
+        case 6: return launch_warp_k<4, FMT, 6, 4, true>(a, st);      // direct, RW=6 (62 items = 2 chunks)  0.61
+        case 7: return launch_warp_k<4, FMT, 3, 4, true>(a, st);      // direct, RW=3 (31 items = 1 chunk)   0.46
         default: return launch_warp_k<4, FMT, 9, 4, true>(a, st);     // direct, RW=9 (93 items, no halo scan) +2.5 %
         }
     }
