@@ -138,8 +138,6 @@ int cfrk_count_dense_device(const void* d_bases, int fmt, const int64_t* d_start
     if (!d_bases || !d_start || !d_length || !d_freq) return fail(CFRK_EINVAL, "null device pointer");
     if ((reinterpret_cast<uintptr_t>(d_bases) & 15) || (reinterpret_cast<uintptr_t>(d_freq) & 15))
         return fail(CFRK_EINVAL, "d_bases and d_freq must be 16-byte aligned");
-    if (read_begin % cfrk::dense_reads_per_tile(k))
-        return fail(CFRK_EINVAL, "read_begin must be a multiple of cfrk_dense_reads_per_tile(k)");
     cudaError_t e = cfrk::launch_dense(d_bases, fmt, d_start, d_length, nN, nS, read_begin, read_end, k, mode,
                                        chunk_size, first_read_index, d_freq, static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail_cuda(e, "dense_count_kernel launch");

@@ -82,8 +82,10 @@ int cfrk_count_dense_host(const void *bases, int fmt, const int64_t *start, cons
  * Device-resident variant: every pointer is device memory on `device`, `stream` is a
  * cudaStream_t (NULL = the legacy default stream).  Asynchronous.  d_bases must honour
  * CFRK_PAD; d_freq must be 16-byte aligned.  Reads [read_begin, read_end) of the batch
- * are counted into d_freq[(i-read_begin)*4^k ...]; read_begin must be a multiple of
- * cfrk_dense_reads_per_tile(k) unless it is 0 (so that row tiles line up).
+ * are counted into d_freq[(i-read_begin)*4^k ...] (any range; row tiles are laid out from
+ * read_begin).  Splitting a batch into ranges -- row rings, multi-GPU shards -- gives exactly
+ * the rows of one call: the last tile of a range scans the first read of the next one for its
+ * spill.  cfrk_dense_reads_per_tile(k) is a good granularity for range sizes.
  * compat mode: the reference drops the spill of the first read of every kmer_main call
  * (one call per chunk, src/main.cu:222,294,300).  chunk_size == 0: the batch is one such
  * call.  chunk_size > 0: read i opens a chunk iff (first_read_index + i) % chunk_size == 0,
