@@ -8,7 +8,8 @@ LIB_PATH = os.path.join(_HERE, "lib", "libcfrk_b200.so")
 # every symbol include/cfrk_b200.h declares (tests/test_abi.py checks header and library agree)
 SYMBOLS = [
     "cfrk_version", "cfrk_last_error", "cfrk_device_count", "cfrk_launch_count",
-    "cfrk_count_dense_host", "cfrk_count_dense_device", "cfrk_dense_reads_per_tile",
+    "cfrk_count_dense_host", "cfrk_count_dense_device", "cfrk_count_dense_packed_device",
+    "cfrk_dense_reads_per_tile",
     "cfrk_encode_2bit_device", "cfrk_global_hist_device", "cfrk_count_sparse_device", "cfrk_scan_fasta_device",
     "cfrk_run_file",
 ]
@@ -33,6 +34,7 @@ def load():
     L.cfrk_dense_reads_per_tile.argtypes = [i32]
     L.cfrk_count_dense_host.argtypes = [vp, i32, vp, vp, i64, i64, i32, i32, i32, vp]
     L.cfrk_count_dense_device.argtypes = [vp, i32, vp, vp, i64, i64, i64, i64, i32, i32, i64, i64, vp, vp]
+    L.cfrk_count_dense_packed_device.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i32, i32, i64, i64, vp, vp]
     L.cfrk_encode_2bit_device.argtypes = [vp, i32, i64, vp, vp, vp]
     L.cfrk_global_hist_device.argtypes = [vp, i32, vp, vp, i64, i64, i32, vp, vp]
     L.cfrk_count_sparse_device.argtypes = [vp, i32, vp, vp, i64, i64, i32, i32, vp, vp, vp, vp, i64,

@@ -84,6 +84,16 @@ def count_dense_device(d_bases, d_start, d_length, nN, nS, k, d_freq, mode=MODE_
     _check(rc, "cfrk_count_dense_device")
 
 
+def count_dense_packed_device(d_codes, d_valid, d_start, d_length, nN, nS, k, d_freq, mode=MODE_COMPAT,
+                              read_begin=0, read_end=None, chunk_size=0, first_read_index=0, stream=0):
+    """Dense rows from packed 2-bit reads (the output of encode_2bit_device)."""
+    if read_end is None:
+        read_end = nS
+    _check(lib().cfrk_count_dense_packed_device(d_codes, d_valid, d_start, d_length, nN, nS, read_begin, read_end,
+                                                k, mode, chunk_size, first_read_index, d_freq, stream),
+           "cfrk_count_dense_packed_device")
+
+
 def encode_2bit_device(d_bases, n, d_codes, d_valid, fmt=FMT_ASCII, stream=0):
     _check(lib().cfrk_encode_2bit_device(d_bases, fmt, n, d_codes, d_valid, stream), "cfrk_encode_2bit_device")
 

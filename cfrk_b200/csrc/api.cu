@@ -144,6 +144,26 @@ int cfrk_count_dense_device(const void* d_bases, int fmt, const int64_t* d_start
     return CFRK_OK;
 }
 
+int cfrk_count_dense_packed_device(const uint32_t* d_codes, const uint16_t* d_valid, const int64_t* d_start,
+                                   const int32_t* d_length, int64_t nN, int64_t nS, int64_t read_begin,
+                                   int64_t read_end, int k, int mode, int64_t chunk_size, int64_t first_read_index,
+                                   int32_t* d_freq, void* stream)
+{
+    int rc = check_common(CFRK_FMT_CODES, k, CFRK_DENSE_MAX_K, mode);
+    if (rc) return rc;
+    if (nS < 0 || nN < 0 || read_begin < 0 || read_end > nS || read_begin > read_end)
+        return fail(CFRK_EINVAL, "bad read range");
+    if (chunk_size < 0 || first_read_index < 0) return fail(CFRK_EINVAL, "negative chunk_size / first_read_index");
+    if (read_begin == read_end) return CFRK_OK;
+    if (!d_codes || !d_valid || !d_start || !d_length || !d_freq) return fail(CFRK_EINVAL, "null device pointer");
+    if (reinterpret_cast<uintptr_t>(d_freq) & 15) return fail(CFRK_EINVAL, "d_freq must be 16-byte aligned");
+    cudaError_t e = cfrk::launch_dense(d_codes, cfrk::FMT_PACKED, d_start, d_length, nN, nS, read_begin, read_end, k,
+                                       mode, chunk_size, first_read_index, d_freq, static_cast<cudaStream_t>(stream),
+                                       d_valid);
+    if (e != cudaSuccess) return fail_cuda(e, "dense kernel launch (packed reads)");
+    return CFRK_OK;
+}
+
 int cfrk_count_dense_host(const void* bases, int fmt, const int64_t* start, const int32_t* length,
                           int64_t nN, int64_t nS, int k, int mode, int device, int32_t* freq_out)
 {

@@ -104,6 +104,7 @@ struct DenseSink {
 
 struct DenseArgs {
     const uint8_t* bases;
+    const uint16_t* valid;   // FMT_PACKED only: validity masks (bases = the uint32 codes)
     const int64_t* start;
     const int32_t* length;
     int64_t nS;          // reads in the batch (halo / spill scope)
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(NTHREADS) dense_count_kernel(const DenseArgs a
         __syncthreads();
 
         DenseSink<K, TILE_BINS_T> sink{(uint32_t)__cvta_generic_to_shared(hist), qb, period};
-        for_each_window<K, FMT, G::TABLE_READS>(a.bases, tb, nreads, nrows, a.mode, sink);
+        for_each_window<K, FMT, G::TABLE_READS>(BasesRef{a.bases, a.valid}, tb, nreads, nrows, a.mode, sink);
 
         fence_async_proxy_shared();  // make the shared-memory counts visible to the TMA engine
         __syncthreads();
@@ -296,7 +297,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dense_warp_kernel(const Dens
             __syncwarp();
         }
         WarpSink<K> sink{(uint32_t)__cvta_generic_to_shared(hist), qb, period, 0};
-        warp_for_each_window<K, FMT, RW + 1>(a.bases, lr, nreads, nrows, a.mode, sink);
+        warp_for_each_window<K, FMT, RW + 1>(BasesRef{a.bases, a.valid}, lr, nreads, nrows, a.mode, sink);
         uint32_t* dst = a.out + (r0 - a.read_begin) * BINS;
         if (halo && !scan_halo) {   // length-only part of the next read's spill
             const int ex = __shfl_sync(0xffffffffu, lr.extra, nrows);
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(kRowThreads) dense_row_kernel(const DenseArgs 
         }
         __syncthreads();
         RowSink<K> sink{(uint32_t)__cvta_generic_to_shared(hist), opens, scan_halo, 0};
-        for_each_window<K, FMT, 2>(a.bases, tb, nreads, 1, a.mode, sink);
+        for_each_window<K, FMT, 2>(BasesRef{a.bases, a.valid}, tb, nreads, 1, a.mode, sink);
         if (sink.carry0) atomicAdd(&s_carry, sink.carry0);
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -625,7 +626,7 @@ __global__ void __launch_bounds__(kBigThreads) dense_bigrow_kernel(const DenseAr
         if (threadIdx.x < 32) scan_read_table(tb, nreads);
         __syncthreads();
         BigRowSink<K, TILE_BYTES> sink{(a.flags & 1) == 0, rows, sub, has_last, qb, period};
-        for_each_window<K, FMT, G::TABLE_READS>(a.bases, tb, nreads, nrows, a.mode, sink);  // 2. + 3.
+        for_each_window<K, FMT, G::TABLE_READS>(BasesRef{a.bases, a.valid}, tb, nreads, nrows, a.mode, sink);  // 2. + 3.
         __syncthreads();  // table is reused by the next tile
     }
     if (threadIdx.x == 0) bulk_wait_all();
@@ -789,10 +790,12 @@ int dense_reads_per_tile(int k)
 
 cudaError_t launch_dense(const void* bases, int fmt, const int64_t* start, const int32_t* length,
                          int64_t nN, int64_t nS, int64_t read_begin, int64_t read_end, int k, int mode,
-                         int64_t chunk_size, int64_t index_base, int32_t* out, cudaStream_t st)
+                         int64_t chunk_size, int64_t index_base, int32_t* out, cudaStream_t st,
+                         const uint16_t* packed_valid)
 {
     DenseArgs a;
     a.bases = static_cast<const uint8_t*>(bases);
+    a.valid = packed_valid;
     a.start = start; a.length = length; a.nS = nS; a.nN = nN;
     a.read_begin = read_begin; a.read_end = read_end;
     a.out = reinterpret_cast<uint32_t*>(out);
@@ -801,6 +804,7 @@ cudaError_t launch_dense(const void* bases, int fmt, const int64_t* start, const
     static const int big_plain = env_int("CFRK_BIG_PLAIN", 0);
     a.flags = big_plain ? 1 : 0;
     a.handoff = nullptr;
+    if (fmt == FMT_PACKED) return launch_dense_fmt<FMT_PACKED>(k, a, st);
     return fmt == FMT_ASCII ? launch_dense_fmt<FMT_ASCII>(k, a, st) : launch_dense_fmt<FMT_CODES>(k, a, st);
 }
 
@@ -856,8 +860,8 @@ __global__ void __launch_bounds__(kHistThreads) global_hist_kernel(const uint8_t
         __syncthreads();
         if (threadIdx.x < 32) scan_read_table(tb, n);
         __syncthreads();
-        if constexpr (SHARED) for_each_window<K, FMT, kHistGroup>(bases, tb, n, n, MODE_EXACT, ssink);
-        else for_each_window<K, FMT, kHistGroup>(bases, tb, n, n, MODE_EXACT, gsink);
+        if constexpr (SHARED) for_each_window<K, FMT, kHistGroup>(BasesRef{bases, nullptr}, tb, n, n, MODE_EXACT, ssink);
+        else for_each_window<K, FMT, kHistGroup>(BasesRef{bases, nullptr}, tb, n, n, MODE_EXACT, gsink);
     }
     if (SHARED) {
         __syncthreads();

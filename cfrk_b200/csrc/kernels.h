@@ -11,7 +11,8 @@ namespace cfrk {
 // else iff (index_base + i) % chunk_size == 0.
 cudaError_t launch_dense(const void* bases, int fmt, const int64_t* start, const int32_t* length,
                          int64_t nN, int64_t nS, int64_t read_begin, int64_t read_end, int k, int mode,
-                         int64_t chunk_size, int64_t index_base, int32_t* out, cudaStream_t st);
+                         int64_t chunk_size, int64_t index_base, int32_t* out, cudaStream_t st,
+                         const uint16_t* packed_valid = nullptr);   // fmt 2 (packed): bases = uint32 codes
 int dense_reads_per_tile(int k);
 
 // hist[4^k] += exact-mode k-mer counts of the whole batch; k in 1..15.

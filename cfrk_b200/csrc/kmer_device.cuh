@@ -18,6 +18,7 @@ namespace cfrk {
 
 constexpr int FMT_CODES = 0;
 constexpr int FMT_ASCII = 1;
+constexpr int FMT_PACKED = 2;   // what encode_2bit_kernel writes: 16 bases per uint32 + uint16 validity
 constexpr int MODE_COMPAT = 0;
 constexpr int MODE_EXACT = 1;
 constexpr int kRefBlockThreads = 1024;  // reference blockDim (src/kmer_main.cu:82)
@@ -32,6 +33,26 @@ __device__ __forceinline__ uint4 ld_block(const uint8_t* p)
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "l"(p));
     return r;
+}
+
+// The bases of a batch: one byte per base (CODES / ASCII), or the packed 2-bit words + validity
+// masks of FMT_PACKED (p = uint32 codes[], valid = uint16 masks[], one entry per 16-base block).
+struct BasesRef {
+    const uint8_t* p;
+    const uint16_t* valid;
+};
+
+// one 16-base block: the 16 raw bytes, or {codes, valid, 0, 0} when the batch is already encoded
+template <int FMT>
+__device__ __forceinline__ uint4 load_block(const BasesRef& b, int64_t blk)
+{
+    if (FMT == FMT_PACKED) {
+        uint32_t c; uint16_t v;
+        asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(c) : "l"(reinterpret_cast<const uint32_t*>(b.p) + blk));
+        asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(b.valid + blk));
+        return make_uint4(c, (uint32_t)v, 0u, 0u);
+    }
+    return ld_block(b.p + blk * 16);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -188,7 +209,8 @@ __device__ __forceinline__ void emit_item(const Item& it, int ncount, int mode, 
     const int lane = threadIdx.x & 31;
     uint32_t codes = 0, valid = 0, count_mask = 0;
     if (it.live) {
-        encode16<FMT>(it.raw, codes, valid);
+        if (FMT == FMT_PACKED) { codes = it.raw.x; valid = it.raw.y; }
+        else encode16<FMT == FMT_PACKED ? FMT_CODES : FMT>(it.raw, codes, valid);
         const uint32_t upto = ~from_pos(min(16, it.tend - it.t0));
         valid &= from_pos(max(0, -it.t0)) & upto;                       // bases of this read only
         count_mask = from_pos(min(16, max(0, K - 1 - it.t0))) & upto;   // window ends that count
@@ -247,7 +269,7 @@ __device__ __forceinline__ void emit_item(const Item& it, int ncount, int mode, 
 //                            anything is emitted (a place for a CTA-wide wait + barrier)
 // MAXREADS bounds n (binary search depth).
 template <int K, int FMT, int MAXREADS, class Sink>
-__device__ __forceinline__ void for_each_window(const uint8_t* __restrict__ bases, const ReadTable& tb,
+__device__ __forceinline__ void for_each_window(const BasesRef& bases, const ReadTable& tb,
                                                 int n, int ncount, int mode, Sink& sink)
 {
     constexpr int STEPS = Log2Ceil<MAXREADS>::value;
@@ -284,7 +306,7 @@ __device__ __forceinline__ void for_each_window(const uint8_t* __restrict__ base
             it.extra = tb.extra[lo];
             it.t0 = (int)(blk * 16 - s);
             it.first_block = (c == 0);
-            it.raw = ld_block(bases + blk * 16);
+            it.raw = load_block<FMT>(bases, blk);
         }
         if constexpr (Sink::kCtaUniform) { if (iter == 0) sink.before_first_emit(); }
         emit_item<K, FMT>(it, ncount, mode, sink);
@@ -322,8 +344,8 @@ __device__ __forceinline__ LaneRead make_lane_read(bool have, bool items, int64_
     return lr;
 }
 
-template <int NREADS_MAX>
-__device__ __forceinline__ Item warp_fetch_item(const uint8_t* __restrict__ bases, const LaneRead& lr, int n,
+template <int FMT, int NREADS_MAX>
+__device__ __forceinline__ Item warp_fetch_item(const BasesRef& bases, const LaneRead& lr, int n,
                                                 uint32_t total, uint32_t chunk, bool any_empty)
 {
     const int lane = threadIdx.x & 31;
@@ -357,22 +379,22 @@ __device__ __forceinline__ Item warp_fetch_item(const uint8_t* __restrict__ base
     it.q = q;
     it.t0 = (int)(blk * 16 - s);
     it.first_block = (c == 0) || !it.live;
-    it.raw = it.live ? ld_block(bases + blk * 16) : make_uint4(0u, 0u, 0u, 0u);
+    it.raw = it.live ? load_block<FMT>(bases, blk) : make_uint4(0u, 0u, 0u, 0u);
     return it;
 }
 
 template <int K, int FMT, int NREADS_MAX, class Sink>
-__device__ __forceinline__ void warp_for_each_window(const uint8_t* __restrict__ bases, const LaneRead& lr,
+__device__ __forceinline__ void warp_for_each_window(const BasesRef& bases, const LaneRead& lr,
                                                      int n, int ncount, int mode, Sink& sink)
 {
     const uint32_t total = __shfl_sync(0xffffffffu, lr.cum + lr.nblk, 31);
     const uint32_t nchunks = (total + 30u) / 31u;
     if (nchunks == 0) return;
     const bool any_empty = __ballot_sync(0xffffffffu, (threadIdx.x & 31) < n && lr.nblk == 0) != 0u;
-    Item next = warp_fetch_item<NREADS_MAX>(bases, lr, n, total, 0, any_empty);
+    Item next = warp_fetch_item<FMT, NREADS_MAX>(bases, lr, n, total, 0, any_empty);
     for (uint32_t chunk = 0; chunk < nchunks; chunk++) {
         const Item cur = next;
-        if (chunk + 1 < nchunks) next = warp_fetch_item<NREADS_MAX>(bases, lr, n, total, chunk + 1, any_empty);
+        if (chunk + 1 < nchunks) next = warp_fetch_item<FMT, NREADS_MAX>(bases, lr, n, total, chunk + 1, any_empty);
         emit_item<K, FMT>(cur, ncount, mode, sink);
     }
 }

@@ -98,6 +98,18 @@ int cfrk_count_dense_device(const void *d_bases, int fmt, const int64_t *d_start
                             int32_t *d_freq, void *stream);
 int cfrk_dense_reads_per_tile(int k);
 
+/*
+ * The same operator on PACKED reads: d_codes / d_valid are what cfrk_encode_2bit_device wrote
+ * (16 bases per uint32, first base in the top bits; validity bit 15-j for base 16w+j), start[]
+ * and length[] still count bases.  This is the batch layout that replaces the reference's
+ * 1-byte-per-base `struct read` (src/tipos.h:23-30): encode once, count for any number of k.
+ */
+int cfrk_count_dense_packed_device(const uint32_t *d_codes, const uint16_t *d_valid,
+                                   const int64_t *d_start, const int32_t *d_length, int64_t nN,
+                                   int64_t nS, int64_t read_begin, int64_t read_end, int k,
+                                   int mode, int64_t chunk_size, int64_t first_read_index,
+                                   int32_t *d_freq, void *stream);
+
 /* ---- stages of the north-star pipeline exposed on their own ------------------------- */
 
 /*

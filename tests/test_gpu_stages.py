@@ -194,3 +194,24 @@ def test_big_rows_under_load(k, nS):
         hi = min(nS, i + 2)
         want = ob.count_dense(h[i:hi].reshape(-1), np.arange(hi - i) * (L + 1), np.full(hi - i, L), k)[0]
         np.testing.assert_array_equal(out[i].cpu().numpy(), want)
+
+
+@pytest.mark.parametrize("k", [1, 3, 4, 5, 6, 7, 8])
+def test_packed_reads_layout(k):
+    """encode once (2-bit codes + validity), count from the packed layout: same rows as from the bytes"""
+    text = fx.fx_with_n() + fx.fx_ragged() + fx.fx_multiline()
+    raw, start, length = fx.ascii_compact(text)
+    data, _, _ = ob.parse_fasta(text=text)
+    n = len(raw)
+    b = padded_bases(raw, 0)
+    nb = (n + 15) // 16
+    codes = torch.zeros(nb + 1, dtype=torch.int32, device="cuda")
+    valid = torch.zeros(nb + 1, dtype=torch.int16, device="cuda")
+    cf.encode_2bit_device(b.data_ptr(), n, codes.data_ptr(), valid.data_ptr(), fmt=cf.FMT_ASCII)
+    s, l = dev(start), dev(length)
+    for mode in (cf.MODE_COMPAT, cf.MODE_EXACT):
+        out = torch.full((len(start), 4 ** k), -3, dtype=torch.int32, device="cuda")
+        cf.count_dense_packed_device(codes.data_ptr(), valid.data_ptr(), s.data_ptr(), l.data_ptr(), n, len(start), k,
+                                     out.data_ptr(), mode=mode)
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(out.cpu().numpy(), ob.count_dense(data, start, length, k, mode))
