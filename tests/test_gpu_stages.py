@@ -215,3 +215,24 @@ def test_packed_reads_layout(k):
                                      out.data_ptr(), mode=mode)
         torch.cuda.synchronize()
         np.testing.assert_array_equal(out.cpu().numpy(), ob.count_dense(data, start, length, k, mode))
+
+
+@pytest.mark.parametrize("k", [1, 2, 3, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("mode", [cf.MODE_COMPAT, cf.MODE_EXACT], ids=["compat", "exact"])
+def test_no_write_outside_the_rows(k, mode):
+    """guard rows before and after the output stay untouched (the reference stores Freq[-1];
+    compute-sanitizer is closed on this pool, so out-of-bounds writes are checked this way)"""
+    data, start, length = ob.parse_fasta(text=fx.fx_with_n() + fx.fx_ragged() + fx.fx_short())
+    nS = len(start)
+    bins = 4 ** k
+    guard = max(1, (4096 + bins - 1) // bins)          # at least 16 KiB of guard on each side
+    buf = torch.full(((nS + 2 * guard) * bins,), 0x5A5A5A5A, dtype=torch.int32, device="cuda")
+    out = buf[guard * bins:(guard + nS) * bins]
+    b, s, l = padded_bases(data, 0xFF), dev(start), dev(length)
+    cuts = [0, nS // 3, nS // 3 + 1, nS]
+    for a, e in zip(cuts, cuts[1:]):
+        cf.count_dense_device(b.data_ptr(), s.data_ptr(), l.data_ptr(), len(data), nS, k, out[a * bins:].data_ptr(),
+                              mode=mode, read_begin=a, read_end=e)
+    torch.cuda.synchronize()
+    assert bool((buf[: guard * bins] == 0x5A5A5A5A).all()) and bool((buf[(guard + nS) * bins:] == 0x5A5A5A5A).all())
+    np.testing.assert_array_equal(out.view(nS, bins).cpu().numpy(), ob.count_dense_fast(data, start, length, k, mode))
