@@ -11,19 +11,54 @@
 //            with funnel shifts, the 32*E keys are sorted by a bitonic network that lives entirely
 //            in registers (blocked layout: strides < E are register swaps, the others shfl.xor) and
 //            run-length encoded with two warp scans.  Hand-written, no library.
-//   long reads: key generation kernel -> cub::DeviceSegmentedRadixSort (LIBRARY sort, to be
-//            replaced) -> hand-written per-row run-length encode.
+//   long reads: key generation kernel -> hand-written segmented LSD radix sort (8-bit digits, one
+//            warp per 2048-key tile, stable ranks from match.any, per-row offsets from ONE flat
+//            uint32 scan used modulo 2^32) -> per-row run-length encode.  cub::DeviceScan is the
+//            only library call (plumbing).
 #include "kernels.h"
 #include "kmer_device.cuh"
 
 #include <cub/device/device_scan.cuh>
-#include <cub/device/device_segmented_radix_sort.cuh>
 
 #include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace cfrk {
 
 extern void count_launch();
+
+// Scratch comes from the stream-ordered pool.  By default the pool gives freed memory back to the
+// OS at the next synchronisation, so every call would map its gigabytes of scratch again (measured:
+// 1.4 s per call for 3.3 GB); keep it cached instead.
+static void keep_pool_memory(int dev)
+{
+    static thread_local int done_for = -1;
+    if (done_for == dev) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+    done_for = dev;
+}
+
+// CFRK_TRACE=1: per-phase wall times of the sparse path on stderr (synchronises the stream)
+struct SparseTrace {
+    bool on = getenv("CFRK_TRACE") != nullptr;
+    cudaStream_t st;
+    std::chrono::steady_clock::time_point last = std::chrono::steady_clock::now();
+    explicit SparseTrace(cudaStream_t s) : st(s) {}
+    void mark(const char* what)
+    {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[cfrk sparse] %9.3f ms  %s\n", std::chrono::duration<double, std::milli>(now - last).count(), what);
+        last = now;
+    }
+};
 
 constexpr int kShortMaxWindows = 512;
 constexpr int kStreamBlocks = (15 + kShortMaxWindows + 30 + 15) / 16 + 3;  // 16-base blocks per warp stream
@@ -265,9 +300,11 @@ __global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) sparse_short_kernel(
 }
 
 // ------------------------------------------------------------------------------------------
-// long reads
-__global__ void collect_long_kernel(const int32_t* __restrict__ length, int64_t nS, int k,
-                                    const int64_t* __restrict__ row_begin, int64_t* __restrict__ long_rows,
+// long reads (> 512 windows)
+constexpr int kSortTile = 2048;   // keys per warp tile of the radix sort
+constexpr int kSortWarps = 8;
+
+__global__ void collect_long_kernel(const int32_t* __restrict__ length, int64_t nS, int k, int64_t* __restrict__ long_rows,
                                     unsigned long long* __restrict__ n_long, int64_t cap)
 {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nS; r += (int64_t)gridDim.x * blockDim.x) {
@@ -278,21 +315,41 @@ __global__ void collect_long_kernel(const int32_t* __restrict__ length, int64_t 
     }
 }
 
+// per long row j: windows and sort tiles (inputs of the two exclusive scans -> loff, ltile)
+__global__ void long_sizes_kernel(const int64_t* __restrict__ long_rows, int64_t n_long, const int32_t* __restrict__ length,
+                                  int k, int64_t* __restrict__ loff, int64_t* __restrict__ ltile)
+{
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j <= n_long) {
+        const int64_t nwin = j < n_long ? length[long_rows[j]] - k + 1 : 0;
+        loff[j] = nwin;
+        ltile[j] = (nwin + kSortTile - 1) / kSortTile;
+    }
+}
+
+template <typename KeyT>
+__device__ __forceinline__ KeyT invalid_marker(int k)
+{
+    // sorts behind every real key; when the key type has a spare bit the sort needs 2k+1 bits only
+    return 2 * k < (int)sizeof(KeyT) * 8 ? (KeyT)1 << (2 * k) : KeyMax<KeyT>::value;
+}
+
 // one CTA per long row: scalar rolling index, 16 windows per thread per pass
 template <typename KeyT, int FMT>
 __global__ void __launch_bounds__(256) long_keygen_kernel(const uint8_t* __restrict__ bases,
                                                           const int64_t* __restrict__ start,
                                                           const int32_t* __restrict__ length, int k,
                                                           const int64_t* __restrict__ long_rows,
-                                                          const int64_t* __restrict__ row_begin,
+                                                          const int64_t* __restrict__ loff,
                                                           KeyT* __restrict__ keys, int32_t* __restrict__ row_valid)
 {
     const int64_t r = long_rows[blockIdx.x];
     const int64_t s = start[r];
     const int len = length[r];
     const int nwin = len - k + 1;
-    KeyT* out = keys + row_begin[r];
+    KeyT* out = keys + loff[blockIdx.x];
     const KeyT mask = k * 2 >= (int)sizeof(KeyT) * 8 ? KeyMax<KeyT>::value : (((KeyT)1 << (2 * k)) - 1);
+    const KeyT bad = invalid_marker<KeyT>(k);
     int valid = 0;
     for (int w0 = threadIdx.x * 16; w0 < nwin; w0 += blockDim.x * 16) {
         KeyT key = 0;
@@ -313,7 +370,7 @@ __global__ void __launch_bounds__(256) long_keygen_kernel(const uint8_t* __restr
             const int wstart = t - k + 1;
             if (wstart >= w0) {
                 const bool good = run >= k;
-                out[wstart] = good ? key : KeyMax<KeyT>::value;
+                out[wstart] = good ? key : bad;
                 valid += good;
             }
         }
@@ -326,21 +383,93 @@ __global__ void __launch_bounds__(256) long_keygen_kernel(const uint8_t* __restr
     if (threadIdx.x == 0) row_valid[r] = s_valid;
 }
 
-__global__ void long_segments_kernel(const int64_t* __restrict__ long_rows, int64_t n_long,
-                                     const int64_t* __restrict__ row_begin, const int32_t* __restrict__ length, int k,
-                                     int64_t* __restrict__ seg_begin, int64_t* __restrict__ seg_end)
+// tile t of the flat tile list -> long row j, tile inside the row, keys of the tile
+struct SortTile {
+    int64_t j, tin, ntiles, key0;   // key0 = offset of the tile's first key in the scratch arrays
+    int n;                          // keys in the tile
+};
+__device__ __forceinline__ SortTile locate_tile(int64_t t, const int64_t* __restrict__ ltile,
+                                                const int64_t* __restrict__ loff, int64_t n_long)
 {
-    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n_long) {
-        const int64_t r = long_rows[j];
-        seg_begin[j] = row_begin[r];
-        seg_end[j] = row_begin[r] + (length[r] - k + 1);
+    int64_t lo = 0, hi = n_long;   // last j with ltile[j] <= t
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (ltile[mid] <= t) lo = mid; else hi = mid;
+    }
+    SortTile st;
+    st.j = lo;
+    st.tin = t - ltile[lo];
+    st.ntiles = ltile[lo + 1] - ltile[lo];
+    const int64_t nwin = loff[lo + 1] - loff[lo];
+    st.key0 = loff[lo] + st.tin * kSortTile;
+    st.n = (int)min((int64_t)kSortTile, nwin - st.tin * kSortTile);
+    return st;
+}
+
+// digit histogram of every tile; counter layout = row-major, then digit, then tile-in-row, so that
+// ONE flat exclusive scan gives, relative to the row's first counter, the destination of every
+// (digit, tile) group inside its row (uint32 arithmetic modulo 2^32: rows are < 2^31 keys)
+template <typename KeyT>
+__global__ void __launch_bounds__(kSortWarps * 32) sort_hist_kernel(const KeyT* __restrict__ src, int shift,
+                                                                    const int64_t* __restrict__ ltile,
+                                                                    const int64_t* __restrict__ loff, int64_t n_long,
+                                                                    int64_t ntiles_total, uint32_t* __restrict__ counters)
+{
+    __shared__ uint32_t s_h[kSortWarps][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* h = s_h[warp];
+    for (int64_t t = (int64_t)blockIdx.x * kSortWarps + warp; t < ntiles_total; t += (int64_t)gridDim.x * kSortWarps) {
+        const SortTile st = locate_tile(t, ltile, loff, n_long);
+        for (int i = lane; i < 256; i += 32) h[i] = 0u;
+        __syncwarp();
+        for (int i = lane; i < st.n; i += 32) atomicAdd(&h[(uint32_t)(src[st.key0 + i] >> shift) & 255u], 1u);
+        __syncwarp();
+        uint32_t* c = counters + ltile[st.j] * 256;
+        for (int d = lane; d < 256; d += 32) c[(int64_t)d * st.ntiles + st.tin] = h[d];
+        __syncwarp();
+    }
+}
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kSortWarps * 32) sort_scatter_kernel(const KeyT* __restrict__ src, KeyT* __restrict__ dst,
+                                                                       int shift, const int64_t* __restrict__ ltile,
+                                                                       const int64_t* __restrict__ loff, int64_t n_long,
+                                                                       int64_t ntiles_total,
+                                                                       const uint32_t* __restrict__ scanned)
+{
+    __shared__ uint32_t s_b[kSortWarps][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t* base = s_b[warp];
+    for (int64_t t = (int64_t)blockIdx.x * kSortWarps + warp; t < ntiles_total; t += (int64_t)gridDim.x * kSortWarps) {
+        const SortTile st = locate_tile(t, ltile, loff, n_long);
+        const uint32_t* c = scanned + ltile[st.j] * 256;
+        const uint32_t row0 = c[0];
+        for (int d = lane; d < 256; d += 32) base[d] = c[(int64_t)d * st.ntiles + st.tin] - row0;
+        __syncwarp();
+        KeyT* out = dst + loff[st.j];
+        for (int i0 = 0; i0 < st.n; i0 += 32) {        // keys in index order: stable
+            const int i = i0 + lane;
+            const bool live = i < st.n;
+            const KeyT key = live ? src[st.key0 + i] : (KeyT)0;
+            const uint32_t d = (uint32_t)(key >> shift) & 255u;
+            const uint32_t active = __ballot_sync(0xffffffffu, live);
+            if (live) {
+                const uint32_t peers = __match_any_sync(active, d);
+                const uint32_t b = base[d];
+                const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+                out[b + rank] = key;
+                __syncwarp(active);
+                if (rank == 0) base[d] = b + __popc(peers);
+            }
+            __syncwarp();
+        }
     }
 }
 
 // sorted keys of one long row (first nvalid real) -> (key,count) pairs, one CTA per row
 template <typename KeyT>
 __global__ void __launch_bounds__(256) long_rle_kernel(const int64_t* __restrict__ long_rows,
+                                                       const int64_t* __restrict__ loff,
                                                        const int64_t* __restrict__ row_begin,
                                                        const KeyT* __restrict__ sorted, KeyT* __restrict__ keys,
                                                        uint32_t* __restrict__ counts, int32_t* __restrict__ row_count)
@@ -349,7 +478,7 @@ __global__ void __launch_bounds__(256) long_rle_kernel(const int64_t* __restrict
     const int64_t r = long_rows[blockIdx.x];
     const int64_t base = row_begin[r];
     const int nvalid = row_count[r];   // holds the number of valid windows on entry
-    const KeyT* in = sorted + base;
+    const KeyT* in = sorted + loff[blockIdx.x];
     KeyT* ko = keys + base;
     uint32_t* co = counts + base;      // pass 1: position of each head; pass 2: run lengths
     __shared__ int s_warp[T / 32];
@@ -375,7 +504,7 @@ __global__ void __launch_bounds__(256) long_rle_kernel(const int64_t* __restrict
             total += x;
         }
         const int pos = nheads + before + __popc(bal & ((1u << lane) - 1u));
-        __syncthreads();   // all reads of `in` for this chunk are done (ko may alias `sorted`'s row)
+        __syncthreads();
         if (head) { ko[pos] = v; co[pos] = (uint32_t)g; }
         nheads += total;
     }
@@ -407,6 +536,8 @@ static cudaError_t sparse_impl(const void* bases, const int64_t* start, const in
     if ((e = cudaGetDevice(&dev)) != cudaSuccess) return e;
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
 
+    SparseTrace tr(st);
+    keep_pool_memory(dev);
     // 1. row_begin = exclusive scan of window counts
     nwin_kernel<<<num_sms * 4, 256, 0, st>>>(length, nS, k, row_begin);
     count_launch();
@@ -423,6 +554,7 @@ static cudaError_t sparse_impl(const void* bases, const int64_t* start, const in
     if (total_windows) *total_windows = total;
     if (total > capacity) return cudaErrorInvalidValue;   // caller maps to CFRK_EINVAL "capacity"
 
+    tr.mark("row offsets");
     // 2. short reads: one warp per read
     {
         const int64_t ctas = (nS + kSparseWarps - 1) / kSparseWarps;
@@ -437,6 +569,7 @@ static cudaError_t sparse_impl(const void* bases, const int64_t* start, const in
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
 
+    tr.mark("short reads");
     // 3. long reads
     int64_t* long_rows = nullptr;
     unsigned long long* d_nlong = nullptr;
@@ -444,42 +577,71 @@ static cudaError_t sparse_impl(const void* bases, const int64_t* start, const in
     if ((e = cudaMallocAsync(reinterpret_cast<void**>(&long_rows), (size_t)cap_long * 8, st)) != cudaSuccess) return e;
     if ((e = cudaMallocAsync(reinterpret_cast<void**>(&d_nlong), 8, st)) != cudaSuccess) return e;
     cudaMemsetAsync(d_nlong, 0, 8, st);
-    collect_long_kernel<<<num_sms * 4, 256, 0, st>>>(length, nS, k, row_begin, long_rows, d_nlong, cap_long);
+    collect_long_kernel<<<num_sms * 4, 256, 0, st>>>(length, nS, k, long_rows, d_nlong, cap_long);
     count_launch();
     unsigned long long n_long = 0;
     cudaMemcpyAsync(&n_long, d_nlong, 8, cudaMemcpyDeviceToHost, st);
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
     if (n_long > 0) {
-        KeyT* unsorted = nullptr;
-        int64_t *seg_b = nullptr, *seg_e = nullptr;
-        if ((e = cudaMallocAsync(reinterpret_cast<void**>(&unsorted), (size_t)total * sizeof(KeyT), st)) != cudaSuccess) return e;
-        if ((e = cudaMallocAsync(reinterpret_cast<void**>(&seg_b), (size_t)n_long * 8, st)) != cudaSuccess) return e;
-        if ((e = cudaMallocAsync(reinterpret_cast<void**>(&seg_e), (size_t)n_long * 8, st)) != cudaSuccess) return e;
-        long_keygen_kernel<KeyT, FMT><<<(unsigned)n_long, 256, 0, st>>>(static_cast<const uint8_t*>(bases), start, length, k,
-                                                                       long_rows, row_begin, unsorted, row_count);
+        const int64_t nl = (int64_t)n_long;
+        int64_t *loff = nullptr, *ltile = nullptr;
+        if ((e = cudaMallocAsync(reinterpret_cast<void**>(&loff), (size_t)(nl + 1) * 8, st)) != cudaSuccess) return e;
+        if ((e = cudaMallocAsync(reinterpret_cast<void**>(&ltile), (size_t)(nl + 1) * 8, st)) != cudaSuccess) return e;
+        long_sizes_kernel<<<(unsigned)((nl + 256) / 256), 256, 0, st>>>(long_rows, nl, length, k, loff, ltile);
         count_launch();
-        long_segments_kernel<<<(unsigned)((n_long + 255) / 256), 256, 0, st>>>(long_rows, (int64_t)n_long, row_begin, length,
-                                                                              k, seg_b, seg_e);
+        size_t sb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, sb, loff, loff, nl + 1, st);
+        void* stmp = nullptr;
+        if ((e = cudaMallocAsync(&stmp, sb ? sb : 16, st)) != cudaSuccess) return e;
+        if ((e = cub::DeviceScan::ExclusiveSum(stmp, sb, loff, loff, nl + 1, st)) != cudaSuccess) return e;
+        if ((e = cub::DeviceScan::ExclusiveSum(stmp, sb, ltile, ltile, nl + 1, st)) != cudaSuccess) return e;
+        cudaFreeAsync(stmp, st);
+        int64_t total_long = 0, ntiles = 0;
+        cudaMemcpyAsync(&total_long, loff + nl, 8, cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(&ntiles, ltile + nl, 8, cudaMemcpyDeviceToHost, st);
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+
+        KeyT *bufA = nullptr, *bufB = nullptr;
+        uint32_t* counters = nullptr;
+        const size_t ncount = (size_t)ntiles * 256;
+        if ((e = cudaMallocAsync(reinterpret_cast<void**>(&bufA), (size_t)total_long * sizeof(KeyT), st)) != cudaSuccess) return e;
+        if ((e = cudaMallocAsync(reinterpret_cast<void**>(&bufB), (size_t)total_long * sizeof(KeyT), st)) != cudaSuccess) return e;
+        if ((e = cudaMallocAsync(reinterpret_cast<void**>(&counters), ncount * 4, st)) != cudaSuccess) return e;
+        tr.mark("long rows: collect + scratch");
+        long_keygen_kernel<KeyT, FMT><<<(unsigned)nl, 256, 0, st>>>(static_cast<const uint8_t*>(bases), start, length, k,
+                                                                   long_rows, loff, bufA, row_count);
         count_launch();
-        // LIBRARY: segmented radix sort of the long rows (unsorted -> keys)
-        size_t sort_bytes = 0;
-        e = cub::DeviceSegmentedRadixSort::SortKeys(nullptr, sort_bytes, unsorted, keys, total, (int)n_long, seg_b, seg_e,
-                                                    0, sizeof(KeyT) * 8, st);
-        if (e != cudaSuccess) return e;
-        void* sort_tmp = nullptr;
-        if ((e = cudaMallocAsync(&sort_tmp, sort_bytes ? sort_bytes : 16, st)) != cudaSuccess) return e;
-        e = cub::DeviceSegmentedRadixSort::SortKeys(sort_tmp, sort_bytes, unsorted, keys, total, (int)n_long, seg_b, seg_e,
-                                                    0, sizeof(KeyT) * 8, st);
-        if (e != cudaSuccess) return e;
-        // the sorted rows sit in `keys`; copy them back so that the RLE can write `keys` in place
-        // from a stable source
-        if ((e = cudaMemcpyAsync(unsorted, keys, (size_t)total * sizeof(KeyT), cudaMemcpyDeviceToDevice, st)) != cudaSuccess) return e;
-        long_rle_kernel<KeyT><<<(unsigned)n_long, 256, 0, st>>>(long_rows, row_begin, unsorted, keys, counts, row_count);
+        tr.mark("long rows: key generation");
+        // segmented LSD radix sort, 8 bits per pass, over the bits that can differ
+        const int key_bits = (int)sizeof(KeyT) * 8;
+        const int nbits = 2 * k + 1 < key_bits ? 2 * k + 1 : key_bits;
+        const int passes = (nbits + 7) / 8;
+        size_t cb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, cb, counters, counters, (int64_t)ncount, st);
+        void* ctmp = nullptr;
+        if ((e = cudaMallocAsync(&ctmp, cb ? cb : 16, st)) != cudaSuccess) return e;
+        const int64_t ctas = (ntiles + kSortWarps - 1) / kSortWarps;
+        const unsigned sgrid = (unsigned)(ctas < (int64_t)num_sms * 8 ? ctas : (int64_t)num_sms * 8);
+        KeyT *src = bufA, *dst = bufB;
+        for (int p = 0; p < passes; p++) {
+            sort_hist_kernel<KeyT><<<sgrid, kSortWarps * 32, 0, st>>>(src, 8 * p, ltile, loff, nl, ntiles, counters);
+            tr.mark("  sort pass: histogram");
+            if ((e = cub::DeviceScan::ExclusiveSum(ctmp, cb, counters, counters, (int64_t)ncount, st)) != cudaSuccess) return e;
+            tr.mark("  sort pass: scan");
+            sort_scatter_kernel<KeyT><<<sgrid, kSortWarps * 32, 0, st>>>(src, dst, 8 * p, ltile, loff, nl, ntiles, counters);
+            tr.mark("  sort pass: scatter");
+            count_launch(); count_launch();
+            KeyT* tmpp = src; src = dst; dst = tmpp;
+        }
+        long_rle_kernel<KeyT><<<(unsigned)nl, 256, 0, st>>>(long_rows, loff, row_begin, src, keys, counts, row_count);
         count_launch();
-        cudaFreeAsync(sort_tmp, st);
-        cudaFreeAsync(unsorted, st);
-        cudaFreeAsync(seg_b, st);
-        cudaFreeAsync(seg_e, st);
+        tr.mark("long rows: run-length encode");
+        cudaFreeAsync(ctmp, st);
+        cudaFreeAsync(counters, st);
+        cudaFreeAsync(bufA, st);
+        cudaFreeAsync(bufB, st);
+        cudaFreeAsync(loff, st);
+        cudaFreeAsync(ltile, st);
     }
     cudaFreeAsync(long_rows, st);
     cudaFreeAsync(d_nlong, st);
