@@ -24,6 +24,9 @@
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <utility>
+#include <vector>
+#include <algorithm>
 
 namespace cfrk {
 
@@ -300,9 +303,32 @@ __global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) sparse_short_kernel(
 }
 
 // ------------------------------------------------------------------------------------------
-// long reads (> 512 windows)
-constexpr int kSortTile = 2048;   // keys per warp tile of the radix sort
+// long reads (> 512 windows): MSD partition + one warp sort per bucket
+//
+//   A row of n windows is split by the top B bits of its keys into 2^B buckets (B chosen per row so
+//   that uniform keys give <= 256 per bucket).  Two passes over the BASES do the split (keys are
+//   never stored unsorted more than once): pass 1 counts the buckets, pass 2 scatters the keys
+//   behind the scanned counts.  Every bucket of <= 512 keys is then sorted by ONE WARP with the
+//   same register network as the short reads and run-length encoded in place; buckets are disjoint
+//   key ranges, so their (key, count) runs are final and only have to be moved behind each other
+//   (scan of the distinct counts + copy).  Buckets above 512 keys (skewed or low-complexity rows)
+//   take the segmented LSD radix sort below.  Rows are processed in batches of <= 128 Mi windows,
+//   which bounds the scratch to 12 bytes per window of one batch.
+constexpr int kBucketTarget = 256;       // mean keys per bucket at most this (uniform keys)
+constexpr int kBucketCap = 512;          // what one warp sorts in registers (E = 16)
+constexpr int kMaxBucketBits = 22;
+constexpr int kPartTile = 4096;          // windows per CTA tile of the two partition passes
+constexpr int kPartBlocks = (15 + kPartTile + 30 + 15) / 16 + 3;
+constexpr int64_t kBatchKeys = (int64_t)128 << 20;
+constexpr int kSortTile = 2048;          // keys per warp tile of the fallback radix sort
 constexpr int kSortWarps = 8;
+
+__host__ __device__ __forceinline__ int bucket_bits(int64_t nwin, int k)
+{
+    int b = 0;
+    while (b < kMaxBucketBits && ((int64_t)kBucketTarget << b) < nwin) b++;
+    return b < 2 * k ? b : 2 * k;
+}
 
 __global__ void collect_long_kernel(const int32_t* __restrict__ length, int64_t nS, int k, int64_t* __restrict__ long_rows,
                                     unsigned long long* __restrict__ n_long, int64_t cap)
@@ -315,116 +341,176 @@ __global__ void collect_long_kernel(const int32_t* __restrict__ length, int64_t 
     }
 }
 
-// per long row j: windows and sort tiles (inputs of the two exclusive scans -> loff, ltile)
+// per long row j: windows, buckets and partition tiles (inputs of three exclusive scans)
 __global__ void long_sizes_kernel(const int64_t* __restrict__ long_rows, int64_t n_long, const int32_t* __restrict__ length,
-                                  int k, int64_t* __restrict__ loff, int64_t* __restrict__ ltile)
+                                  int k, int64_t* __restrict__ loff, int64_t* __restrict__ boff, int64_t* __restrict__ ptile)
 {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j <= n_long) {
         const int64_t nwin = j < n_long ? length[long_rows[j]] - k + 1 : 0;
         loff[j] = nwin;
-        ltile[j] = (nwin + kSortTile - 1) / kSortTile;
+        boff[j] = j < n_long ? (int64_t)1 << bucket_bits(nwin, k) : 0;
+        ptile[j] = (nwin + kPartTile - 1) / kPartTile;
     }
 }
 
-template <typename KeyT>
-__device__ __forceinline__ KeyT invalid_marker(int k)
+// last j in [lo, hi) with scan[j] <= t (scan strictly increasing, scan[lo] <= t < scan[hi])
+__device__ __forceinline__ int64_t locate(const int64_t* __restrict__ scan, int64_t lo, int64_t hi, int64_t t)
 {
-    // sorts behind every real key; when the key type has a spare bit the sort needs 2k+1 bits only
-    return 2 * k < (int)sizeof(KeyT) * 8 ? (KeyT)1 << (2 * k) : KeyMax<KeyT>::value;
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (scan[mid] <= t) lo = mid; else hi = mid;
+    }
+    return lo;
 }
 
-// one CTA per long row: scalar rolling index, 16 windows per thread per pass
-template <typename KeyT, int FMT>
-__global__ void __launch_bounds__(256) long_keygen_kernel(const uint8_t* __restrict__ bases,
-                                                          const int64_t* __restrict__ start,
-                                                          const int32_t* __restrict__ length, int k,
-                                                          const int64_t* __restrict__ long_rows,
-                                                          const int64_t* __restrict__ loff,
-                                                          KeyT* __restrict__ keys, int32_t* __restrict__ row_valid)
+// Partition pass over the bases of the batch rows [j0, j1): CTA tiles of 4096 windows, the tile's
+// bases encoded once into a shared-memory bit stream (as for the short reads), every thread
+// extracts windows by funnel shift.  SCATTER = false: count the buckets.  SCATTER = true: bucket[]
+// holds the scanned counts; a key takes the next slot of its bucket (afterwards bucket[b] = end of b).
+template <typename KeyT, int FMT, bool SCATTER>
+__global__ void __launch_bounds__(256) partition_kernel(const uint8_t* __restrict__ bases, const int64_t* __restrict__ start,
+                                                        const int32_t* __restrict__ length, int k,
+                                                        const int64_t* __restrict__ long_rows,
+                                                        const int64_t* __restrict__ boff, const int64_t* __restrict__ ptile,
+                                                        int64_t j0, int64_t j1, unsigned long long* __restrict__ bucket,
+                                                        KeyT* __restrict__ scratch)
 {
-    const int64_t r = long_rows[blockIdx.x];
-    const int64_t s = start[r];
-    const int len = length[r];
-    const int nwin = len - k + 1;
-    KeyT* out = keys + loff[blockIdx.x];
-    const KeyT mask = k * 2 >= (int)sizeof(KeyT) * 8 ? KeyMax<KeyT>::value : (((KeyT)1 << (2 * k)) - 1);
-    const KeyT bad = invalid_marker<KeyT>(k);
-    int valid = 0;
-    for (int w0 = threadIdx.x * 16; w0 < nwin; w0 += blockDim.x * 16) {
-        KeyT key = 0;
-        int run = 0;
-        const int wend = min(nwin, w0 + 16);
-        for (int t = w0; t < wend + k - 1; t++) {       // base t closes the window starting at t-k+1
-            const uint32_t c = bases[s + t];
-            uint32_t code; bool ok;
-            if (FMT == FMT_ASCII) {
-                const uint32_t u = c & 0xDFu;
-                code = ((c >> 1) ^ (c >> 2)) & 3u;
-                ok = u == 'A' || u == 'C' || u == 'G' || u == 'T';
-            } else {
-                code = c & 3u; ok = !(c & 0x80u);
+    __shared__ uint32_t s_cw[kPartBlocks];
+    __shared__ __align__(4) uint16_t s_vh[2 * ((kPartBlocks + 1) / 2) + 2];
+    WarpStream st{s_cw, s_vh};
+    const int64_t t0 = ptile[j0], ntiles = ptile[j1] - t0, b0 = boff[j0];
+    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int64_t j = locate(ptile, j0, j1, t0 + t);
+        const int64_t r = long_rows[j];
+        const int64_t s = start[r];
+        const int len = length[r];
+        const int nwin = len - k + 1;
+        const int64_t w0 = (t0 + t - ptile[j]) * kPartTile;
+        const int n = (int)min((int64_t)kPartTile, nwin - w0);
+        const int shift = 2 * k - bucket_bits(nwin, k);
+        // stream position 0 = first byte of the 16-byte block that holds base w0 of the read
+        const int64_t blk0 = (s + w0) >> 4;
+        const int a = (int)((s + w0) & 15);
+        const int nblocks = (a + n + k - 1 + 15) >> 4;
+        const int64_t rs = s - blk0 * 16, re = s + len - blk0 * 16;   // the read in stream coordinates
+        __syncthreads();   // the previous tile has been read
+        for (int b = threadIdx.x; b < kPartBlocks; b += 256) {
+            uint32_t c = 0, v = 0;
+            if (b < nblocks) {
+                encode16<FMT>(ld_block(bases + (blk0 + b) * 16), c, v);
+                const int lo = (int)max((int64_t)0, min((int64_t)16, rs - 16 * b));
+                const int hi = (int)max((int64_t)0, min((int64_t)16, re - 16 * b));
+                v &= from_pos(lo) & ~from_pos(hi);
             }
-            key = ((key << 2) | code) & mask;
-            run = ok ? run + 1 : 0;
-            const int wstart = t - k + 1;
-            if (wstart >= w0) {
-                const bool good = run >= k;
-                out[wstart] = good ? key : bad;
-                valid += good;
+            st.cw[b] = c;
+            st.vh[b ^ 1] = (uint16_t)v;
+        }
+        __syncthreads();
+        unsigned long long* bk = bucket + (boff[j] - b0);
+        for (int g = threadIdx.x; g < n; g += 256) {
+            KeyT key;
+            if (stream_window<KeyT>(st, a + g, k, key)) {
+                const uint64_t d = (uint64_t)key >> shift;
+                if (SCATTER) {
+                    const unsigned long long pos = atomicAdd(&bk[d], 1ull);
+                    scratch[pos] = key;
+                } else {
+                    atomicAdd(&bk[d], 1ull);
+                }
             }
         }
     }
-    __shared__ int s_valid;
-    if (threadIdx.x == 0) s_valid = 0;
-    __syncthreads();
-    atomicAdd(&s_valid, valid);
-    __syncthreads();
-    if (threadIdx.x == 0) row_valid[r] = s_valid;
 }
 
-// tile t of the flat tile list -> long row j, tile inside the row, keys of the tile
+// one warp per bucket of <= 32*E keys: load, sort in registers, run-length encode IN PLACE (the
+// pairs of bucket b start where its keys started).  The E = 4 instance also lists the buckets that
+// are too large for a warp.
+template <typename KeyT, int E>
+__global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) bucket_sort_kernel(
+    const unsigned long long* __restrict__ bend, int64_t nb, KeyT* __restrict__ scratch, uint32_t* __restrict__ pc,
+    unsigned long long* __restrict__ distinct, int64_t* __restrict__ fb_list, unsigned long long* __restrict__ n_fb)
+{
+    constexpr int WARPS = SparseCta<E>::WARPS;
+    __shared__ KeyT s_stage_k[WARPS][32 * E];
+    __shared__ uint32_t s_stage_c[WARPS][32 * E];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t b = (int64_t)blockIdx.x * WARPS + warp; b < nb; b += (int64_t)gridDim.x * WARPS) {
+        const int64_t beg = b ? (int64_t)bend[b - 1] : 0;
+        const int64_t n64 = (int64_t)bend[b] - beg;
+        if (E == 4 && n64 > kBucketCap && lane == 0) fb_list[atomicAdd(n_fb, 1ull)] = b;
+        if (n64 == 0 || n64 > 32 * E || (E > 4 && n64 <= 16 * E)) continue;
+        const int n = (int)n64;
+        KeyT key[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) {      // any placement will do: the network sorts it
+            const int g = e * 32 + lane;
+            key[e] = g < n ? scratch[beg + g] : KeyMax<KeyT>::value;
+        }
+        bitonic_sort_blocked<KeyT, E>(key);
+        const int nd = warp_rle_store<KeyT, E>(key, n, scratch + beg, pc + beg, s_stage_k[warp], s_stage_c[warp]);
+        if (lane == 0) distinct[b] = (unsigned long long)nd;
+    }
+}
+
+// ---- fallback for buckets above 512 keys: segmented LSD radix sort (8-bit digits, one warp per
+// 2048-key tile, stable ranks from match.any, per-segment offsets from ONE flat uint32 scan used
+// modulo 2^32: segments are < 2^31 keys)
+__global__ void fallback_segments_kernel(const int64_t* __restrict__ fb_list, int64_t nfb,
+                                         const unsigned long long* __restrict__ bend, int64_t* __restrict__ seg_begin,
+                                         int64_t* __restrict__ seg_n, int64_t* __restrict__ stile)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nfb) {
+        const int64_t b = fb_list[i];
+        const int64_t beg = b ? (int64_t)bend[b - 1] : 0;
+        const int64_t n = (int64_t)bend[b] - beg;
+        seg_begin[i] = beg;
+        seg_n[i] = n;
+        stile[i] = (n + kSortTile - 1) / kSortTile;
+    } else if (i == nfb) {
+        stile[i] = 0;
+    }
+}
+
+// tile t of the flat tile list -> segment, tile inside the segment, keys of the tile
 struct SortTile {
     int64_t j, tin, ntiles, key0;   // key0 = offset of the tile's first key in the scratch arrays
     int n;                          // keys in the tile
 };
-__device__ __forceinline__ SortTile locate_tile(int64_t t, const int64_t* __restrict__ ltile,
-                                                const int64_t* __restrict__ loff, int64_t n_long)
+__device__ __forceinline__ SortTile locate_tile(int64_t t, const int64_t* __restrict__ stile,
+                                                const int64_t* __restrict__ seg_begin,
+                                                const int64_t* __restrict__ seg_n, int64_t nseg)
 {
-    int64_t lo = 0, hi = n_long;   // last j with ltile[j] <= t
-    while (hi - lo > 1) {
-        const int64_t mid = (lo + hi) >> 1;
-        if (ltile[mid] <= t) lo = mid; else hi = mid;
-    }
     SortTile st;
-    st.j = lo;
-    st.tin = t - ltile[lo];
-    st.ntiles = ltile[lo + 1] - ltile[lo];
-    const int64_t nwin = loff[lo + 1] - loff[lo];
-    st.key0 = loff[lo] + st.tin * kSortTile;
-    st.n = (int)min((int64_t)kSortTile, nwin - st.tin * kSortTile);
+    st.j = locate(stile, 0, nseg, t);
+    st.tin = t - stile[st.j];
+    st.ntiles = stile[st.j + 1] - stile[st.j];
+    st.key0 = seg_begin[st.j] + st.tin * kSortTile;
+    st.n = (int)min((int64_t)kSortTile, seg_n[st.j] - st.tin * kSortTile);
     return st;
 }
 
-// digit histogram of every tile; counter layout = row-major, then digit, then tile-in-row, so that
-// ONE flat exclusive scan gives, relative to the row's first counter, the destination of every
-// (digit, tile) group inside its row (uint32 arithmetic modulo 2^32: rows are < 2^31 keys)
+// digit histogram of every tile; counter layout = segment-major, then digit, then tile-in-segment,
+// so that ONE flat exclusive scan gives, relative to the segment's first counter, the destination
+// of every (digit, tile) group inside its segment
 template <typename KeyT>
 __global__ void __launch_bounds__(kSortWarps * 32) sort_hist_kernel(const KeyT* __restrict__ src, int shift,
-                                                                    const int64_t* __restrict__ ltile,
-                                                                    const int64_t* __restrict__ loff, int64_t n_long,
+                                                                    const int64_t* __restrict__ stile,
+                                                                    const int64_t* __restrict__ seg_begin,
+                                                                    const int64_t* __restrict__ seg_n, int64_t nseg,
                                                                     int64_t ntiles_total, uint32_t* __restrict__ counters)
 {
     __shared__ uint32_t s_h[kSortWarps][256];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* h = s_h[warp];
     for (int64_t t = (int64_t)blockIdx.x * kSortWarps + warp; t < ntiles_total; t += (int64_t)gridDim.x * kSortWarps) {
-        const SortTile st = locate_tile(t, ltile, loff, n_long);
+        const SortTile st = locate_tile(t, stile, seg_begin, seg_n, nseg);
         for (int i = lane; i < 256; i += 32) h[i] = 0u;
         __syncwarp();
         for (int i = lane; i < st.n; i += 32) atomicAdd(&h[(uint32_t)(src[st.key0 + i] >> shift) & 255u], 1u);
         __syncwarp();
-        uint32_t* c = counters + ltile[st.j] * 256;
+        uint32_t* c = counters + stile[st.j] * 256;
         for (int d = lane; d < 256; d += 32) c[(int64_t)d * st.ntiles + st.tin] = h[d];
         __syncwarp();
     }
@@ -432,8 +518,9 @@ __global__ void __launch_bounds__(kSortWarps * 32) sort_hist_kernel(const KeyT* 
 
 template <typename KeyT>
 __global__ void __launch_bounds__(kSortWarps * 32) sort_scatter_kernel(const KeyT* __restrict__ src, KeyT* __restrict__ dst,
-                                                                       int shift, const int64_t* __restrict__ ltile,
-                                                                       const int64_t* __restrict__ loff, int64_t n_long,
+                                                                       int shift, const int64_t* __restrict__ stile,
+                                                                       const int64_t* __restrict__ seg_begin,
+                                                                       const int64_t* __restrict__ seg_n, int64_t nseg,
                                                                        int64_t ntiles_total,
                                                                        const uint32_t* __restrict__ scanned)
 {
@@ -441,12 +528,12 @@ __global__ void __launch_bounds__(kSortWarps * 32) sort_scatter_kernel(const Key
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t* base = s_b[warp];
     for (int64_t t = (int64_t)blockIdx.x * kSortWarps + warp; t < ntiles_total; t += (int64_t)gridDim.x * kSortWarps) {
-        const SortTile st = locate_tile(t, ltile, loff, n_long);
-        const uint32_t* c = scanned + ltile[st.j] * 256;
-        const uint32_t row0 = c[0];
-        for (int d = lane; d < 256; d += 32) base[d] = c[(int64_t)d * st.ntiles + st.tin] - row0;
+        const SortTile st = locate_tile(t, stile, seg_begin, seg_n, nseg);
+        const uint32_t* c = scanned + stile[st.j] * 256;
+        const uint32_t seg0 = c[0];
+        for (int d = lane; d < 256; d += 32) base[d] = c[(int64_t)d * st.ntiles + st.tin] - seg0;
         __syncwarp();
-        KeyT* out = dst + loff[st.j];
+        KeyT* out = dst + seg_begin[st.j];
         for (int i0 = 0; i0 < st.n; i0 += 32) {        // keys in index order: stable
             const int i = i0 + lane;
             const bool live = i < st.n;
@@ -466,23 +553,23 @@ __global__ void __launch_bounds__(kSortWarps * 32) sort_scatter_kernel(const Key
     }
 }
 
-// sorted keys of one long row (first nvalid real) -> (key,count) pairs, one CTA per row
+// sorted keys of one fallback segment -> (key,count) pairs at the start of the segment, one CTA
+// per segment.  `sorted` may be the scratch itself: a head is written at or before its own
+// position, after the chunk has been read.
 template <typename KeyT>
-__global__ void __launch_bounds__(256) long_rle_kernel(const int64_t* __restrict__ long_rows,
-                                                       const int64_t* __restrict__ loff,
-                                                       const int64_t* __restrict__ row_begin,
-                                                       const KeyT* __restrict__ sorted, KeyT* __restrict__ keys,
-                                                       uint32_t* __restrict__ counts, int32_t* __restrict__ row_count)
+__global__ void __launch_bounds__(256) segment_rle_kernel(const int64_t* __restrict__ fb_list,
+                                                          const int64_t* __restrict__ seg_begin,
+                                                          const int64_t* __restrict__ seg_n,
+                                                          const KeyT* __restrict__ sorted, KeyT* __restrict__ scratch,
+                                                          uint32_t* __restrict__ pc, unsigned long long* __restrict__ distinct)
 {
     constexpr int T = 256;
-    const int64_t r = long_rows[blockIdx.x];
-    const int64_t base = row_begin[r];
-    const int nvalid = row_count[r];   // holds the number of valid windows on entry
-    const KeyT* in = sorted + loff[blockIdx.x];
-    KeyT* ko = keys + base;
-    uint32_t* co = counts + base;      // pass 1: position of each head; pass 2: run lengths
+    const int64_t base = seg_begin[blockIdx.x];
+    const int nvalid = (int)seg_n[blockIdx.x];
+    const KeyT* in = sorted + base;
+    KeyT* ko = scratch + base;
+    uint32_t* co = pc + base;      // pass 1: position of each head; pass 2: run lengths
     __shared__ int s_warp[T / 32];
-    __shared__ int s_total;
     int nheads = 0;
     for (int c0 = 0; c0 < nvalid; c0 += T) {
         const int g = c0 + threadIdx.x;
@@ -504,12 +591,10 @@ __global__ void __launch_bounds__(256) long_rle_kernel(const int64_t* __restrict
             total += x;
         }
         const int pos = nheads + before + __popc(bal & ((1u << lane) - 1u));
-        __syncthreads();
+        __syncthreads();   // all reads of `in` for this chunk are done (ko may alias it)
         if (head) { ko[pos] = v; co[pos] = (uint32_t)g; }
         nheads += total;
     }
-    __syncthreads();
-    if (threadIdx.x == 0) s_total = nheads;
     __syncthreads();
     for (int c0 = 0; c0 < nheads; c0 += T) {
         const int j = c0 + threadIdx.x;
@@ -522,7 +607,199 @@ __global__ void __launch_bounds__(256) long_rle_kernel(const int64_t* __restrict
         if (j < nheads) co[j] = nxt - cur;
         __syncthreads();
     }
-    if (threadIdx.x == 0) row_count[r] = s_total;
+    if (threadIdx.x == 0) distinct[fb_list[blockIdx.x]] = (unsigned long long)nheads;
+}
+
+// the pairs of every bucket move behind those of the buckets before it in the same row (dscan =
+// exclusive scan of the distinct counts over the batch's buckets); one warp per bucket
+template <typename KeyT>
+__global__ void __launch_bounds__(256) bucket_copy_kernel(const unsigned long long* __restrict__ bend,
+                                                          const unsigned long long* __restrict__ dscan, int64_t nb,
+                                                          const int64_t* __restrict__ boff, int64_t j0, int64_t j1,
+                                                          const int64_t* __restrict__ long_rows,
+                                                          const int64_t* __restrict__ row_begin,
+                                                          const KeyT* __restrict__ scratch, const uint32_t* __restrict__ pc,
+                                                          KeyT* __restrict__ keys, uint32_t* __restrict__ counts,
+                                                          int32_t* __restrict__ row_count)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t nwarps = (int64_t)gridDim.x * 8, b0 = boff[j0];
+    for (int64_t b = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5); b < nb; b += nwarps) {
+        const int64_t j = locate(boff, j0, j1, b0 + b);
+        const int64_t bfirst = boff[j] - b0;
+        const int64_t r = long_rows[j];
+        if (b == bfirst && lane == 0) row_count[r] = (int32_t)(dscan[boff[j + 1] - b0] - dscan[bfirst]);
+        const int64_t nd = (int64_t)(dscan[b + 1] - dscan[b]);
+        if (nd == 0) continue;
+        const int64_t beg = b ? (int64_t)bend[b - 1] : 0;
+        const int64_t dst = row_begin[r] + (int64_t)(dscan[b] - dscan[bfirst]);
+        for (int64_t i = lane; i < nd; i += 32) {
+            keys[dst + i] = scratch[beg + i];
+            counts[dst + i] = pc[beg + i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// scratch of one call: everything is released (stream-ordered) when the object goes out of scope
+struct PoolScratch {
+    cudaStream_t st;
+    std::vector<void*> ptrs;
+    explicit PoolScratch(cudaStream_t s) : st(s) {}
+    ~PoolScratch() { for (void* p : ptrs) cudaFreeAsync(p, st); }
+    template <typename T> cudaError_t get(T** out, size_t n)
+    {
+        void* p = nullptr;
+        const cudaError_t e = cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), st);
+        if (e == cudaSuccess) ptrs.push_back(p);
+        *out = static_cast<T*>(p);
+        return e;
+    }
+};
+
+template <typename T>
+static cudaError_t scan_in_place(T* data, int64_t n, void* tmp, size_t tmp_bytes, cudaStream_t st)
+{
+    return cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, data, data, n, st);
+}
+
+#define CFRK_TRY(x) do { if ((e = (x)) != cudaSuccess) return e; } while (0)
+
+template <typename KeyT, int FMT>
+static cudaError_t sparse_long_rows(const uint8_t* bases, const int64_t* start, const int32_t* length, int k,
+                                    const int64_t* row_begin, int32_t* row_count, KeyT* keys, uint32_t* counts,
+                                    const int64_t* long_rows, int64_t nl, int num_sms, SparseTrace& tr, cudaStream_t st)
+{
+    cudaError_t e;
+    PoolScratch pool(st);
+    // per-row windows / buckets / partition tiles, scanned
+    int64_t *loff = nullptr, *boff = nullptr, *ptile = nullptr;
+    CFRK_TRY(pool.get(&loff, (size_t)nl + 1));
+    CFRK_TRY(pool.get(&boff, (size_t)nl + 1));
+    CFRK_TRY(pool.get(&ptile, (size_t)nl + 1));
+    long_sizes_kernel<<<(unsigned)((nl + 256) / 256), 256, 0, st>>>(long_rows, nl, length, k, loff, boff, ptile);
+    count_launch();
+    {
+        size_t sb = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, sb, loff, loff, nl + 1, st);
+        void* stmp = nullptr;
+        CFRK_TRY(pool.get(reinterpret_cast<char**>(&stmp), sb));
+        CFRK_TRY(scan_in_place(loff, nl + 1, stmp, sb, st));
+        CFRK_TRY(scan_in_place(boff, nl + 1, stmp, sb, st));
+        CFRK_TRY(scan_in_place(ptile, nl + 1, stmp, sb, st));
+    }
+    std::vector<int64_t> h_loff((size_t)nl + 1), h_boff((size_t)nl + 1);
+    cudaMemcpyAsync(h_loff.data(), loff, ((size_t)nl + 1) * 8, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(h_boff.data(), boff, ((size_t)nl + 1) * 8, cudaMemcpyDeviceToHost, st);
+    CFRK_TRY(cudaStreamSynchronize(st));
+
+    // batches of consecutive long rows, <= kBatchKeys windows each (a larger row is its own batch)
+    std::vector<int64_t> cuts{0};
+    int64_t max_keys = 0, max_nb = 0;
+    for (int64_t j0 = 0; j0 < nl;) {
+        int64_t j1 = j0 + 1;
+        while (j1 < nl && h_loff[(size_t)j1 + 1] - h_loff[(size_t)j0] <= kBatchKeys) j1++;
+        cuts.push_back(j1);
+        max_keys = std::max(max_keys, h_loff[(size_t)j1] - h_loff[(size_t)j0]);
+        max_nb = std::max(max_nb, h_boff[(size_t)j1] - h_boff[(size_t)j0]);
+        j0 = j1;
+    }
+    KeyT* scratch = nullptr;
+    uint32_t* pc = nullptr;
+    unsigned long long *bucket = nullptr, *distinct = nullptr, *n_fb = nullptr;
+    int64_t* fb_list = nullptr;
+    void* btmp = nullptr;
+    size_t bb = 0;
+    CFRK_TRY(pool.get(&scratch, (size_t)max_keys));
+    CFRK_TRY(pool.get(&pc, (size_t)max_keys));
+    CFRK_TRY(pool.get(&bucket, (size_t)max_nb + 1));
+    CFRK_TRY(pool.get(&distinct, (size_t)max_nb + 1));
+    CFRK_TRY(pool.get(&fb_list, (size_t)(max_keys / kBucketCap + 1)));
+    CFRK_TRY(pool.get(&n_fb, 1));
+    cub::DeviceScan::ExclusiveSum(nullptr, bb, bucket, bucket, max_nb + 1, st);
+    CFRK_TRY(pool.get(reinterpret_cast<char**>(&btmp), bb));
+    tr.mark("long rows: collect + scratch");
+
+    for (size_t c = 0; c + 1 < cuts.size(); c++) {
+        const int64_t j0 = cuts[c], j1 = cuts[c + 1];
+        const int64_t nb = h_boff[(size_t)j1] - h_boff[(size_t)j0];
+        const int64_t nkeys = h_loff[(size_t)j1] - h_loff[(size_t)j0];
+        const int64_t ntiles = (nkeys + kPartTile - 1) / kPartTile + (j1 - j0);   // upper bound: sizes the grid only
+        const unsigned pgrid = (unsigned)std::min<int64_t>(ntiles, (int64_t)num_sms * 8);
+        cudaMemsetAsync(bucket, 0, ((size_t)nb + 1) * 8, st);
+        cudaMemsetAsync(distinct, 0, ((size_t)nb + 1) * 8, st);
+        cudaMemsetAsync(n_fb, 0, 8, st);
+        partition_kernel<KeyT, FMT, false><<<pgrid, 256, 0, st>>>(bases, start, length, k, long_rows, boff, ptile, j0, j1, bucket, scratch);
+        count_launch();
+        tr.mark("long rows: bucket histogram");
+        CFRK_TRY(scan_in_place(bucket, nb + 1, btmp, bb, st));
+        partition_kernel<KeyT, FMT, true><<<pgrid, 256, 0, st>>>(bases, start, length, k, long_rows, boff, ptile, j0, j1, bucket, scratch);
+        count_launch();
+        tr.mark("long rows: scatter");
+        {
+            const unsigned g4 = (unsigned)std::min<int64_t>((nb + SparseCta<4>::WARPS - 1) / SparseCta<4>::WARPS, (int64_t)num_sms * 8);
+            const unsigned g16 = (unsigned)std::min<int64_t>((nb + SparseCta<16>::WARPS - 1) / SparseCta<16>::WARPS, (int64_t)num_sms * 8);
+            bucket_sort_kernel<KeyT, 4><<<g4, SparseCta<4>::WARPS * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb);
+            bucket_sort_kernel<KeyT, 8><<<g4, SparseCta<8>::WARPS * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb);
+            bucket_sort_kernel<KeyT, 16><<<g16, SparseCta<16>::WARPS * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb);
+            count_launch(); count_launch(); count_launch();
+        }
+        unsigned long long nfb = 0;
+        cudaMemcpyAsync(&nfb, n_fb, 8, cudaMemcpyDeviceToHost, st);
+        CFRK_TRY(cudaStreamSynchronize(st));
+        tr.mark("long rows: bucket sort");
+        if (nfb > 0) {
+            // buckets above 512 keys: segmented LSD radix sort over all 2k key bits
+            PoolScratch fpool(st);
+            const int64_t ns = (int64_t)nfb;
+            int64_t *seg_begin = nullptr, *seg_n = nullptr, *stile = nullptr;
+            KeyT* other = nullptr;
+            CFRK_TRY(fpool.get(&seg_begin, (size_t)ns));
+            CFRK_TRY(fpool.get(&seg_n, (size_t)ns));
+            CFRK_TRY(fpool.get(&stile, (size_t)ns + 1));
+            CFRK_TRY(fpool.get(&other, (size_t)nkeys));
+            fallback_segments_kernel<<<(unsigned)((ns + 256) / 256), 256, 0, st>>>(fb_list, ns, bucket, seg_begin, seg_n, stile);
+            count_launch();
+            size_t sb = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, sb, stile, stile, ns + 1, st);
+            void* stmp = nullptr;
+            CFRK_TRY(fpool.get(reinterpret_cast<char**>(&stmp), sb));
+            CFRK_TRY(scan_in_place(stile, ns + 1, stmp, sb, st));
+            int64_t stiles = 0;
+            cudaMemcpyAsync(&stiles, stile + ns, 8, cudaMemcpyDeviceToHost, st);
+            CFRK_TRY(cudaStreamSynchronize(st));
+            uint32_t* counters = nullptr;
+            const size_t ncount = (size_t)stiles * 256;
+            CFRK_TRY(fpool.get(&counters, ncount));
+            size_t cb = 0;
+            cub::DeviceScan::ExclusiveSum(nullptr, cb, counters, counters, (int64_t)ncount, st);
+            void* ctmp = nullptr;
+            CFRK_TRY(fpool.get(reinterpret_cast<char**>(&ctmp), cb));
+            const unsigned sgrid = (unsigned)std::min<int64_t>((stiles + kSortWarps - 1) / kSortWarps, (int64_t)num_sms * 8);
+            const int passes = (2 * k + 7) / 8;
+            KeyT *src = scratch, *dst = other;
+            for (int p = 0; p < passes; p++) {
+                sort_hist_kernel<KeyT><<<sgrid, kSortWarps * 32, 0, st>>>(src, 8 * p, stile, seg_begin, seg_n, ns, stiles, counters);
+                CFRK_TRY(scan_in_place(counters, (int64_t)ncount, ctmp, cb, st));
+                sort_scatter_kernel<KeyT><<<sgrid, kSortWarps * 32, 0, st>>>(src, dst, 8 * p, stile, seg_begin, seg_n, ns, stiles, counters);
+                count_launch(); count_launch();
+                std::swap(src, dst);
+            }
+            segment_rle_kernel<KeyT><<<(unsigned)ns, 256, 0, st>>>(fb_list, seg_begin, seg_n, src, scratch, pc, distinct);
+            count_launch();
+            tr.mark("long rows: oversized buckets (radix sort)");
+        }
+        CFRK_TRY(scan_in_place(distinct, nb + 1, btmp, bb, st));
+        {
+            const unsigned cgrid = (unsigned)std::min<int64_t>((nb + 7) / 8, (int64_t)num_sms * 8);
+            bucket_copy_kernel<KeyT><<<cgrid, 256, 0, st>>>(bucket, distinct, nb, boff, j0, j1, long_rows, row_begin, scratch, pc,
+                                                           keys, counts, row_count);
+            count_launch();
+        }
+        tr.mark("long rows: compaction");
+        CFRK_TRY(cudaGetLastError());
+    }
+    return cudaSuccess;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -582,70 +859,11 @@ static cudaError_t sparse_impl(const void* bases, const int64_t* start, const in
     unsigned long long n_long = 0;
     cudaMemcpyAsync(&n_long, d_nlong, 8, cudaMemcpyDeviceToHost, st);
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-    if (n_long > 0) {
-        const int64_t nl = (int64_t)n_long;
-        int64_t *loff = nullptr, *ltile = nullptr;
-        if ((e = cudaMallocAsync(reinterpret_cast<void**>(&loff), (size_t)(nl + 1) * 8, st)) != cudaSuccess) return e;
-        if ((e = cudaMallocAsync(reinterpret_cast<void**>(&ltile), (size_t)(nl + 1) * 8, st)) != cudaSuccess) return e;
-        long_sizes_kernel<<<(unsigned)((nl + 256) / 256), 256, 0, st>>>(long_rows, nl, length, k, loff, ltile);
-        count_launch();
-        size_t sb = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, sb, loff, loff, nl + 1, st);
-        void* stmp = nullptr;
-        if ((e = cudaMallocAsync(&stmp, sb ? sb : 16, st)) != cudaSuccess) return e;
-        if ((e = cub::DeviceScan::ExclusiveSum(stmp, sb, loff, loff, nl + 1, st)) != cudaSuccess) return e;
-        if ((e = cub::DeviceScan::ExclusiveSum(stmp, sb, ltile, ltile, nl + 1, st)) != cudaSuccess) return e;
-        cudaFreeAsync(stmp, st);
-        int64_t total_long = 0, ntiles = 0;
-        cudaMemcpyAsync(&total_long, loff + nl, 8, cudaMemcpyDeviceToHost, st);
-        cudaMemcpyAsync(&ntiles, ltile + nl, 8, cudaMemcpyDeviceToHost, st);
-        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-
-        KeyT *bufA = nullptr, *bufB = nullptr;
-        uint32_t* counters = nullptr;
-        const size_t ncount = (size_t)ntiles * 256;
-        if ((e = cudaMallocAsync(reinterpret_cast<void**>(&bufA), (size_t)total_long * sizeof(KeyT), st)) != cudaSuccess) return e;
-        if ((e = cudaMallocAsync(reinterpret_cast<void**>(&bufB), (size_t)total_long * sizeof(KeyT), st)) != cudaSuccess) return e;
-        if ((e = cudaMallocAsync(reinterpret_cast<void**>(&counters), ncount * 4, st)) != cudaSuccess) return e;
-        tr.mark("long rows: collect + scratch");
-        long_keygen_kernel<KeyT, FMT><<<(unsigned)nl, 256, 0, st>>>(static_cast<const uint8_t*>(bases), start, length, k,
-                                                                   long_rows, loff, bufA, row_count);
-        count_launch();
-        tr.mark("long rows: key generation");
-        // segmented LSD radix sort, 8 bits per pass, over the bits that can differ
-        const int key_bits = (int)sizeof(KeyT) * 8;
-        const int nbits = 2 * k + 1 < key_bits ? 2 * k + 1 : key_bits;
-        const int passes = (nbits + 7) / 8;
-        size_t cb = 0;
-        cub::DeviceScan::ExclusiveSum(nullptr, cb, counters, counters, (int64_t)ncount, st);
-        void* ctmp = nullptr;
-        if ((e = cudaMallocAsync(&ctmp, cb ? cb : 16, st)) != cudaSuccess) return e;
-        const int64_t ctas = (ntiles + kSortWarps - 1) / kSortWarps;
-        const unsigned sgrid = (unsigned)(ctas < (int64_t)num_sms * 8 ? ctas : (int64_t)num_sms * 8);
-        KeyT *src = bufA, *dst = bufB;
-        for (int p = 0; p < passes; p++) {
-            sort_hist_kernel<KeyT><<<sgrid, kSortWarps * 32, 0, st>>>(src, 8 * p, ltile, loff, nl, ntiles, counters);
-            tr.mark("  sort pass: histogram");
-            if ((e = cub::DeviceScan::ExclusiveSum(ctmp, cb, counters, counters, (int64_t)ncount, st)) != cudaSuccess) return e;
-            tr.mark("  sort pass: scan");
-            sort_scatter_kernel<KeyT><<<sgrid, kSortWarps * 32, 0, st>>>(src, dst, 8 * p, ltile, loff, nl, ntiles, counters);
-            tr.mark("  sort pass: scatter");
-            count_launch(); count_launch();
-            KeyT* tmpp = src; src = dst; dst = tmpp;
-        }
-        long_rle_kernel<KeyT><<<(unsigned)nl, 256, 0, st>>>(long_rows, loff, row_begin, src, keys, counts, row_count);
-        count_launch();
-        tr.mark("long rows: run-length encode");
-        cudaFreeAsync(ctmp, st);
-        cudaFreeAsync(counters, st);
-        cudaFreeAsync(bufA, st);
-        cudaFreeAsync(bufB, st);
-        cudaFreeAsync(loff, st);
-        cudaFreeAsync(ltile, st);
-    }
+    if (n_long > 0) e = sparse_long_rows<KeyT, FMT>(static_cast<const uint8_t*>(bases), start, length, k, row_begin, row_count,
+                                                    keys, counts, long_rows, (int64_t)n_long, num_sms, tr, st);
     cudaFreeAsync(long_rows, st);
     cudaFreeAsync(d_nlong, st);
-    return cudaGetLastError();
+    return e != cudaSuccess ? e : cudaGetLastError();
 }
 
 cudaError_t launch_sparse(const void* bases, int fmt, const int64_t* start, const int32_t* length, int64_t nS, int k,
