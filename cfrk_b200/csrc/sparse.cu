@@ -80,19 +80,19 @@ __global__ void nwin_kernel(const int32_t* __restrict__ length, int64_t nS, int 
 }
 
 // ------------------------------------------------------------------------------------------
-// keep min(mine, other) if take_min else max: min ^ ((mine ^ other) & mask), mask = take_min ? 0 : ~0
+// the lower lane of a pair keeps the minimum, the upper one the maximum: one compare whose result
+// is XOR-ed with the lane's side (ISETP.LT.XOR) and one select per 32-bit word
 template <typename KeyT>
-__device__ __forceinline__ KeyT keep_minmax(KeyT mine, KeyT other, KeyT mask)
+__device__ __forceinline__ KeyT keep_minmax(KeyT mine, KeyT other, bool upper)
 {
-    const KeyT mn = mine < other ? mine : other;
-    return mn ^ ((mine ^ other) & mask);
+    return ((mine < other) != upper) ? mine : other;
 }
 
 // Bitonic network over 32*E keys in blocked layout (lane L holds elements L*E .. L*E+E-1), in the
 // direction-free form: every merge starts with a MIRRORED compare (i with i ^ (size-1)) and goes on
 // with the usual strides, and every comparator leaves the minimum at the lower index.  In-lane
 // comparators are then pure min/max on compile-time registers; cross-lane ones need one per-lane
-// mask per stage.
+// predicate per stage.
 template <typename KeyT, int E>
 __device__ __forceinline__ void bitonic_sort_blocked(KeyT (&key)[E])
 {
@@ -112,23 +112,23 @@ __device__ __forceinline__ void bitonic_sort_blocked(KeyT (&key)[E])
             }
         } else {
             const int lm = size / E - 1;
-            const KeyT mask = (lane & (size / (2 * E))) == 0 ? (KeyT)0 : ~(KeyT)0;
+            const bool upper = (lane & (size / (2 * E))) != 0;
             KeyT other[E];
 #pragma unroll
             for (int e = 0; e < E; e++) other[e] = __shfl_xor_sync(0xffffffffu, key[E - 1 - e], lm);
 #pragma unroll
-            for (int e = 0; e < E; e++) key[e] = keep_minmax<KeyT>(key[e], other[e], mask);
+            for (int e = 0; e < E; e++) key[e] = keep_minmax<KeyT>(key[e], other[e], upper);
         }
         // remaining strides
 #pragma unroll
         for (int stride = size >> 2; stride >= 1; stride >>= 1) {
             if (stride >= E) {
                 const int ls = stride / E;
-                const KeyT mask = (lane & ls) == 0 ? (KeyT)0 : ~(KeyT)0;
+                const bool upper = (lane & ls) != 0;
 #pragma unroll
                 for (int e = 0; e < E; e++) {
                     const KeyT other = __shfl_xor_sync(0xffffffffu, key[e], ls);
-                    key[e] = keep_minmax<KeyT>(key[e], other, mask);
+                    key[e] = keep_minmax<KeyT>(key[e], other, upper);
                 }
             } else {
 #pragma unroll
@@ -319,7 +319,7 @@ constexpr int kBucketCap = 512;          // what one warp sorts in registers (E 
 constexpr int kMaxBucketBits = 22;
 constexpr int kPartTile = 4096;          // windows per CTA tile of the two partition passes
 constexpr int kPartBlocks = (15 + kPartTile + 30 + 15) / 16 + 3;
-constexpr int64_t kBatchKeys = (int64_t)128 << 20;
+constexpr int64_t kDefaultBatchKeys = (int64_t)128 << 20;
 constexpr int kSortTile = 2048;          // keys per warp tile of the fallback radix sort
 constexpr int kSortWarps = 8;
 
@@ -330,13 +330,22 @@ __host__ __device__ __forceinline__ int bucket_bits(int64_t nwin, int k)
     return b < 2 * k ? b : 2 * k;
 }
 
-__global__ void collect_long_kernel(const int32_t* __restrict__ length, int64_t nS, int k, int64_t* __restrict__ long_rows,
-                                    unsigned long long* __restrict__ n_long, int64_t cap)
+// A row is NARROW when the key bits below its bucket digit fit 32 bits: all keys of a bucket share
+// the digit, so only these 32-bit suffixes are stored, sorted and run-length encoded, and the digit
+// is put back when the pairs move to the output (uint64 keys with k <= ~23 on Mbp rows: half the
+// scratch traffic and a 32-bit sorting network).
+__host__ __device__ __forceinline__ bool narrow_row(int64_t nwin, int k) { return 2 * k - bucket_bits(nwin, k) <= 32; }
+
+// long rows, listed from both ends of long_rows[cap]: narrow rows from the front, wide ones from the back
+__global__ void collect_long_kernel(const int32_t* __restrict__ length, int64_t nS, int k, bool split,
+                                    int64_t* __restrict__ long_rows, unsigned long long* __restrict__ n_long, int64_t cap)
 {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nS; r += (int64_t)gridDim.x * blockDim.x) {
-        if (length[r] - k + 1 > kShortMaxWindows) {
-            const unsigned long long slot = atomicAdd(n_long, 1ull);
-            if ((int64_t)slot < cap) long_rows[slot] = r;
+        const int64_t nwin = (int64_t)length[r] - k + 1;
+        if (nwin > kShortMaxWindows) {
+            const bool wide = split && !narrow_row(nwin, k);
+            const unsigned long long slot = atomicAdd(n_long + (wide ? 1 : 0), 1ull);
+            if ((int64_t)slot < cap) long_rows[wide ? cap - 1 - (int64_t)slot : (int64_t)slot] = r;
         }
     }
 }
@@ -368,13 +377,13 @@ __device__ __forceinline__ int64_t locate(const int64_t* __restrict__ scan, int6
 // bases encoded once into a shared-memory bit stream (as for the short reads), every thread
 // extracts windows by funnel shift.  SCATTER = false: count the buckets.  SCATTER = true: bucket[]
 // holds the scanned counts; a key takes the next slot of its bucket (afterwards bucket[b] = end of b).
-template <typename KeyT, int FMT, bool SCATTER>
+template <typename KeyT, typename SortT, int FMT, bool SCATTER>
 __global__ void __launch_bounds__(256) partition_kernel(const uint8_t* __restrict__ bases, const int64_t* __restrict__ start,
                                                         const int32_t* __restrict__ length, int k,
                                                         const int64_t* __restrict__ long_rows,
                                                         const int64_t* __restrict__ boff, const int64_t* __restrict__ ptile,
                                                         int64_t j0, int64_t j1, unsigned long long* __restrict__ bucket,
-                                                        KeyT* __restrict__ scratch)
+                                                        SortT* __restrict__ scratch)
 {
     __shared__ uint32_t s_cw[kPartBlocks];
     __shared__ __align__(4) uint16_t s_vh[2 * ((kPartBlocks + 1) / 2) + 2];
@@ -414,7 +423,7 @@ __global__ void __launch_bounds__(256) partition_kernel(const uint8_t* __restric
                 const uint64_t d = (uint64_t)key >> shift;
                 if (SCATTER) {
                     const unsigned long long pos = atomicAdd(&bk[d], 1ull);
-                    scratch[pos] = key;
+                    scratch[pos] = (SortT)key;   // narrow rows: the suffix (shift <= 32, the digit is cut off)
                 } else {
                     atomicAdd(&bk[d], 1ull);
                 }
@@ -611,14 +620,16 @@ __global__ void __launch_bounds__(256) segment_rle_kernel(const int64_t* __restr
 }
 
 // the pairs of every bucket move behind those of the buckets before it in the same row (dscan =
-// exclusive scan of the distinct counts over the batch's buckets); one warp per bucket
-template <typename KeyT>
+// exclusive scan of the distinct counts over the batch's buckets); one warp per bucket.  Narrow rows
+// get the bucket digit back here.
+template <typename KeyT, typename SortT>
 __global__ void __launch_bounds__(256) bucket_copy_kernel(const unsigned long long* __restrict__ bend,
                                                           const unsigned long long* __restrict__ dscan, int64_t nb,
                                                           const int64_t* __restrict__ boff, int64_t j0, int64_t j1,
                                                           const int64_t* __restrict__ long_rows,
+                                                          const int32_t* __restrict__ length, int k,
                                                           const int64_t* __restrict__ row_begin,
-                                                          const KeyT* __restrict__ scratch, const uint32_t* __restrict__ pc,
+                                                          const SortT* __restrict__ scratch, const uint32_t* __restrict__ pc,
                                                           KeyT* __restrict__ keys, uint32_t* __restrict__ counts,
                                                           int32_t* __restrict__ row_count)
 {
@@ -631,10 +642,15 @@ __global__ void __launch_bounds__(256) bucket_copy_kernel(const unsigned long lo
         if (b == bfirst && lane == 0) row_count[r] = (int32_t)(dscan[boff[j + 1] - b0] - dscan[bfirst]);
         const int64_t nd = (int64_t)(dscan[b + 1] - dscan[b]);
         if (nd == 0) continue;
+        KeyT digit = 0;
+        if (sizeof(SortT) < sizeof(KeyT)) {
+            const int shift = 2 * k - bucket_bits((int64_t)length[r] - k + 1, k);
+            digit = (KeyT)(b - bfirst) << shift;
+        }
         const int64_t beg = b ? (int64_t)bend[b - 1] : 0;
         const int64_t dst = row_begin[r] + (int64_t)(dscan[b] - dscan[bfirst]);
         for (int64_t i = lane; i < nd; i += 32) {
-            keys[dst + i] = scratch[beg + i];
+            keys[dst + i] = (KeyT)scratch[beg + i] | digit;
             counts[dst + i] = pc[beg + i];
         }
     }
@@ -665,7 +681,7 @@ static cudaError_t scan_in_place(T* data, int64_t n, void* tmp, size_t tmp_bytes
 
 #define CFRK_TRY(x) do { if ((e = (x)) != cudaSuccess) return e; } while (0)
 
-template <typename KeyT, int FMT>
+template <typename KeyT, typename SortT, int FMT>
 static cudaError_t sparse_long_rows(const uint8_t* bases, const int64_t* start, const int32_t* length, int k,
                                     const int64_t* row_begin, int32_t* row_count, KeyT* keys, uint32_t* counts,
                                     const int64_t* long_rows, int64_t nl, int num_sms, SparseTrace& tr, cudaStream_t st)
@@ -693,18 +709,20 @@ static cudaError_t sparse_long_rows(const uint8_t* bases, const int64_t* start, 
     cudaMemcpyAsync(h_boff.data(), boff, ((size_t)nl + 1) * 8, cudaMemcpyDeviceToHost, st);
     CFRK_TRY(cudaStreamSynchronize(st));
 
-    // batches of consecutive long rows, <= kBatchKeys windows each (a larger row is its own batch)
+    // batches of consecutive long rows, <= batch_keys windows each (a larger row is its own batch)
     std::vector<int64_t> cuts{0};
     int64_t max_keys = 0, max_nb = 0;
+    int64_t batch_keys = kDefaultBatchKeys;
+    if (const char* ev = getenv("CFRK_SPARSE_BATCH_KEYS")) batch_keys = std::max<int64_t>(1, atoll(ev));   // tests: force many batches
     for (int64_t j0 = 0; j0 < nl;) {
         int64_t j1 = j0 + 1;
-        while (j1 < nl && h_loff[(size_t)j1 + 1] - h_loff[(size_t)j0] <= kBatchKeys) j1++;
+        while (j1 < nl && h_loff[(size_t)j1 + 1] - h_loff[(size_t)j0] <= batch_keys) j1++;
         cuts.push_back(j1);
         max_keys = std::max(max_keys, h_loff[(size_t)j1] - h_loff[(size_t)j0]);
         max_nb = std::max(max_nb, h_boff[(size_t)j1] - h_boff[(size_t)j0]);
         j0 = j1;
     }
-    KeyT* scratch = nullptr;
+    SortT* scratch = nullptr;
     uint32_t* pc = nullptr;
     unsigned long long *bucket = nullptr, *distinct = nullptr, *n_fb = nullptr;
     int64_t* fb_list = nullptr;
@@ -729,19 +747,19 @@ static cudaError_t sparse_long_rows(const uint8_t* bases, const int64_t* start, 
         cudaMemsetAsync(bucket, 0, ((size_t)nb + 1) * 8, st);
         cudaMemsetAsync(distinct, 0, ((size_t)nb + 1) * 8, st);
         cudaMemsetAsync(n_fb, 0, 8, st);
-        partition_kernel<KeyT, FMT, false><<<pgrid, 256, 0, st>>>(bases, start, length, k, long_rows, boff, ptile, j0, j1, bucket, scratch);
+        partition_kernel<KeyT, SortT, FMT, false><<<pgrid, 256, 0, st>>>(bases, start, length, k, long_rows, boff, ptile, j0, j1, bucket, scratch);
         count_launch();
         tr.mark("long rows: bucket histogram");
         CFRK_TRY(scan_in_place(bucket, nb + 1, btmp, bb, st));
-        partition_kernel<KeyT, FMT, true><<<pgrid, 256, 0, st>>>(bases, start, length, k, long_rows, boff, ptile, j0, j1, bucket, scratch);
+        partition_kernel<KeyT, SortT, FMT, true><<<pgrid, 256, 0, st>>>(bases, start, length, k, long_rows, boff, ptile, j0, j1, bucket, scratch);
         count_launch();
         tr.mark("long rows: scatter");
         {
             const unsigned g4 = (unsigned)std::min<int64_t>((nb + SparseCta<4>::WARPS - 1) / SparseCta<4>::WARPS, (int64_t)num_sms * 8);
             const unsigned g16 = (unsigned)std::min<int64_t>((nb + SparseCta<16>::WARPS - 1) / SparseCta<16>::WARPS, (int64_t)num_sms * 8);
-            bucket_sort_kernel<KeyT, 4><<<g4, SparseCta<4>::WARPS * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb);
-            bucket_sort_kernel<KeyT, 8><<<g4, SparseCta<8>::WARPS * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb);
-            bucket_sort_kernel<KeyT, 16><<<g16, SparseCta<16>::WARPS * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb);
+            bucket_sort_kernel<SortT, 4><<<g4, SparseCta<4>::WARPS * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb);
+            bucket_sort_kernel<SortT, 8><<<g4, SparseCta<8>::WARPS * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb);
+            bucket_sort_kernel<SortT, 16><<<g16, SparseCta<16>::WARPS * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb);
             count_launch(); count_launch(); count_launch();
         }
         unsigned long long nfb = 0;
@@ -753,7 +771,7 @@ static cudaError_t sparse_long_rows(const uint8_t* bases, const int64_t* start, 
             PoolScratch fpool(st);
             const int64_t ns = (int64_t)nfb;
             int64_t *seg_begin = nullptr, *seg_n = nullptr, *stile = nullptr;
-            KeyT* other = nullptr;
+            SortT* other = nullptr;
             CFRK_TRY(fpool.get(&seg_begin, (size_t)ns));
             CFRK_TRY(fpool.get(&seg_n, (size_t)ns));
             CFRK_TRY(fpool.get(&stile, (size_t)ns + 1));
@@ -776,24 +794,25 @@ static cudaError_t sparse_long_rows(const uint8_t* bases, const int64_t* start, 
             void* ctmp = nullptr;
             CFRK_TRY(fpool.get(reinterpret_cast<char**>(&ctmp), cb));
             const unsigned sgrid = (unsigned)std::min<int64_t>((stiles + kSortWarps - 1) / kSortWarps, (int64_t)num_sms * 8);
-            const int passes = (2 * k + 7) / 8;
-            KeyT *src = scratch, *dst = other;
+            const int bits = std::min(2 * k, (int)sizeof(SortT) * 8);
+            const int passes = (bits + 7) / 8;
+            SortT *src = scratch, *dst = other;
             for (int p = 0; p < passes; p++) {
-                sort_hist_kernel<KeyT><<<sgrid, kSortWarps * 32, 0, st>>>(src, 8 * p, stile, seg_begin, seg_n, ns, stiles, counters);
+                sort_hist_kernel<SortT><<<sgrid, kSortWarps * 32, 0, st>>>(src, 8 * p, stile, seg_begin, seg_n, ns, stiles, counters);
                 CFRK_TRY(scan_in_place(counters, (int64_t)ncount, ctmp, cb, st));
-                sort_scatter_kernel<KeyT><<<sgrid, kSortWarps * 32, 0, st>>>(src, dst, 8 * p, stile, seg_begin, seg_n, ns, stiles, counters);
+                sort_scatter_kernel<SortT><<<sgrid, kSortWarps * 32, 0, st>>>(src, dst, 8 * p, stile, seg_begin, seg_n, ns, stiles, counters);
                 count_launch(); count_launch();
                 std::swap(src, dst);
             }
-            segment_rle_kernel<KeyT><<<(unsigned)ns, 256, 0, st>>>(fb_list, seg_begin, seg_n, src, scratch, pc, distinct);
+            segment_rle_kernel<SortT><<<(unsigned)ns, 256, 0, st>>>(fb_list, seg_begin, seg_n, src, scratch, pc, distinct);
             count_launch();
             tr.mark("long rows: oversized buckets (radix sort)");
         }
         CFRK_TRY(scan_in_place(distinct, nb + 1, btmp, bb, st));
         {
             const unsigned cgrid = (unsigned)std::min<int64_t>((nb + 7) / 8, (int64_t)num_sms * 8);
-            bucket_copy_kernel<KeyT><<<cgrid, 256, 0, st>>>(bucket, distinct, nb, boff, j0, j1, long_rows, row_begin, scratch, pc,
-                                                           keys, counts, row_count);
+            bucket_copy_kernel<KeyT, SortT><<<cgrid, 256, 0, st>>>(bucket, distinct, nb, boff, j0, j1, long_rows, length, k, row_begin,
+                                                                  scratch, pc, keys, counts, row_count);
             count_launch();
         }
         tr.mark("long rows: compaction");
@@ -847,20 +866,25 @@ static cudaError_t sparse_impl(const void* bases, const int64_t* start, const in
     }
 
     tr.mark("short reads");
-    // 3. long reads
+    // 3. long reads: narrow rows (32-bit suffixes) listed from the front, wide ones from the back
     int64_t* long_rows = nullptr;
     unsigned long long* d_nlong = nullptr;
     const int64_t cap_long = total / kShortMaxWindows + 1;   // a long row has > 512 windows
     if ((e = cudaMallocAsync(reinterpret_cast<void**>(&long_rows), (size_t)cap_long * 8, st)) != cudaSuccess) return e;
-    if ((e = cudaMallocAsync(reinterpret_cast<void**>(&d_nlong), 8, st)) != cudaSuccess) return e;
-    cudaMemsetAsync(d_nlong, 0, 8, st);
-    collect_long_kernel<<<num_sms * 4, 256, 0, st>>>(length, nS, k, long_rows, d_nlong, cap_long);
+    if ((e = cudaMallocAsync(reinterpret_cast<void**>(&d_nlong), 16, st)) != cudaSuccess) return e;
+    cudaMemsetAsync(d_nlong, 0, 16, st);
+    collect_long_kernel<<<num_sms * 4, 256, 0, st>>>(length, nS, k, sizeof(KeyT) == 8, long_rows, d_nlong, cap_long);
     count_launch();
-    unsigned long long n_long = 0;
-    cudaMemcpyAsync(&n_long, d_nlong, 8, cudaMemcpyDeviceToHost, st);
+    unsigned long long n_long[2] = {0, 0};
+    cudaMemcpyAsync(n_long, d_nlong, 16, cudaMemcpyDeviceToHost, st);
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-    if (n_long > 0) e = sparse_long_rows<KeyT, FMT>(static_cast<const uint8_t*>(bases), start, length, k, row_begin, row_count,
-                                                    keys, counts, long_rows, (int64_t)n_long, num_sms, tr, st);
+    const uint8_t* b8 = static_cast<const uint8_t*>(bases);
+    if (n_long[0] > 0)
+        e = sparse_long_rows<KeyT, uint32_t, FMT>(b8, start, length, k, row_begin, row_count, keys, counts, long_rows,
+                                                  (int64_t)n_long[0], num_sms, tr, st);
+    if (e == cudaSuccess && n_long[1] > 0)
+        e = sparse_long_rows<KeyT, KeyT, FMT>(b8, start, length, k, row_begin, row_count, keys, counts,
+                                              long_rows + (cap_long - (int64_t)n_long[1]), (int64_t)n_long[1], num_sms, tr, st);
     cudaFreeAsync(long_rows, st);
     cudaFreeAsync(d_nlong, st);
     return e != cudaSuccess ? e : cudaGetLastError();

@@ -57,9 +57,10 @@ def test_repeats_and_all_same(k, key_bytes):
     check(data, start, length, k, key_bytes)
 
 
-@pytest.mark.parametrize("k,key_bytes", [(12, 4), (16, 4), (21, 8), (31, 8)])
+@pytest.mark.parametrize("k,key_bytes", [(12, 4), (16, 4), (12, 8), (17, 8), (18, 8), (21, 8), (31, 8)])
 def test_window_count_boundaries_and_long_reads(k, key_bytes):
-    """reads around the 128/256/512-window network sizes and long reads (radix-sort path)"""
+    """reads around the 128/256/512-window network sizes and long reads (bucket path; uint64 keys:
+    k=12,17 rows are all narrow (32-bit suffixes), k=18 mixes narrow and wide rows, k>=21 wide)"""
     import random
     rng = random.Random(k)
     lens = [k - 1, k, k + 1, 127 + k, 128 + k, 255 + k, 256 + k, 257 + k, 511 + k, 512 + k - 1, 512 + k, 513 + k,
@@ -71,6 +72,26 @@ def test_window_count_boundaries_and_long_reads(k, key_bytes):
             s[L // 3] = "N"
         reads.append("".join(s))
     reads.append(("ACGTTGCA" * 4000)[:30000])      # long AND repetitive
+    text = "".join(f">r{i}\n{r}\n" for i, r in enumerate(reads))
+    data, start, length = ob.parse_fasta(text=text)
+    check(data, start, length, k, key_bytes)
+
+
+@pytest.mark.parametrize("k,key_bytes,batch", [(16, 4, 4000), (18, 8, 25000), (31, 8, 1)])
+def test_long_rows_in_many_batches(k, key_bytes, batch, monkeypatch):
+    """the long-row scratch is bounded by batches of rows: force tiny batches (several rows per batch,
+    one row per batch, a row larger than the batch) and skewed rows (oversized buckets -> radix sort)"""
+    import random
+    rng = random.Random(100 + k)
+    monkeypatch.setenv("CFRK_SPARSE_BATCH_KEYS", str(batch))
+    reads = []
+    for L in [700, 900, 5000, 150, 2500, 40000, 800, 12000, 600 + k]:
+        reads.append("".join(rng.choice("ACGT") for _ in range(L)))
+    reads.append("A" * 9000)                                   # one bucket holds everything
+    reads.append(("ACGT" * 10 + "N") * 300)                    # few distinct k-mers, many invalid windows
+    reads.append("N" * 2000)                                   # long row without a single valid window
+    unit = "".join(rng.choice("ACGT") for _ in range(700))
+    reads.append(unit * 12)                                    # every k-mer 11-12 times
     text = "".join(f">r{i}\n{r}\n" for i, r in enumerate(reads))
     data, start, length = ob.parse_fasta(text=text)
     check(data, start, length, k, key_bytes)
