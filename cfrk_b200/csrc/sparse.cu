@@ -161,6 +161,26 @@ __device__ __forceinline__ int warp_rle_store(const KeyT (&key)[E], int nvalid, 
         heads |= head ? (1u << e) : 0u;
         prev = key[e];
     }
+    // common case: every key is distinct -> element g goes to slot g with count 1
+    const int nlive = min(E, max(0, nvalid - lane * E));
+    if (__all_sync(0xffffffffu, heads == (1u << nlive) - 1u)) {
+        constexpr int V = 16 / (int)sizeof(KeyT);   // keys per 16-byte shared-memory store
+        static_assert(E % V == 0, "blocked keys are staged with 16-byte stores");
+#pragma unroll
+        for (int q = 0; q < E / V; q++) {
+            if (sizeof(KeyT) == 4)
+                reinterpret_cast<uint4*>(stage_k + lane * E)[q] = make_uint4((uint32_t)key[4 * q], (uint32_t)key[4 * q + 1], (uint32_t)key[4 * q + 2], (uint32_t)key[4 * q + 3]);
+            else
+                reinterpret_cast<ulonglong2*>(stage_k + lane * E)[q] = make_ulonglong2((unsigned long long)key[2 * q], (unsigned long long)key[2 * q + 1]);
+        }
+        __syncwarp();
+        for (int i = lane; i < nvalid; i += 32) {
+            keys_out[i] = stage_k[i];
+            counts_out[i] = 1u;
+        }
+        __syncwarp();
+        return nvalid;
+    }
     // exclusive scan of head counts -> first output slot of this lane
     const int hc = __popc(heads);
     int inc = hc;
@@ -212,45 +232,49 @@ struct WarpStream {
     uint16_t* vh;   // validity, 16 bases per half-word; stored so that 32-bit loads see 32 positions MSB-first
 };
 
-// window of k bases starting at stream position P
-template <typename KeyT>
-__device__ __forceinline__ bool stream_window(const WarpStream& st, int P, int k, KeyT& key)
+// E consecutive windows starting at stream position P0: the 48 bases and 64 validity bits behind P0
+// are pulled into registers once (4 + 3 shared-memory words), every window is then two funnel
+// shifts.  A window that is not entirely inside the read is invalid by the validity masks alone
+// (positions outside the read are masked when the stream is built), so no window count is needed.
+// Invalid windows get the maximum key.  Returns the valid windows of this lane as a bit mask.
+template <typename KeyT, int E>
+__device__ __forceinline__ uint32_t extract_windows(const WarpStream& st, int P0, int k, KeyT (&key)[E])
 {
-    const int b = P >> 4, o = (P & 15) * 2;
-    const uint32_t w0 = st.cw[b], w1 = st.cw[b + 1];
-    const uint32_t hi = __funnelshift_l(w1, w0, o);
-    if (sizeof(KeyT) == 4) {
-        key = (KeyT)(hi >> (32 - 2 * k));
-    } else {
-        const uint32_t lo = __funnelshift_l(st.cw[b + 2], w1, o);
-        key = (KeyT)((((uint64_t)hi << 32) | lo) >> (64 - 2 * k));
-    }
+    static_assert(E <= 16, "2*e must stay below 32");
+    const int b = P0 >> 4, o = (P0 & 15) * 2;
+    const uint32_t w0 = st.cw[b], w1 = st.cw[b + 1], w2 = st.cw[b + 2], w3 = st.cw[b + 3];
+    const uint32_t x0 = __funnelshift_l(w1, w0, o), x1 = __funnelshift_l(w2, w1, o), x2 = __funnelshift_l(w3, w2, o);
     const uint32_t* vw = reinterpret_cast<const uint32_t*>(st.vh);
-    const int c = P >> 5, vo = P & 31;
-    const uint32_t v = __funnelshift_l(vw[c + 1], vw[c], vo);
+    const int c = P0 >> 5, vo = P0 & 31;
+    const uint32_t u0 = vw[c], u1 = vw[c + 1], u2 = vw[c + 2];
+    const uint32_t v0 = __funnelshift_l(u1, u0, vo), v1 = __funnelshift_l(u2, u1, vo);
     const uint32_t need = 0xFFFFFFFFu << (32 - k);
-    return (v & need) == need;
+    uint32_t valid = 0;
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const uint32_t hi = __funnelshift_l(x1, x0, 2 * e);
+        KeyT kk;
+        if (sizeof(KeyT) == 4) {
+            kk = (KeyT)(hi >> (32 - 2 * k));
+        } else {
+            const uint32_t lo = __funnelshift_l(x2, x1, 2 * e);
+            kk = (KeyT)((((uint64_t)hi << 32) | lo) >> (64 - 2 * k));
+        }
+        const bool ok = (__funnelshift_l(v1, v0, e) & need) == need;
+        key[e] = ok ? kk : KeyMax<KeyT>::value;
+        valid |= ok ? 1u << e : 0u;
+    }
+    return valid;
 }
 
 template <typename KeyT, int E>
-__device__ __forceinline__ int warp_count_read(const WarpStream& st, int a, int nwin, int k,
+__device__ __forceinline__ int warp_count_read(const WarpStream& st, int a, int k,
                                                KeyT* __restrict__ keys_out, uint32_t* __restrict__ counts_out,
                                                KeyT* __restrict__ stage_k, uint32_t* __restrict__ stage_c)
 {
     const int lane = threadIdx.x & 31;
     KeyT key[E];
-    int myvalid = 0;
-#pragma unroll
-    for (int e = 0; e < E; e++) {
-        const int g = lane * E + e;
-        KeyT kk = KeyMax<KeyT>::value;
-        if (g < nwin) {
-            KeyT t;
-            if (stream_window<KeyT>(st, a + g, k, t)) { kk = t; myvalid++; }
-        }
-        key[e] = kk;
-    }
-    int nvalid = myvalid;
+    int nvalid = __popc(extract_windows<KeyT, E>(st, a + lane * E, k, key));
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, d);
     bitonic_sort_blocked<KeyT, E>(key);
@@ -271,7 +295,7 @@ __global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) sparse_short_kernel(
     constexpr int WARPS = SparseCta<E>::WARPS;
     __shared__ uint32_t s_cw[WARPS][kStreamBlocks];
     __shared__ __align__(4) uint16_t s_vh[WARPS][2 * ((kStreamBlocks + 1) / 2) + 2];
-    __shared__ KeyT s_stage_k[WARPS][32 * E];
+    __shared__ __align__(16) KeyT s_stage_k[WARPS][32 * E];
     __shared__ uint32_t s_stage_c[WARPS][32 * E];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpStream st{s_cw[warp], s_vh[warp]};
@@ -297,7 +321,7 @@ __global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) sparse_short_kernel(
         __syncwarp();
         KeyT* ko = keys + row_begin[r];
         uint32_t* co = counts + row_begin[r];
-        const int nd = warp_count_read<KeyT, E>(st, a, nwin, k, ko, co, s_stage_k[warp], s_stage_c[warp]);
+        const int nd = warp_count_read<KeyT, E>(st, a, k, ko, co, s_stage_k[warp], s_stage_c[warp]);
         if (lane == 0) row_count[r] = nd;
     }
 }
@@ -417,13 +441,16 @@ __global__ void __launch_bounds__(256) partition_kernel(const uint8_t* __restric
         }
         __syncthreads();
         unsigned long long* bk = bucket + (boff[j] - b0);
-        for (int g = threadIdx.x; g < n; g += 256) {
-            KeyT key;
-            if (stream_window<KeyT>(st, a + g, k, key)) {
-                const uint64_t d = (uint64_t)key >> shift;
+        constexpr int W = kPartTile / 256;   // consecutive windows per thread
+        KeyT key[W];
+        const uint32_t valid = extract_windows<KeyT, W>(st, a + (int)threadIdx.x * W, k, key);
+#pragma unroll
+        for (int e = 0; e < W; e++) {
+            if (valid >> e & 1u) {
+                const uint64_t d = (uint64_t)key[e] >> shift;
                 if (SCATTER) {
                     const unsigned long long pos = atomicAdd(&bk[d], 1ull);
-                    scratch[pos] = (SortT)key;   // narrow rows: the suffix (shift <= 32, the digit is cut off)
+                    scratch[pos] = (SortT)key[e];   // narrow rows: the suffix (shift <= 32, the digit is cut off)
                 } else {
                     atomicAdd(&bk[d], 1ull);
                 }
@@ -441,7 +468,7 @@ __global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) bucket_sort_kernel(
     unsigned long long* __restrict__ distinct, int64_t* __restrict__ fb_list, unsigned long long* __restrict__ n_fb)
 {
     constexpr int WARPS = SparseCta<E>::WARPS;
-    __shared__ KeyT s_stage_k[WARPS][32 * E];
+    __shared__ __align__(16) KeyT s_stage_k[WARPS][32 * E];
     __shared__ uint32_t s_stage_c[WARPS][32 * E];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int64_t b = (int64_t)blockIdx.x * WARPS + warp; b < nb; b += (int64_t)gridDim.x * WARPS) {
