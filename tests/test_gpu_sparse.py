@@ -118,3 +118,68 @@ def test_capacity_error():
         cf.count_sparse_device(b.data_ptr(), s.data_ptr(), l.data_ptr(), len(data), 10, 12, rb.data_ptr(), rc.data_ptr(),
                                keys.data_ptr(), cnt.data_ptr(), 100)
     assert e.value.code == -1 and "capacity" in str(e.value)
+
+
+def _device_batch(nS, L, seed, n_frac):
+    """nS reads of L ASCII bases generated on the GPU (uniform ACGT, n_frac of them 'N'), '\\n' separated"""
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device="cuda")
+    flat = torch.full((nS * (L + 1) + 16,), 10, dtype=torch.uint8, device="cuda")
+    body = lut[torch.randint(0, 4, (nS, L), generator=g, device="cuda")]
+    if n_frac > 0:
+        body[torch.rand((nS, L), generator=g, device="cuda") < n_frac] = 78
+    flat[: nS * (L + 1)].view(nS, L + 1)[:, :L] = body
+    start = torch.arange(nS, dtype=torch.int64, device="cuda") * (L + 1)
+    length = torch.full((nS,), L, dtype=torch.int32, device="cuda")
+    return flat, start, length
+
+
+@pytest.mark.parametrize("nS,L,k,key_bytes", [(2_000_000, 150, 12, 4), (30, 5_000_000, 21, 8), (12, 5_000_000, 31, 8)])
+def test_scale_properties(nS, L, k, key_bytes):
+    """configs C3/C4 at sizes the oracle cannot sort in a test: size-independent properties of every row
+    (keys strictly increasing, counts >= 1 and summing to the row's valid windows, nothing written past the
+    row) over the whole batch -- 150 M windows = two scratch batches at the default batch size -- plus the
+    oracle on the first and the last row."""
+    flat, start, length = _device_batch(nS, L, 7 + k, 0.001)
+    nwin = L - k + 1
+    cap = nS * nwin
+    rb = torch.zeros(nS + 1, dtype=torch.int64, device="cuda")
+    rc = torch.full((nS,), -7, dtype=torch.int32, device="cuda")
+    kdt = torch.int32 if key_bytes == 4 else torch.int64
+    keys = torch.full((cap,), -1, dtype=kdt, device="cuda")
+    cnt = torch.zeros(cap, dtype=torch.int32, device="cuda")
+    total = cf.count_sparse_device(flat.data_ptr(), start.data_ptr(), length.data_ptr(), nS * (L + 1), nS, k, rb.data_ptr(),
+                                   rc.data_ptr(), keys.data_ptr(), cnt.data_ptr(), cap, key_bytes=key_bytes, fmt=cf.FMT_ASCII)
+    torch.cuda.synchronize()
+    assert total == cap
+    assert torch.equal(rb, torch.arange(nS + 1, dtype=torch.int64, device="cuda") * nwin)
+    rc64 = rc.to(torch.int64)
+    assert int(rc64.min()) > 0 and int(rc64.max()) <= nwin
+    # valid windows per row from the bases: a window is valid iff no 'N' among its k bases
+    bad = (flat[: nS * (L + 1)].view(nS, L + 1)[:, :L] == 78).to(torch.int32)
+    csum = torch.cumsum(torch.nn.functional.pad(bad, (1, 0)), dim=1)
+    valid = ((csum[:, k:] - csum[:, :-k]) == 0).sum(dim=1)
+    del bad, csum
+    K = keys.view(nS, nwin)
+    Cn = cnt.view(nS, nwin)
+    col = torch.arange(nwin, device="cuda").unsqueeze(0)
+    live = col < rc64.unsqueeze(1)
+    assert torch.equal((Cn * live).sum(dim=1, dtype=torch.int64), valid)          # counts sum to the valid windows
+    assert bool((Cn[live] >= 1).all())
+    assert bool((Cn[~live] == 0).all()) and bool((K[~live] == -1).all())          # nothing behind the row's pairs
+    # strictly increasing keys (unsigned order; keys use at most 62 bits, uint32 keys compared as int64)
+    Kl = K.to(torch.int64) & 0xFFFFFFFF if key_bytes == 4 else K
+    inc = (Kl[:, 1:] > Kl[:, :-1]) | ~live[:, 1:]
+    assert bool(inc.all())
+    assert int(Kl[live].max()) < 4 ** k and int(Kl[live].min()) >= 0
+    # oracle on the first and the last row
+    for r in (0, nS - 1):
+        raw = flat[r * (L + 1): (r + 1) * (L + 1)].cpu().numpy()
+        codes = np.full(L + 1, -1, dtype=np.int8)
+        for ch, c in ((65, 0), (67, 1), (71, 2), (84, 3)):
+            codes[:L][raw[:L] == ch] = c
+        orp, okeys, ocnt = ob.count_sparse(codes, np.array([0], dtype=np.int64), np.array([L], dtype=np.int32), k, ascii=False)
+        n = int(rc[r])
+        assert n == orp[1]
+        np.testing.assert_array_equal(K[r, :n].cpu().numpy().view(np.uint32 if key_bytes == 4 else np.uint64).astype(np.uint64), okeys)
+        np.testing.assert_array_equal(Cn[r, :n].cpu().numpy().view(np.uint32), ocnt)
