@@ -341,8 +341,7 @@ __global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) sparse_short_kernel(
 constexpr int kBucketTarget = 256;       // mean keys per bucket at most this (uniform keys)
 constexpr int kBucketCap = 512;          // what one warp sorts in registers (E = 16)
 constexpr int kMaxBucketBits = 22;
-constexpr int kPartTile = 4096;          // windows per CTA tile of the two partition passes
-constexpr int kPartBlocks = (15 + kPartTile + 30 + 15) / 16 + 3;
+constexpr int kPartTile = 4096;          // windows per tile: the unit in which partition work is cut
 constexpr int64_t kDefaultBatchKeys = (int64_t)128 << 20;
 constexpr int kSortTile = 2048;          // keys per warp tile of the fallback radix sort
 constexpr int kSortWarps = 8;
@@ -374,16 +373,36 @@ __global__ void collect_long_kernel(const int32_t* __restrict__ length, int64_t 
     }
 }
 
-// per long row j: windows, buckets and partition tiles (inputs of three exclusive scans)
+// A row's partition work is cut into SLABS of up to 64 consecutive tiles; a CTA owns one slab.  In
+// the counting pass it keeps the row's bucket counters PRIVATE in shared memory, so the per-key
+// atomics never leave the SM, and adds them to the row's counters in HBM once per slab.  Rows with
+// more buckets than fit shared memory (> 8 Mi windows) are one slab and count with global atomics.
+// The scatter pass keeps ONE cursor per bucket in HBM (L2): a bucket then fills front to back, its
+// write frontier is one 32-byte sector, and the frontiers of all rows in flight (26 rows x 32768
+// buckets x 32 B = 27 MB) stay L2-resident so that partial sector writes merge there.  Private
+// per-slab cursors were measured: 20x as many frontiers (545 MB), scatter 1.7 -> 3.1 ms.
+constexpr int kSlabTiles = 64;
+constexpr int kSmemBuckets = 32768;      // 128 KiB of uint32 counters
+__host__ __device__ __forceinline__ int64_t row_slabs(int64_t ntiles, int64_t nbuckets)
+{
+    return nbuckets > kSmemBuckets ? 1 : (ntiles + kSlabTiles - 1) / kSlabTiles;
+}
+
+// per long row j: windows, buckets, partition tiles and slabs (inputs of four exclusive scans)
 __global__ void long_sizes_kernel(const int64_t* __restrict__ long_rows, int64_t n_long, const int32_t* __restrict__ length,
-                                  int k, int64_t* __restrict__ loff, int64_t* __restrict__ boff, int64_t* __restrict__ ptile)
+                                  int k, int64_t* __restrict__ loff, int64_t* __restrict__ boff, int64_t* __restrict__ ptile,
+                                  int64_t* __restrict__ uoff)
 {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j <= n_long) {
         const int64_t nwin = j < n_long ? length[long_rows[j]] - k + 1 : 0;
+        const int64_t nb = j < n_long ? (int64_t)1 << bucket_bits(nwin, k) : 0;
+        const int64_t nt = (nwin + kPartTile - 1) / kPartTile;
+        const int64_t ns = j < n_long ? row_slabs(nt, nb) : 0;
         loff[j] = nwin;
-        boff[j] = j < n_long ? (int64_t)1 << bucket_bits(nwin, k) : 0;
-        ptile[j] = (nwin + kPartTile - 1) / kPartTile;
+        boff[j] = nb;
+        ptile[j] = nt;
+        uoff[j] = ns;
     }
 }
 
@@ -397,63 +416,118 @@ __device__ __forceinline__ int64_t locate(const int64_t* __restrict__ scan, int6
     return lo;
 }
 
-// Partition pass over the bases of the batch rows [j0, j1): CTA tiles of 4096 windows, the tile's
-// bases encoded once into a shared-memory bit stream (as for the short reads), every thread
-// extracts windows by funnel shift.  SCATTER = false: count the buckets.  SCATTER = true: bucket[]
-// holds the scanned counts; a key takes the next slot of its bucket (afterwards bucket[b] = end of b).
-template <typename KeyT, typename SortT, int FMT, bool SCATTER>
-__global__ void __launch_bounds__(256) partition_kernel(const uint8_t* __restrict__ bases, const int64_t* __restrict__ start,
-                                                        const int32_t* __restrict__ length, int k,
-                                                        const int64_t* __restrict__ long_rows,
-                                                        const int64_t* __restrict__ boff, const int64_t* __restrict__ ptile,
-                                                        int64_t j0, int64_t j1, unsigned long long* __restrict__ bucket,
-                                                        SortT* __restrict__ scratch)
+// Partition pass over the bases of the batch rows [j0, j1).  Work unit = one slab (see above) of one
+// row, walked in steps of 16*T windows: the step's bases are encoded once into a shared-memory bit
+// stream (as for the short reads; the raw blocks of the next step are already in flight), every
+// thread extracts 16 consecutive windows from registers.  T = 512 for the counting pass when the
+// counters leave room for one CTA per SM only, T = 256 otherwise.
+//   SCATTER = false: count the buckets of the row into bucket[] (through shared memory).
+//   SCATTER = true : bucket[] holds the scanned counts; a key takes the next slot of its bucket
+//                    (afterwards bucket[b] = end of bucket b in the scratch).
+template <typename KeyT, typename SortT, int FMT, bool SCATTER, int T, int ILP = 1>
+__global__ void __launch_bounds__(T, SCATTER ? (ILP > 1 ? 4 : 5) : 1) partition_kernel(
+    const uint8_t* __restrict__ bases, const int64_t* __restrict__ start, const int32_t* __restrict__ length, int k,
+    const int64_t* __restrict__ long_rows, const int64_t* __restrict__ boff, const int64_t* __restrict__ ptile,
+    const int64_t* __restrict__ uoff, int64_t j0, int64_t j1, unsigned long long* __restrict__ bucket,
+    SortT* __restrict__ scratch)
 {
+    extern __shared__ uint32_t s_cnt[];   // counting pass: private counters of the slab's row
+    constexpr int W = 16;                 // consecutive windows per thread
+    constexpr int STEP = W * T;           // windows per step
+    constexpr int kPartBlocks = (15 + STEP + 30 + 15) / 16 + 3;
+    constexpr int NB = (kPartBlocks + T - 1) / T;   // raw blocks per thread and step
     __shared__ uint32_t s_cw[kPartBlocks];
     __shared__ __align__(4) uint16_t s_vh[2 * ((kPartBlocks + 1) / 2) + 2];
     WarpStream st{s_cw, s_vh};
-    const int64_t t0 = ptile[j0], ntiles = ptile[j1] - t0, b0 = boff[j0];
-    for (int64_t t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        const int64_t j = locate(ptile, j0, j1, t0 + t);
+    const int64_t u0 = uoff[j0], nunits = uoff[j1] - u0, b0 = boff[j0];
+    for (int64_t u = blockIdx.x; u < nunits; u += gridDim.x) {
+        const int64_t j = locate(uoff, j0, j1, u0 + u);
+        const int64_t slab = u0 + u - uoff[j], S = uoff[j + 1] - uoff[j];
+        const int nb = (int)(boff[j + 1] - boff[j]);
+        const int64_t ntiles_row = ptile[j + 1] - ptile[j];
+        const int64_t per = (ntiles_row + S - 1) / S;
         const int64_t r = long_rows[j];
         const int64_t s = start[r];
         const int len = length[r];
         const int nwin = len - k + 1;
-        const int64_t w0 = (t0 + t - ptile[j]) * kPartTile;
-        const int n = (int)min((int64_t)kPartTile, nwin - w0);
+        const int64_t wbeg = slab * per * kPartTile, wend = min((int64_t)nwin, wbeg + per * kPartTile);   // the slab's windows
         const int shift = 2 * k - bucket_bits(nwin, k);
-        // stream position 0 = first byte of the 16-byte block that holds base w0 of the read
-        const int64_t blk0 = (s + w0) >> 4;
-        const int a = (int)((s + w0) & 15);
-        const int nblocks = (a + n + k - 1 + 15) >> 4;
-        const int64_t rs = s - blk0 * 16, re = s + len - blk0 * 16;   // the read in stream coordinates
-        __syncthreads();   // the previous tile has been read
-        for (int b = threadIdx.x; b < kPartBlocks; b += 256) {
-            uint32_t c = 0, v = 0;
-            if (b < nblocks) {
-                encode16<FMT>(ld_block(bases + (blk0 + b) * 16), c, v);
-                const int lo = (int)max((int64_t)0, min((int64_t)16, rs - 16 * b));
-                const int hi = (int)max((int64_t)0, min((int64_t)16, re - 16 * b));
-                v &= from_pos(lo) & ~from_pos(hi);
-            }
-            st.cw[b] = c;
-            st.vh[b ^ 1] = (uint16_t)v;
-        }
-        __syncthreads();
         unsigned long long* bk = bucket + (boff[j] - b0);
-        constexpr int W = kPartTile / 256;   // consecutive windows per thread
-        KeyT key[W];
-        const uint32_t valid = extract_windows<KeyT, W>(st, a + (int)threadIdx.x * W, k, key);
+        const bool priv = !SCATTER && nb <= kSmemBuckets;
+        if (priv) {
+            __syncthreads();   // the previous unit has flushed its counters
+            for (int b = threadIdx.x; b < nb; b += T) s_cnt[b] = 0u;
+        }
+        // a step covers windows [w0, w0 + STEP): stream position 0 = first byte of the 16-byte block that
+        // holds the step's first base; consecutive steps are STEP/16 blocks apart
+        const int a = (int)((s + wbeg) & 15);
+        int64_t blk0 = (s + wbeg) >> 4;
+        const int64_t blk_end = (s + len + 15) >> 4;       // blocks of this read end here
+        uint4 raw[NB];
 #pragma unroll
-        for (int e = 0; e < W; e++) {
-            if (valid >> e & 1u) {
-                const uint64_t d = (uint64_t)key[e] >> shift;
-                if (SCATTER) {
-                    const unsigned long long pos = atomicAdd(&bk[d], 1ull);
-                    scratch[pos] = (SortT)key[e];   // narrow rows: the suffix (shift <= 32, the digit is cut off)
-                } else {
-                    atomicAdd(&bk[d], 1ull);
+        for (int q = 0; q < NB; q++) {
+            const int64_t b = blk0 + threadIdx.x + q * T;
+            raw[q] = threadIdx.x + q * T < kPartBlocks && b < blk_end ? ld_block(bases + b * 16) : make_uint4(0, 0, 0, 0);
+        }
+        for (int64_t w0 = wbeg; w0 < wend; w0 += STEP) {
+            const int64_t rs = s - blk0 * 16, re = s + len - blk0 * 16;   // the read in stream coordinates
+            __syncthreads();   // the previous tile has been read (and the counters are cleared)
+#pragma unroll
+            for (int q = 0; q < NB; q++) {
+                const int b = threadIdx.x + q * T;
+                if (b < kPartBlocks) {
+                    uint32_t cc, v;
+                    encode16<FMT>(raw[q], cc, v);
+                    const int lo = (int)max((int64_t)0, min((int64_t)16, rs - 16 * b));
+                    const int hi = (int)max((int64_t)0, min((int64_t)16, re - 16 * b));
+                    v &= from_pos(lo) & ~from_pos(hi);
+                    st.cw[b] = cc;
+                    st.vh[b ^ 1] = (uint16_t)v;
                 }
+            }
+            __syncthreads();
+            blk0 += STEP / 16;
+            if (w0 + STEP < wend) {
+#pragma unroll
+                for (int q = 0; q < NB; q++) {
+                    const int64_t b = blk0 + threadIdx.x + q * T;
+                    raw[q] = threadIdx.x + q * T < kPartBlocks && b < blk_end ? ld_block(bases + b * 16) : make_uint4(0, 0, 0, 0);
+                }
+            }
+            KeyT key[W];
+            uint32_t valid = extract_windows<KeyT, W>(st, a + (int)threadIdx.x * W, k, key);
+            if (w0 + (int64_t)threadIdx.x * W >= wend) valid = 0;   // the next slab's windows (slabs end at multiples of 16)
+            if (!SCATTER) {
+#pragma unroll
+                for (int e = 0; e < W; e++) {
+                    if (valid >> e & 1u) {
+                        const uint32_t d = (uint32_t)((uint64_t)key[e] >> shift);
+                        if (priv) atomicAdd(&s_cnt[d], 1u); else atomicAdd(&bk[d], 1ull);
+                    }
+                }
+            } else {
+                // slots of ILP keys first, then their stores.  Measured: ILP = 8 (64 registers, 4 CTAs/SM) 1.87 ms
+                // per 128 Mi keys, ILP = 1 (48 registers, 5 CTAs/SM) 1.71 ms: the pass is bound by L2 operations
+                // (one atomic + one sector write per key, ~150 G/s), not by latency
+#pragma unroll
+                for (int h = 0; h < W; h += ILP) {
+                    unsigned long long pos[ILP];
+#pragma unroll
+                    for (int e = 0; e < ILP; e++) {
+                        pos[e] = 0;
+                        if (valid >> (h + e) & 1u) pos[e] = atomicAdd(&bk[(uint32_t)((uint64_t)key[h + e] >> shift)], 1ull);
+                    }
+#pragma unroll
+                    for (int e = 0; e < ILP; e++)
+                        if (valid >> (h + e) & 1u) scratch[pos[e]] = (SortT)key[h + e];   // narrow rows: the suffix (the digit is cut off)
+                }
+            }
+        }
+        if (priv) {
+            __syncthreads();
+            for (int b = threadIdx.x; b < nb; b += T) {
+                const uint32_t n = s_cnt[b];
+                if (n) atomicAdd(&bk[b], (unsigned long long)n);
             }
         }
     }
@@ -715,12 +789,13 @@ static cudaError_t sparse_long_rows(const uint8_t* bases, const int64_t* start, 
 {
     cudaError_t e;
     PoolScratch pool(st);
-    // per-row windows / buckets / partition tiles, scanned
-    int64_t *loff = nullptr, *boff = nullptr, *ptile = nullptr;
+    // per-row windows / buckets / partition tiles / slabs / counters, scanned
+    int64_t *loff = nullptr, *boff = nullptr, *ptile = nullptr, *uoff = nullptr;
     CFRK_TRY(pool.get(&loff, (size_t)nl + 1));
     CFRK_TRY(pool.get(&boff, (size_t)nl + 1));
     CFRK_TRY(pool.get(&ptile, (size_t)nl + 1));
-    long_sizes_kernel<<<(unsigned)((nl + 256) / 256), 256, 0, st>>>(long_rows, nl, length, k, loff, boff, ptile);
+    CFRK_TRY(pool.get(&uoff, (size_t)nl + 1));
+    long_sizes_kernel<<<(unsigned)((nl + 256) / 256), 256, 0, st>>>(long_rows, nl, length, k, loff, boff, ptile, uoff);
     count_launch();
     {
         size_t sb = 0;
@@ -730,10 +805,12 @@ static cudaError_t sparse_long_rows(const uint8_t* bases, const int64_t* start, 
         CFRK_TRY(scan_in_place(loff, nl + 1, stmp, sb, st));
         CFRK_TRY(scan_in_place(boff, nl + 1, stmp, sb, st));
         CFRK_TRY(scan_in_place(ptile, nl + 1, stmp, sb, st));
+        CFRK_TRY(scan_in_place(uoff, nl + 1, stmp, sb, st));
     }
-    std::vector<int64_t> h_loff((size_t)nl + 1), h_boff((size_t)nl + 1);
+    std::vector<int64_t> h_loff((size_t)nl + 1), h_boff((size_t)nl + 1), h_uoff((size_t)nl + 1);
     cudaMemcpyAsync(h_loff.data(), loff, ((size_t)nl + 1) * 8, cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(h_boff.data(), boff, ((size_t)nl + 1) * 8, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(h_uoff.data(), uoff, ((size_t)nl + 1) * 8, cudaMemcpyDeviceToHost, st);
     CFRK_TRY(cudaStreamSynchronize(st));
 
     // batches of consecutive long rows, <= batch_keys windows each (a larger row is its own batch)
@@ -763,22 +840,43 @@ static cudaError_t sparse_long_rows(const uint8_t* bases, const int64_t* start, 
     CFRK_TRY(pool.get(&n_fb, 1));
     cub::DeviceScan::ExclusiveSum(nullptr, bb, bucket, bucket, max_nb + 1, st);
     CFRK_TRY(pool.get(reinterpret_cast<char**>(&btmp), bb));
+    const size_t max_dyn = (size_t)kSmemBuckets * 4;
+    CFRK_TRY(cudaFuncSetAttribute(partition_kernel<KeyT, SortT, FMT, false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_dyn));
     tr.mark("long rows: collect + scratch");
 
     for (size_t c = 0; c + 1 < cuts.size(); c++) {
         const int64_t j0 = cuts[c], j1 = cuts[c + 1];
         const int64_t nb = h_boff[(size_t)j1] - h_boff[(size_t)j0];
         const int64_t nkeys = h_loff[(size_t)j1] - h_loff[(size_t)j0];
-        const int64_t ntiles = (nkeys + kPartTile - 1) / kPartTile + (j1 - j0);   // upper bound: sizes the grid only
-        const unsigned pgrid = (unsigned)std::min<int64_t>(ntiles, (int64_t)num_sms * 8);
+        const int64_t nunits = h_uoff[(size_t)j1] - h_uoff[(size_t)j0];
+        // shared-memory counters: as many as the largest row of the batch that keeps them private
+        int64_t priv_nb = 1;
+        for (int64_t j = j0; j < j1; j++) {
+            const int64_t rnb = h_boff[(size_t)j + 1] - h_boff[(size_t)j];
+            if (rnb <= kSmemBuckets) priv_nb = std::max(priv_nb, rnb);
+        }
+        const size_t dyn = (size_t)priv_nb * 4;
+        const bool big = dyn > 48 * 1024;   // counters leave room for few CTAs per SM: 512 threads each
+        const int ht = big ? 512 : 256;
+        const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(2048 / ht, (size_t)(220 * 1024) / (dyn + 4096)));
+        const unsigned hgrid = (unsigned)std::min<int64_t>(nunits, (int64_t)num_sms * ctas_per_sm);
+        const unsigned sgrid = (unsigned)std::min<int64_t>((nkeys + kPartTile - 1) / kPartTile + (j1 - j0), (int64_t)num_sms * 8);
         cudaMemsetAsync(bucket, 0, ((size_t)nb + 1) * 8, st);
         cudaMemsetAsync(distinct, 0, ((size_t)nb + 1) * 8, st);
         cudaMemsetAsync(n_fb, 0, 8, st);
-        partition_kernel<KeyT, SortT, FMT, false><<<pgrid, 256, 0, st>>>(bases, start, length, k, long_rows, boff, ptile, j0, j1, bucket, scratch);
+        if (big)
+            partition_kernel<KeyT, SortT, FMT, false, 512><<<hgrid, 512, dyn, st>>>(bases, start, length, k, long_rows, boff, ptile, uoff,
+                                                                                   j0, j1, bucket, scratch);
+        else
+            partition_kernel<KeyT, SortT, FMT, false, 256><<<hgrid, 256, dyn, st>>>(bases, start, length, k, long_rows, boff, ptile, uoff,
+                                                                                   j0, j1, bucket, scratch);
         count_launch();
         tr.mark("long rows: bucket histogram");
         CFRK_TRY(scan_in_place(bucket, nb + 1, btmp, bb, st));
-        partition_kernel<KeyT, SortT, FMT, true><<<pgrid, 256, 0, st>>>(bases, start, length, k, long_rows, boff, ptile, j0, j1, bucket, scratch);
+        // scatter: units = single tiles in row order (ptile as the unit scan), so that few rows are in
+        // flight and the write frontiers stay hot in L2
+        partition_kernel<KeyT, SortT, FMT, true, 256><<<sgrid, 256, 0, st>>>(bases, start, length, k, long_rows, boff, ptile, ptile,
+                                                                            j0, j1, bucket, scratch);
         count_launch();
         tr.mark("long rows: scatter");
         {
