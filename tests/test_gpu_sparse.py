@@ -134,12 +134,14 @@ def _device_batch(nS, L, seed, n_frac):
     return flat, start, length
 
 
-@pytest.mark.parametrize("nS,L,k,key_bytes", [(2_000_000, 150, 12, 4), (30, 5_000_000, 21, 8), (12, 5_000_000, 31, 8)])
+@pytest.mark.parametrize("nS,L,k,key_bytes", [(2_000_000, 150, 12, 4), (30, 5_000_000, 21, 8), (12, 5_000_000, 31, 8),
+                                               (2, 9_000_000, 21, 8), (1, 9_000_000, 31, 8)])
 def test_scale_properties(nS, L, k, key_bytes):
     """configs C3/C4 at sizes the oracle cannot sort in a test: size-independent properties of every row
     (keys strictly increasing, counts >= 1 and summing to the row's valid windows, nothing written past the
     row) over the whole batch -- 150 M windows = two scratch batches at the default batch size -- plus the
-    oracle on the first and the last row."""
+    oracle on the first and the last row.  The 9 Mbp rows have 65536 buckets: more than the shared-memory
+    counters of the counting pass hold, so they count with global atomics."""
     flat, start, length = _device_batch(nS, L, 7 + k, 0.001)
     nwin = L - k + 1
     cap = nS * nwin
