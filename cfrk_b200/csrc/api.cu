@@ -309,7 +309,7 @@ int cfrk_global_hist_device(const void* d_bases, int fmt, const int64_t* d_start
     if (nS == 0) return CFRK_OK;
     if (!d_bases || !d_start || !d_length || !d_hist) return fail(CFRK_EINVAL, "null device pointer");
     if (reinterpret_cast<uintptr_t>(d_bases) & 15) return fail(CFRK_EINVAL, "d_bases must be 16-byte aligned");
-    cudaError_t e = cfrk::launch_global_hist(d_bases, fmt, d_start, d_length, nS, k, d_hist,
+    cudaError_t e = cfrk::launch_global_hist(d_bases, fmt, d_start, d_length, nN, nS, k, d_hist,
                                              static_cast<cudaStream_t>(stream));
     if (e != cudaSuccess) return fail_cuda(e, "global_hist_kernel launch");
     return CFRK_OK;

@@ -912,8 +912,9 @@ static cudaError_t launch_hist_fmt(int k, const void* b, const int64_t* s, const
 }
 
 cudaError_t launch_global_hist(const void* bases, int fmt, const int64_t* start, const int32_t* length,
-                               int64_t nS, int k, uint32_t* hist, cudaStream_t st)
+                               int64_t nN, int64_t nS, int k, uint32_t* hist, cudaStream_t st)
 {
+    if (hist_split_applies(k, nN)) return launch_global_hist_split(bases, fmt, start, length, nN, nS, k, hist, st);
     return fmt == FMT_ASCII ? launch_hist_fmt<FMT_ASCII>(k, bases, start, length, nS, hist, st)
                             : launch_hist_fmt<FMT_CODES>(k, bases, start, length, nS, hist, st);
 }

@@ -15,9 +15,14 @@ cudaError_t launch_dense(const void* bases, int fmt, const int64_t* start, const
                          const uint16_t* packed_valid = nullptr);   // fmt 2 (packed): bases = uint32 codes
 int dense_reads_per_tile(int k);
 
-// hist[4^k] += exact-mode k-mer counts of the whole batch; k in 1..15.
+// hist[4^k] += exact-mode k-mer counts of the whole batch (nN bytes of bases); k in 1..15.
+// k = 9..13 on large batches goes through the partitioned path (hist_split.cu).
 cudaError_t launch_global_hist(const void* bases, int fmt, const int64_t* start, const int32_t* length,
-                               int64_t nS, int k, uint32_t* hist, cudaStream_t st);
+                               int64_t nN, int64_t nS, int k, uint32_t* hist, cudaStream_t st);
+bool hist_split_applies(int k, int64_t nN);
+void keep_pool_memory(int dev);   // scratch of the stream-ordered pool stays mapped between calls (sparse.cu)
+cudaError_t launch_global_hist_split(const void* bases, int fmt, const int64_t* start, const int32_t* length, int64_t nN,
+                                     int64_t nS, int k, uint32_t* hist, cudaStream_t st);
 
 // n bytes of bases -> ceil(n/16) words of 2-bit codes + 16-bit validity masks.
 cudaError_t launch_encode_2bit(const void* bases, int fmt, int64_t n, uint32_t* codes, uint16_t* valid,

@@ -66,6 +66,43 @@ def test_global_hist(k):
     np.testing.assert_array_equal(hist.cpu().numpy().astype(np.uint64), 2 * want)   # accumulates
 
 
+@pytest.mark.parametrize("k", [9, 10, 12, 13])
+@pytest.mark.parametrize("layout", ["codes", "fasta_bytes", "skewed"])
+def test_global_hist_split_path(k, layout, monkeypatch):
+    """the partitioned histogram (hist_split.cu; default only for large batches) forced on small inputs:
+    reference codes; raw FASTA bytes, where header lines full of ACGT letters lie between the reads and must
+    not be counted; and a skewed batch whose k-mers overflow the fixed partition capacity (those suffixes
+    are counted directly)"""
+    monkeypatch.setenv("CFRK_HIST_SPLIT", "1")
+    if layout == "fasta_bytes":
+        import random
+        rng = random.Random(k)
+        recs = []
+        for i in range(400):
+            L = rng.choice([0, 1, k - 1, k, k + 1, 40, 150, 151, 700, 5000])
+            seq = "".join(rng.choice("ACGT") for _ in range(L))
+            if L > 30:
+                seq = seq[:L // 2] + "N" + seq[L // 2 + 1:]
+            recs.append(f">ACGTACGTACGTACGT_read{i}_GATTACA\n{seq}\n")
+        data, start, length = fx.ascii_batch("".join(recs))     # the raw file bytes, headers included
+        want = ob.global_hist(data, start, length, k, ascii=True)
+        b, fmt, n = padded_bases(data, 0), cf.FMT_ASCII, len(data)
+    else:
+        if layout == "skewed":
+            reads = ["A" * 30000, "ACGT" * 5000, "T" * 9000 + "N" + "T" * 9000] + ["AC" * 300] * 50
+            data, start, length = ob.parse_fasta(text="".join(f">r{i}\n{r}\n" for i, r in enumerate(reads)))
+        else:
+            data, start, length = ob.parse_fasta(text=fx.fx_with_n() + fx.fx_ragged() + fx.fx_long())
+        want = ob.global_hist(data, start, length, k)
+        b, fmt, n = padded_bases(data, 0xFF), cf.FMT_CODES, len(data)
+    hist = torch.zeros(4 ** k, dtype=torch.int32, device="cuda")
+    s, l = dev(start), dev(length)
+    for _ in range(2):
+        cf.global_hist_device(b.data_ptr(), s.data_ptr(), l.data_ptr(), n, len(start), k, hist.data_ptr(), fmt=fmt)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(hist.cpu().numpy().astype(np.uint64), 2 * want)   # accumulates
+
+
 @pytest.mark.parametrize("k", [2, 4, 5, 6, 8])
 def test_device_read_ranges_and_chunk_openers(k):
     """one launch over many reference chunks == one kmer_main call per chunk (src/main.cu:222,294,300);
