@@ -363,6 +363,28 @@ def run_ours(args):
                "sample": f"{cn} reads x {L} bp per k (one reference chunk), cfrk_count_dense_host, pinned host "
                          f"buffers, codes layout", "ms_per_step": round(dt / steps * 1e3, 2)}
 
+    # ---- the same reference chunk resident in HBM: what sits next to the reference arm's kernels_only
+    chunk_resident = None
+    if not args.no_e2e and rank == 0:
+        db, ds, dl = hb_t.to(dev), hs_t.to(dev), hl_t.to(dev)
+        rows = max(cn * 4 ** k for k in ks)
+        dout = ring if ring.numel() >= rows else torch.empty(rows, dtype=torch.int32, device=dev)
+        per, tot = [], 0.0
+        for k in ks:
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for r in range(6):
+                if r == 1:
+                    c0.record()
+                cf.count_dense_device(db.data_ptr(), ds.data_ptr(), dl.data_ptr(), hb.nbytes, cn, k, dout.data_ptr(),
+                                      mode=mode, fmt=cf.FMT_CODES, stream=stream)
+            c1.record(); torch.cuda.synchronize()
+            ms = c0.elapsed_time(c1) / 5
+            per.append({"k": k, "ms": round(ms, 4), "gbases_s": round(cn * L / ms / 1e6, 2)})
+            tot += ms
+        chunk_resident = {"value": round(cn * L * len(ks) / tot / 1e6, 2), "unit": UNIT, "ms_per_sweep": round(tot, 3), "per_k": per,
+                          "what": f"{cn} reads x {L} bp (one reference chunk, codes layout) resident in HBM, rows left in HBM: "
+                                  f"the counterpart of the reference arm's kernels_only"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -378,7 +400,7 @@ def run_ours(args):
                    "l2_policy": "inputs (1.5 GB) and outputs (>= 10 GB per k) larger than L2 (126 MB); no flush needed",
                    "reads_per_gpu": nS, "read_len": L, "k": ks, "parallelism": f"read-range shards x{world}"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-        "clocks": clocks, "per_k": per_k,
+        "clocks": clocks, "per_k": per_k, "chunk_resident": chunk_resident,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
@@ -445,13 +467,34 @@ def run_reference(args):
             os.dup2(saved_fd, 1)
             os.close(saved_fd)
         v = cn * L * len(ks) * steps / dt / 1e9
+        # SURVEY 8(d) baseline 1b: the reference's four kernel launches alone, inputs resident in HBM
+        # (oracle/ref_helper.cu restates the launch shapes of src/kmer_main.cu:66-111)
+        kernels_only = None
+        if hasattr(lib, "ref_kernels_time"):
+            lib.ref_kernels_time.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_long, C.c_long, C.c_int, C.c_int,
+                                             C.POINTER(C.c_float)]
+            db, ds, dl = hb_t.cuda(), hs_t.cuda(), hl_t.cuda()
+            per_k, tot_ms = [], 0.0
+            for k in ks:
+                ms = C.c_float(0)
+                rc = lib.ref_kernels_time(db.data_ptr(), ds.data_ptr(), dl.data_ptr(), nN, cn, k, 5, C.byref(ms))
+                if rc != 0:
+                    per_k = None
+                    break
+                per_k.append({"k": k, "ms": round(ms.value, 4), "gbases_s": round(cn * L / ms.value / 1e6, 3)})
+                tot_ms += ms.value
+            if per_k:
+                kernels_only = {"value": round(cn * L * len(ks) / tot_ms / 1e6, 3), "unit": UNIT, "ms_per_sweep": round(tot_ms, 3),
+                                "per_k": per_k,
+                                "what": "SetMatrix x2 + ComputeIndex + ComputeFreqNew (the reference's objects, its launch shapes), "
+                                        f"{cn} reads x {L} bp resident in HBM, CUDA events, no allocation or copy in the timed region"}
         line = {"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": 1,
                 "steps": steps, "warmup": args.warmup, "ms_per_step": round(dt / steps * 1e3, 2),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32/i32",
                 "data": "synthetic", "config": cfg,
                 "reference_kind": "the reference's own kmer_main (unmodified kmer_main.cu + kmer_kernel.cu, nvcc "
                                   "sm_100) on one B200 -- the reference has no CPU path",
-                "cpu_baseline": cpu,
+                "cpu_baseline": cpu, "kernels_only": kernels_only,
                 "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     else:
         v = cpu["value"] if cpu else None
