@@ -57,10 +57,11 @@ def test_repeats_and_all_same(k, key_bytes):
     check(data, start, length, k, key_bytes)
 
 
-@pytest.mark.parametrize("k,key_bytes", [(12, 4), (16, 4), (12, 8), (17, 8), (18, 8), (21, 8), (31, 8)])
+@pytest.mark.parametrize("k,key_bytes", [(3, 4), (5, 8), (12, 4), (16, 4), (12, 8), (17, 8), (18, 8), (21, 8), (31, 8)])
 def test_window_count_boundaries_and_long_reads(k, key_bytes):
     """reads around the 128/256/512-window network sizes and long reads (bucket path; uint64 keys:
-    k=12,17 rows are all narrow (32-bit suffixes), k=18 mixes narrow and wide rows, k>=21 wide)"""
+    k=12,17 rows are all narrow (32-bit suffixes), k=18 mixes narrow and wide rows, k>=21 wide; k=3,5: fewer
+    key bits than bucket bits, every bucket oversized -> radix-sort fallback)"""
     import random
     rng = random.Random(k)
     lens = [k - 1, k, k + 1, 127 + k, 128 + k, 255 + k, 256 + k, 257 + k, 511 + k, 512 + k - 1, 512 + k, 513 + k,
