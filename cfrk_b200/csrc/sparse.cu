@@ -7,14 +7,20 @@
 //            row_begin[r] = sum_{j<r} max(0, len_j - k + 1) (every window distinct: worst case), so
 //            rows are written independently; callers compact if they want tight CSR.
 //   short reads (<= 512 windows): ONE WARP per read.  The read is encoded once into a per-warp
-//            bit stream in shared memory (2-bit codes + validity), every lane extracts E windows
-//            with funnel shifts, the 32*E keys are sorted by a bitonic network that lives entirely
-//            in registers (blocked layout: strides < E are register swaps, the others shfl.xor) and
-//            run-length encoded with two warp scans.  Hand-written, no library.
-//   long reads: key generation kernel -> hand-written segmented LSD radix sort (8-bit digits, one
-//            warp per 2048-key tile, stable ranks from match.any, per-row offsets from ONE flat
-//            uint32 scan used modulo 2^32) -> per-row run-length encode.  cub::DeviceScan is the
-//            only library call (plumbing).
+//            bit stream in shared memory (2-bit codes + validity); every lane pulls the bases and
+//            validity bits behind its E consecutive windows into registers and forms each window
+//            with two funnel shifts (stream_device.cuh); the 32*E keys are sorted by a bitonic
+//            network that lives entirely in registers (blocked layout: strides < E are register
+//            min/max, the others shfl.xor + compare-xor-select) and run-length encoded with two
+//            warp scans (all-distinct reads skip them).
+//   long reads: MSD bucket partition over the bases (counting pass with slab-private shared-memory
+//            counters, scatter pass with one L2 cursor per bucket), one warp sort + RLE per bucket
+//            with the same register network, compaction of the runs into the row; 32-bit suffixes
+//            for rows whose key bits below the bucket digit fit 32 bits; segmented LSD radix sort
+//            (8-bit digits, one warp per 2048-key tile, stable ranks from match.any) for buckets
+//            above 512 keys.  Details at "long reads" below.
+//   Everything is hand-written; cub::DeviceScan (exclusive sums of offsets) is the only library
+//   call (plumbing).
 #include "kernels.h"
 #include "kmer_device.cuh"
 #include "stream_device.cuh"
