@@ -198,6 +198,32 @@ def cpu_baseline(args, ks, L, budget_s):
                       f"{dt:.1f} s)"}
 
 
+def bind_to_gpu_numa_node(torch, local):
+    """Run this rank on the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned buffer is
+    allocated (first touch puts the pages there): the e2e leg moves gigabytes of rows per step over
+    PCIe into host memory, and a rank whose buffers sit on the other socket pays the inter-socket
+    link as well.  Returns the node, or None when the topology is not visible (containers)."""
+    if os.environ.get("CFRK_BENCH_NO_NUMA"):
+        return None
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bus = f"{getattr(p, 'pci_domain_id', 0):04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -211,6 +237,7 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the CUDA path has no fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_node = bind_to_gpu_numa_node(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -398,7 +425,8 @@ def run_ours(args):
                                f"counts, sweep k={ks}, {args.mode} semantics, {args.fmt} bases resident in HBM, rows to a "
                                f"{ring.numel() * 4 / 2**30:.1f} GiB HBM ring",
                    "l2_policy": "inputs (1.5 GB) and outputs (>= 10 GB per k) larger than L2 (126 MB); no flush needed",
-                   "reads_per_gpu": nS, "read_len": L, "k": ks, "parallelism": f"read-range shards x{world}"},
+                   "reads_per_gpu": nS, "read_len": L, "k": ks, "parallelism": f"read-range shards x{world}",
+                   "host_numa_node_rank0": numa_node},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
         "clocks": clocks, "per_k": per_k, "chunk_resident": chunk_resident,
     }
@@ -438,6 +466,7 @@ def run_reference(args):
         km.restype = None
         lib.ref_free_host.argtypes = [C.c_void_p]
         torch.cuda.set_device(0)
+        bind_to_gpu_numa_node(torch, 0)
         hb, hs, hl = make_reads_host(cn, L, 1000, "codes")
         hb_t = torch.from_numpy(hb).pin_memory(); hs_t = torch.from_numpy(hs).pin_memory()
         hl_t = torch.from_numpy(hl).pin_memory()
