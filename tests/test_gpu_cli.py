@@ -6,6 +6,7 @@ import os
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 
 import fixtures as fx
@@ -173,3 +174,36 @@ def test_wrapped_equals_single_line_in_exact_mode(tmp_path):
         run_cfrk(one, a, k, 4, 8192, "--all-rows", "--exact")
         run_cfrk(wrapped, b, k, 4, 8192, "--all-rows", "--exact")
         assert a.read_bytes() == b.read_bytes()
+
+
+@pytest.mark.parametrize("k", [16, 21])
+def test_genome_like_wrapped_fasta_sparse(tmp_path, k):
+    """config C4 through the command line: a few long sequences, wrapped at 70 columns, N runs inside,
+    --exact --sparse: the long-row path (bucket partition + warp sorts) behind the GPU-side unwrap"""
+    import random
+    rng = random.Random(40 + k)
+    seqs = []
+    for L in (200_000, 1, 150_000, 3_000, 260_000):
+        s = [rng.choice("ACGT") for _ in range(L)]
+        for _ in range(L // 50_000):
+            p = rng.randrange(0, L - 200)
+            s[p:p + 100] = "N" * 100
+        seqs.append("".join(s))
+    seqs[0] = seqs[0][:100_000] + seqs[0][20_000:120_000]          # a 100 kbp repeat: counts > 1
+    text = "".join(f">chr{i} len={len(s)}\n" + "\n".join(s[j:j + 70] for j in range(0, len(s), 70)) + "\n"
+                   for i, s in enumerate(seqs))
+    fa = tmp_path / "genome.fa"
+    fa.write_text(text)
+    out = tmp_path / "out.cfrk"
+    run_cfrk(fa, out, k, 4, 8192, "--all-rows", "--sparse", "--exact")
+    data, start, length = ob.parse_fasta(text=text, unwrap=True)
+    rp, keys, cnt = ob.count_sparse(data, start, length, k)
+    lines = out.read_bytes().split(b"\n")
+    assert len(lines) == len(start)
+    for i, line in enumerate(lines):
+        toks = line.split()
+        assert len(toks) == rp[i + 1] - rp[i], f"row {i}"
+        got_k = np.array([int(t.split(b":")[0]) for t in toks], dtype=np.uint64)
+        got_c = np.array([int(t.split(b":")[1]) for t in toks], dtype=np.uint32)
+        np.testing.assert_array_equal(got_k, keys[rp[i]:rp[i + 1]], err_msg=f"row {i}")
+        np.testing.assert_array_equal(got_c, cnt[rp[i]:rp[i + 1]], err_msg=f"row {i}")
