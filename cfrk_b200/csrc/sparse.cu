@@ -96,12 +96,13 @@ __device__ __forceinline__ KeyT keep_minmax(KeyT mine, KeyT other, bool upper)
 // with the usual strides, and every comparator leaves the minimum at the lower index.  In-lane
 // comparators are then pure min/max on compile-time registers; cross-lane ones need one per-lane
 // predicate per stage.
-template <typename KeyT, int E>
+// MAXSIZE < 32*E sorts every aligned block of MAXSIZE slots on its own (the grouped path below).
+template <typename KeyT, int E, int MAXSIZE = 32 * E>
 __device__ __forceinline__ void bitonic_sort_blocked(KeyT (&key)[E])
 {
     const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int size = 2; size <= 32 * E; size <<= 1) {
+    for (int size = 2; size <= MAXSIZE; size <<= 1) {
         // mirrored step
         if (size <= E) {
 #pragma unroll
@@ -148,33 +149,40 @@ __device__ __forceinline__ void bitonic_sort_blocked(KeyT (&key)[E])
     }
 }
 
-// keys sorted ascending in blocked layout, the first nvalid of them real -> (key, count) pairs
-template <typename KeyT, int E>
-__device__ __forceinline__ int warp_rle_store(const KeyT (&key)[E], int nvalid, KeyT* __restrict__ keys_out,
-                                              uint32_t* __restrict__ counts_out, KeyT* __restrict__ stage_k,
-                                              uint32_t* __restrict__ stage_c)
+// Sorted keys in blocked layout -> (key, count) pairs.  The lane's E slots are consecutive in the
+// sorted sequence of REAL keys: slot e is real iff bit e of `live` (a low-bit mask), and then it is
+// element number vpos0 + e of that sequence; nvalid = its length.  first0: the lane's slot 0 starts
+// a sorted group, so it is a head whatever the key before it (plain case: lane 0 only).
+template <typename KeyT, int E, bool BLOCKED = false>
+__device__ __forceinline__ int warp_rle_store(const KeyT (&key)[E], uint32_t live, int vpos0, bool first0, int nvalid,
+                                              KeyT* __restrict__ keys_out, uint32_t* __restrict__ counts_out,
+                                              KeyT* __restrict__ stage_k, uint32_t* __restrict__ stage_c)
 {
     const int lane = threadIdx.x & 31;
     KeyT prev = __shfl_up_sync(0xffffffffu, key[E - 1], 1);
     uint32_t heads = 0;
 #pragma unroll
     for (int e = 0; e < E; e++) {
-        const int g = lane * E + e;
-        const bool head = g < nvalid && (g == 0 || key[e] != prev);
+        const bool head = (live >> e & 1u) && ((e == 0 && first0) || key[e] != prev);
         heads |= head ? (1u << e) : 0u;
         prev = key[e];
     }
-    // common case: every key is distinct -> element g goes to slot g with count 1
-    const int nlive = min(E, max(0, nvalid - lane * E));
-    if (__all_sync(0xffffffffu, heads == (1u << nlive) - 1u)) {
-        constexpr int V = 16 / (int)sizeof(KeyT);   // keys per 16-byte shared-memory store
-        static_assert(E % V == 0, "blocked keys are staged with 16-byte stores");
+    // common case: every key is distinct -> element v goes to slot v with count 1
+    if (__all_sync(0xffffffffu, heads == live)) {
+        if (BLOCKED) {   // vpos0 == lane * E: the lane's slots are one aligned block, pads included
+            constexpr int V = 16 / (int)sizeof(KeyT);   // keys per 16-byte shared-memory store
+            static_assert(E % V == 0, "blocked keys are staged with 16-byte stores");
 #pragma unroll
-        for (int q = 0; q < E / V; q++) {
-            if (sizeof(KeyT) == 4)
-                reinterpret_cast<uint4*>(stage_k + lane * E)[q] = make_uint4((uint32_t)key[4 * q], (uint32_t)key[4 * q + 1], (uint32_t)key[4 * q + 2], (uint32_t)key[4 * q + 3]);
-            else
-                reinterpret_cast<ulonglong2*>(stage_k + lane * E)[q] = make_ulonglong2((unsigned long long)key[2 * q], (unsigned long long)key[2 * q + 1]);
+            for (int q = 0; q < E / V; q++) {
+                if (sizeof(KeyT) == 4)
+                    reinterpret_cast<uint4*>(stage_k + lane * E)[q] = make_uint4((uint32_t)key[4 * q], (uint32_t)key[4 * q + 1], (uint32_t)key[4 * q + 2], (uint32_t)key[4 * q + 3]);
+                else
+                    reinterpret_cast<ulonglong2*>(stage_k + lane * E)[q] = make_ulonglong2((unsigned long long)key[2 * q], (unsigned long long)key[2 * q + 1]);
+            }
+        } else {
+#pragma unroll
+            for (int e = 0; e < E; e++)
+                if (live >> e & 1u) stage_k[vpos0 + e] = key[e];
         }
         __syncwarp();
         for (int i = lane; i < nvalid; i += 32) {
@@ -194,8 +202,8 @@ __device__ __forceinline__ int warp_rle_store(const KeyT (&key)[E], int nvalid, 
     }
     int off = inc - hc;
     const int total = __shfl_sync(0xffffffffu, inc, 31);
-    // position of the next head after this lane: suffix-min of each lane's first head
-    int first = heads ? lane * E + (__ffs(heads) - 1) : nvalid;
+    // sequence position of the next head after this lane: suffix-min of each lane's first head
+    int first = heads ? vpos0 + (__ffs(heads) - 1) : nvalid;
     int nxt = __shfl_down_sync(0xffffffffu, first, 1);
     if (lane == 31) nxt = nvalid;
 #pragma unroll
@@ -208,9 +216,8 @@ __device__ __forceinline__ int warp_rle_store(const KeyT (&key)[E], int nvalid, 
     uint32_t cnt[E];
 #pragma unroll
     for (int e = E - 1; e >= 0; e--) {
-        const int g = lane * E + e;
-        cnt[e] = (uint32_t)(nxt - g);
-        if (heads & (1u << e)) nxt = g;
+        cnt[e] = (uint32_t)(nxt - (vpos0 + e));
+        if (heads & (1u << e)) nxt = vpos0 + e;
     }
     // stage the pairs in shared memory, then write the row with coalesced stores
 #pragma unroll
@@ -230,14 +237,99 @@ __device__ __forceinline__ int warp_rle_store(const KeyT (&key)[E], int nvalid, 
     return total;
 }
 
+// plain case: the first nvalid slots of the warp are the real keys
 template <typename KeyT, int E>
-__device__ __forceinline__ int warp_count_read(const WarpStream& st, int a, int k,
+__device__ __forceinline__ int warp_rle_store(const KeyT (&key)[E], int nvalid, KeyT* __restrict__ keys_out,
+                                              uint32_t* __restrict__ counts_out, KeyT* __restrict__ stage_k,
+                                              uint32_t* __restrict__ stage_c)
+{
+    const int lane = threadIdx.x & 31;
+    const int nlive = min(E, max(0, nvalid - lane * E));
+    return warp_rle_store<KeyT, E, true>(key, (1u << nlive) - 1u, lane * E, lane == 0, nvalid, keys_out, counts_out, stage_k, stage_c);
+}
+
+// One read, E keys per lane: extract, sort, run-length encode.
+//
+// GROUPED (E = 8, 64-bit keys, reads of <= 160 windows, k >= 2): the keys are first split by their top 3 bits
+// into 8 groups of <= 32 slots (4 lanes each) through shared memory (ranks from match.any), and
+// every group is sorted on its own: a 32-slot network has 3 cross-lane stages instead of the 15 of
+// the 256-slot one.  Groups are disjoint key ranges in ascending
+// order, so the concatenation is sorted.  A group that overflows (low-complexity reads) sends the
+// read through the full network instead.
+constexpr int kGroupSlots = 32;
+constexpr int kGroupedMaxWindows = 160;   // mean <= 20 keys per group on random reads: overflow is rare
+
+template <typename KeyT, int E>
+__device__ __forceinline__ int warp_count_read(const WarpStream& st, int a, int k, bool grouped,
                                                KeyT* __restrict__ keys_out, uint32_t* __restrict__ counts_out,
-                                               KeyT* __restrict__ stage_k, uint32_t* __restrict__ stage_c)
+                                               KeyT* __restrict__ stage_k, uint32_t* __restrict__ stage_c,
+                                               uint32_t* __restrict__ gcount)
 {
     const int lane = threadIdx.x & 31;
     KeyT key[E];
-    int nvalid = __popc(extract_windows<KeyT, E>(st, a + lane * E, k, key));
+    const uint32_t valid = extract_windows<KeyT, E>(st, a + lane * E, k, key);
+    if (E == 8 && grouped) {
+        // pad every group, clear the group counters
+        constexpr int V = 16 / (int)sizeof(KeyT);
+#pragma unroll
+        for (int q = 0; q < E / V; q++) {
+            if (sizeof(KeyT) == 4)
+                reinterpret_cast<uint4*>(stage_k + lane * E)[q] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
+            else
+                reinterpret_cast<ulonglong2*>(stage_k + lane * E)[q] = make_ulonglong2(~0ull, ~0ull);
+        }
+        if (lane < 8) gcount[lane] = 0u;
+        __syncwarp();
+        const int gshift = 2 * k - 3;
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const bool live = valid >> e & 1u;
+            const uint32_t d = live ? (uint32_t)(key[e] >> gshift) : 8u + (uint32_t)lane;   // dead slots match nobody
+            const uint32_t peers = __match_any_sync(0xffffffffu, d);
+            const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+            uint32_t base = 0;
+            if (live) {
+                base = gcount[d];
+                if (base + rank < kGroupSlots) stage_k[d * kGroupSlots + base + rank] = key[e];
+            }
+            __syncwarp();   // every lane has read its group counter
+            if (live && rank == 0) gcount[d] = base + __popc(peers);
+            __syncwarp();
+        }
+        const uint32_t gc = gcount[lane & 7];
+        if (!__any_sync(0xffffffffu, gc > kGroupSlots)) {
+            // group sizes -> start of every group in the sorted sequence (scan over lanes 0..7)
+            uint32_t inc = lane < 8 ? gc : 0u;
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            const int g = lane >> 2;
+            const int ng = (int)__shfl_sync(0xffffffffu, gc, g);
+            const int gstart = (int)__shfl_sync(0xffffffffu, inc, g) - ng;
+            const int nvalid = (int)__shfl_sync(0xffffffffu, inc, 7);
+#pragma unroll
+            for (int q = 0; q < E / V; q++) {
+                if (sizeof(KeyT) == 4) {
+                    const uint4 v = reinterpret_cast<const uint4*>(stage_k + lane * E)[q];
+                    key[4 * q] = (KeyT)v.x; key[4 * q + 1] = (KeyT)v.y; key[4 * q + 2] = (KeyT)v.z; key[4 * q + 3] = (KeyT)v.w;
+                } else {
+                    const ulonglong2 v = reinterpret_cast<const ulonglong2*>(stage_k + lane * E)[q];
+                    key[2 * q] = (KeyT)v.x; key[2 * q + 1] = (KeyT)v.y;
+                }
+            }
+            __syncwarp();   // the staging buffer is free again
+            bitonic_sort_blocked<KeyT, E, kGroupSlots>(key);
+            const int sig0 = (lane & 3) * E;                 // the lane's first slot inside its group
+            const int nlive = min(E, max(0, ng - sig0));
+            return warp_rle_store<KeyT, E>(key, (1u << nlive) - 1u, gstart + sig0, (lane & 3) == 0, nvalid, keys_out, counts_out,
+                                           stage_k, stage_c);
+        }
+        __syncwarp();
+        // overflow: the full network on the keys as extracted
+    }
+    int nvalid = __popc(valid);
 #pragma unroll
     for (int d = 16; d >= 1; d >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, d);
     bitonic_sort_blocked<KeyT, E>(key);
@@ -253,13 +345,14 @@ template <typename KeyT, int FMT, int E>
 __global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) sparse_short_kernel(
     const uint8_t* __restrict__ bases, const int64_t* __restrict__ start, const int32_t* __restrict__ length,
     int64_t nS, int k, const int64_t* __restrict__ row_begin, int32_t* __restrict__ row_count,
-    KeyT* __restrict__ keys, uint32_t* __restrict__ counts)
+    KeyT* __restrict__ keys, uint32_t* __restrict__ counts, bool group_split)
 {
     constexpr int WARPS = SparseCta<E>::WARPS;
     __shared__ uint32_t s_cw[WARPS][kStreamBlocks];
     __shared__ __align__(4) uint16_t s_vh[WARPS][2 * ((kStreamBlocks + 1) / 2) + 2];
     __shared__ __align__(16) KeyT s_stage_k[WARPS][32 * E];
     __shared__ uint32_t s_stage_c[WARPS][32 * E];
+    __shared__ uint32_t s_gcount[WARPS][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpStream st{s_cw[warp], s_vh[warp]};
     const int64_t nwarps = (int64_t)gridDim.x * WARPS;
@@ -284,7 +377,10 @@ __global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) sparse_short_kernel(
         __syncwarp();
         KeyT* ko = keys + row_begin[r];
         uint32_t* co = counts + row_begin[r];
-        const int nd = warp_count_read<KeyT, E>(st, a, k, ko, co, s_stage_k[warp], s_stage_c[warp]);
+        // measured (10 M x 150 bp): uint64 keys k=20 49.5 -> 63.5 Gbases/s; uint32 keys k=12 100.6 -> 90.0 (the
+        // split costs more than the cheaper network saves): grouped for 64-bit keys only
+        const bool grouped = E == 8 && sizeof(KeyT) == 8 && group_split && nwin <= kGroupedMaxWindows && k >= 2;
+        const int nd = warp_count_read<KeyT, E>(st, a, k, grouped, ko, co, s_stage_k[warp], s_stage_c[warp], s_gcount[warp]);
         if (lane == 0) row_count[r] = nd;
     }
 }
@@ -946,9 +1042,11 @@ static cudaError_t sparse_impl(const void* bases, const int64_t* start, const in
         // which classes occur is not known on the host without a pass over the lengths: launch all
         // three; a class without reads costs one pass over length[] (4 B/read)
         const uint8_t* b8 = static_cast<const uint8_t*>(bases);
-        sparse_short_kernel<KeyT, FMT, 4><<<grid, SparseCta<4>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts);
-        sparse_short_kernel<KeyT, FMT, 8><<<grid, SparseCta<8>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts);
-        sparse_short_kernel<KeyT, FMT, 16><<<grid, SparseCta<16>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts);
+        const char* gev = getenv("CFRK_SPARSE_GROUPS");          // 0: always the full network (A/B measurements)
+        const bool group_split = !(gev && atoi(gev) == 0);
+        sparse_short_kernel<KeyT, FMT, 4><<<grid, SparseCta<4>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts, group_split);
+        sparse_short_kernel<KeyT, FMT, 8><<<grid, SparseCta<8>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts, group_split);
+        sparse_short_kernel<KeyT, FMT, 16><<<grid, SparseCta<16>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts, group_split);
         count_launch(); count_launch(); count_launch();
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }

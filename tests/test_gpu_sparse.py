@@ -98,6 +98,25 @@ def test_long_rows_in_many_batches(k, key_bytes, batch, monkeypatch):
     check(data, start, length, k, key_bytes)
 
 
+@pytest.mark.parametrize("k,key_bytes,L", [(12, 4, 150), (12, 8, 150), (9, 8, 168), (20, 8, 150), (2, 8, 150)])
+def test_grouped_network_with_biased_reads(k, key_bytes, L):
+    """reads of <= 160 windows with 64-bit keys take the grouped network (8 groups by the top 3 key bits); base composition
+    skewed towards A fills group 0 beyond its 32 slots in part of the reads -> those take the full network:
+    both paths, mixed in one launch, against the oracle"""
+    rng = np.random.default_rng(k * 7 + L)
+    nS = 6000
+    p_a = rng.choice([0.25, 0.4, 0.55, 0.8], size=nS)
+    data = np.full(nS * (L + 1), -1, dtype=np.int8)
+    u = rng.random((nS, L))
+    rest = (1 - p_a[:, None]) / 3
+    codes = np.where(u < p_a[:, None], 0, 1 + np.minimum(2, ((u - p_a[:, None]) / rest).astype(np.int64))).astype(np.int8)
+    codes[rng.random((nS, L)) < 0.002] = -1
+    data.reshape(nS, L + 1)[:, :L] = codes
+    start = np.arange(nS, dtype=np.int64) * (L + 1)
+    length = np.full(nS, L, dtype=np.int32)
+    check(data, start, length, k, key_bytes)
+
+
 def test_ascii_input_and_150bp_batch():
     nS, L, k = 20000, 150, 12
     data, start, length = fx.synthetic_codes(nS, L, seed=12, n_frac=0.001)
