@@ -250,65 +250,63 @@ __device__ __forceinline__ int warp_rle_store(const KeyT (&key)[E], int nvalid, 
 
 // One read, E keys per lane: extract, sort, run-length encode.
 //
-// GROUPED (E = 8, 64-bit keys, reads of <= 160 windows, k >= 2): the keys are first split by their top 3 bits
-// into 8 groups of <= 32 slots (4 lanes each) through shared memory (ranks from match.any), and
-// every group is sorted on its own: a 32-slot network has 3 cross-lane stages instead of the 15 of
-// the 256-slot one.  Groups are disjoint key ranges in ascending
-// order, so the concatenation is sorted.  A group that overflows (low-complexity reads) sends the
-// read through the full network instead.
+// GROUPED (E = 8, reads of <= 160 windows, k >= 2): the keys are first split by their top 3 bits into
+// 8 groups of <= 32 slots (4 lanes each) through shared memory, ranks from a warp scan of byte-packed
+// per-lane group counts (no shared counters, no match.any), and every group is sorted on its own: a
+// 32-slot network has 3 cross-lane stages instead of the 15 of the 256-slot one.  Groups are disjoint
+// key ranges in ascending order, so the concatenation is sorted.  A group that overflows
+// (low-complexity reads) sends the read through the full network instead.
 constexpr int kGroupSlots = 32;
 constexpr int kGroupedMaxWindows = 160;   // mean <= 20 keys per group on random reads: overflow is rare
 
 template <typename KeyT, int E>
 __device__ __forceinline__ int warp_count_read(const WarpStream& st, int a, int k, bool grouped,
                                                KeyT* __restrict__ keys_out, uint32_t* __restrict__ counts_out,
-                                               KeyT* __restrict__ stage_k, uint32_t* __restrict__ stage_c,
-                                               uint32_t* __restrict__ gcount)
+                                               KeyT* __restrict__ stage_k, uint32_t* __restrict__ stage_c)
 {
     const int lane = threadIdx.x & 31;
     KeyT key[E];
     const uint32_t valid = extract_windows<KeyT, E>(st, a + lane * E, k, key);
     if (E == 8 && grouped) {
-        // pad every group, clear the group counters
+        // Split without shared counters: every lane packs its keys-per-group into 8 bytes of a 64-bit
+        // word; a warp scan of that word gives, byte by byte, the keys of each group in the lanes
+        // before it; the rank of a key = that + the lane's own earlier keys of the group.  (At most
+        // 160 keys in all, so no byte overflows.)
         constexpr int V = 16 / (int)sizeof(KeyT);
-#pragma unroll
-        for (int q = 0; q < E / V; q++) {
-            if (sizeof(KeyT) == 4)
-                reinterpret_cast<uint4*>(stage_k + lane * E)[q] = make_uint4(0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu);
-            else
-                reinterpret_cast<ulonglong2*>(stage_k + lane * E)[q] = make_ulonglong2(~0ull, ~0ull);
-        }
-        if (lane < 8) gcount[lane] = 0u;
-        __syncwarp();
         const int gshift = 2 * k - 3;
+        uint64_t h = 0;
+        uint32_t lrank = 0;   // 4 bits per slot: keys of the same group in earlier slots of this lane
 #pragma unroll
         for (int e = 0; e < E; e++) {
-            const bool live = valid >> e & 1u;
-            const uint32_t d = live ? (uint32_t)(key[e] >> gshift) : 8u + (uint32_t)lane;   // dead slots match nobody
-            const uint32_t peers = __match_any_sync(0xffffffffu, d);
-            const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
-            uint32_t base = 0;
-            if (live) {
-                base = gcount[d];
-                if (base + rank < kGroupSlots) stage_k[d * kGroupSlots + base + rank] = key[e];
+            if (valid >> e & 1u) {
+                const uint32_t sh = (uint32_t)(key[e] >> gshift) * 8u;
+                lrank |= ((uint32_t)(h >> sh) & 0xFu) << (4 * e);
+                h += 1ull << sh;
             }
-            __syncwarp();   // every lane has read its group counter
-            if (live && rank == 0) gcount[d] = base + __popc(peers);
-            __syncwarp();
         }
-        const uint32_t gc = gcount[lane & 7];
-        if (!__any_sync(0xffffffffu, gc > kGroupSlots)) {
-            // group sizes -> start of every group in the sorted sequence (scan over lanes 0..7)
-            uint32_t inc = lane < 8 ? gc : 0u;
+        uint64_t inc = h;
 #pragma unroll
-            for (int d = 1; d < 8; d <<= 1) {
-                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
-                if (lane >= d) inc += o;
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint64_t o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        const uint64_t excl = inc - h;
+        const uint64_t totals = __shfl_sync(0xffffffffu, inc, 31);
+        // a group above 32 keys (byte + 95 >= 128): the full network below
+        if (((totals + 0x5F5F5F5F5F5F5F5Full) & 0x8080808080808080ull) == 0) {
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                if (valid >> e & 1u) {
+                    const uint32_t d = (uint32_t)(key[e] >> gshift);
+                    const uint32_t slot = ((uint32_t)(excl >> (8 * d)) & 0xFFu) + ((lrank >> (4 * e)) & 0xFu);
+                    stage_k[d * kGroupSlots + slot] = key[e];
+                }
             }
+            __syncwarp();
             const int g = lane >> 2;
-            const int ng = (int)__shfl_sync(0xffffffffu, gc, g);
-            const int gstart = (int)__shfl_sync(0xffffffffu, inc, g) - ng;
-            const int nvalid = (int)__shfl_sync(0xffffffffu, inc, 7);
+            const int ng = (int)((totals >> (8 * g)) & 0xFFu);
+            const int gstart = (int)(((totals * 0x0101010101010100ull) >> (8 * g)) & 0xFFu);   // keys of the groups before g
+            const int nvalid = (int)((totals * 0x0101010101010101ull) >> 56);
 #pragma unroll
             for (int q = 0; q < E / V; q++) {
                 if (sizeof(KeyT) == 4) {
@@ -319,14 +317,16 @@ __device__ __forceinline__ int warp_count_read(const WarpStream& st, int a, int 
                     key[2 * q] = (KeyT)v.x; key[2 * q + 1] = (KeyT)v.y;
                 }
             }
-            __syncwarp();   // the staging buffer is free again
-            bitonic_sort_blocked<KeyT, E, kGroupSlots>(key);
             const int sig0 = (lane & 3) * E;                 // the lane's first slot inside its group
             const int nlive = min(E, max(0, ng - sig0));
+#pragma unroll
+            for (int e = 0; e < E; e++)
+                if (e >= nlive) key[e] = KeyMax<KeyT>::value;   // slots behind the group's keys hold leftovers: pad
+            __syncwarp();   // the staging buffer is free again
+            bitonic_sort_blocked<KeyT, E, kGroupSlots>(key);
             return warp_rle_store<KeyT, E>(key, (1u << nlive) - 1u, gstart + sig0, (lane & 3) == 0, nvalid, keys_out, counts_out,
                                            stage_k, stage_c);
         }
-        __syncwarp();
         // overflow: the full network on the keys as extracted
     }
     int nvalid = __popc(valid);
@@ -352,7 +352,6 @@ __global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) sparse_short_kernel(
     __shared__ __align__(4) uint16_t s_vh[WARPS][2 * ((kStreamBlocks + 1) / 2) + 2];
     __shared__ __align__(16) KeyT s_stage_k[WARPS][32 * E];
     __shared__ uint32_t s_stage_c[WARPS][32 * E];
-    __shared__ uint32_t s_gcount[WARPS][8];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     WarpStream st{s_cw[warp], s_vh[warp]};
     const int64_t nwarps = (int64_t)gridDim.x * WARPS;
@@ -377,10 +376,9 @@ __global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) sparse_short_kernel(
         __syncwarp();
         KeyT* ko = keys + row_begin[r];
         uint32_t* co = counts + row_begin[r];
-        // measured (10 M x 150 bp): uint64 keys k=20 49.5 -> 63.5 Gbases/s; uint32 keys k=12 100.6 -> 90.0 (the
-        // split costs more than the cheaper network saves): grouped for 64-bit keys only
-        const bool grouped = E == 8 && sizeof(KeyT) == 8 && group_split && nwin <= kGroupedMaxWindows && k >= 2;
-        const int nd = warp_count_read<KeyT, E>(st, a, k, grouped, ko, co, s_stage_k[warp], s_stage_c[warp], s_gcount[warp]);
+        // measured (10 M x 150 bp): uint32 keys k=12 100.1 -> 107.8 Gbases/s, uint64 keys k=20 49.4 -> 68.0
+        const bool grouped = E == 8 && group_split && nwin <= kGroupedMaxWindows && k >= 2;
+        const int nd = warp_count_read<KeyT, E>(st, a, k, grouped, ko, co, s_stage_k[warp], s_stage_c[warp]);
         if (lane == 0) row_count[r] = nd;
     }
 }
