@@ -387,7 +387,7 @@ __global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) sparse_short_kernel(
 // long reads (> 512 windows): MSD partition + one warp sort per bucket
 //
 //   A row of n windows is split by the top B bits of its keys into 2^B buckets (B chosen per row so
-//   that uniform keys give <= 256 per bucket).  Two passes over the BASES do the split (keys are
+//   that uniform keys give <= 192 per bucket).  Two passes over the BASES do the split (keys are
 //   never stored unsorted more than once): pass 1 counts the buckets, pass 2 scatters the keys
 //   behind the scanned counts.  Every bucket of <= 512 keys is then sorted by ONE WARP with the
 //   same register network as the short reads and run-length encoded in place; buckets are disjoint
@@ -395,7 +395,9 @@ __global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) sparse_short_kernel(
 //   (scan of the distinct counts + copy).  Buckets above 512 keys (skewed or low-complexity rows)
 //   take the segmented LSD radix sort below.  Rows are processed in batches of <= 128 Mi windows,
 //   which bounds the scratch to 12 bytes per window of one batch.
-constexpr int kBucketTarget = 256;       // mean keys per bucket at most this (uniform keys)
+constexpr int kBucketTarget = 192;       // mean keys per bucket at most this (uniform keys): with 256 the buckets of a
+                                         // row whose mean lands just below 256 straddle the 256-slot network size and
+                                         // half of them pay for the 512-slot one
 constexpr int kBucketCap = 512;          // what one warp sorts in registers (E = 16)
 constexpr int kMaxBucketBits = 22;
 constexpr int kPartTile = 4096;          // windows per tile: the unit in which partition work is cut
