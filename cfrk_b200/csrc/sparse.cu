@@ -259,27 +259,27 @@ __device__ __forceinline__ int warp_rle_store(const KeyT (&key)[E], int nvalid, 
 constexpr int kGroupSlots = 32;
 constexpr int kGroupedMaxWindows = 160;   // mean <= 20 keys per group on random reads: overflow is rare
 
+// key[]: E keys per lane in any order, bit e of `valid` set for the real ones (the others hold the
+// maximum key).  gshift >= 0 (E = 8, at most 160 real keys): grouped, the group of a key is bits
+// gshift..gshift+2.  Returns the number of pairs written to keys_out / counts_out.
 template <typename KeyT, int E>
-__device__ __forceinline__ int warp_count_read(const WarpStream& st, int a, int k, bool grouped,
-                                               KeyT* __restrict__ keys_out, uint32_t* __restrict__ counts_out,
-                                               KeyT* __restrict__ stage_k, uint32_t* __restrict__ stage_c)
+__device__ __forceinline__ int warp_sort_rle(KeyT (&key)[E], uint32_t valid, int gshift,
+                                             KeyT* __restrict__ keys_out, uint32_t* __restrict__ counts_out,
+                                             KeyT* __restrict__ stage_k, uint32_t* __restrict__ stage_c)
 {
     const int lane = threadIdx.x & 31;
-    KeyT key[E];
-    const uint32_t valid = extract_windows<KeyT, E>(st, a + lane * E, k, key);
-    if (E == 8 && grouped) {
+    if (E == 8 && gshift >= 0) {
         // Split without shared counters: every lane packs its keys-per-group into 8 bytes of a 64-bit
         // word; a warp scan of that word gives, byte by byte, the keys of each group in the lanes
         // before it; the rank of a key = that + the lane's own earlier keys of the group.  (At most
         // 160 keys in all, so no byte overflows.)
         constexpr int V = 16 / (int)sizeof(KeyT);
-        const int gshift = 2 * k - 3;
         uint64_t h = 0;
         uint32_t lrank = 0;   // 4 bits per slot: keys of the same group in earlier slots of this lane
 #pragma unroll
         for (int e = 0; e < E; e++) {
             if (valid >> e & 1u) {
-                const uint32_t sh = (uint32_t)(key[e] >> gshift) * 8u;
+                const uint32_t sh = ((uint32_t)(key[e] >> gshift) & 7u) * 8u;
                 lrank |= ((uint32_t)(h >> sh) & 0xFu) << (4 * e);
                 h += 1ull << sh;
             }
@@ -297,7 +297,7 @@ __device__ __forceinline__ int warp_count_read(const WarpStream& st, int a, int 
 #pragma unroll
             for (int e = 0; e < E; e++) {
                 if (valid >> e & 1u) {
-                    const uint32_t d = (uint32_t)(key[e] >> gshift);
+                    const uint32_t d = (uint32_t)(key[e] >> gshift) & 7u;
                     const uint32_t slot = ((uint32_t)(excl >> (8 * d)) & 0xFFu) + ((lrank >> (4 * e)) & 0xFu);
                     stage_k[d * kGroupSlots + slot] = key[e];
                 }
@@ -334,6 +334,17 @@ __device__ __forceinline__ int warp_count_read(const WarpStream& st, int a, int 
     for (int d = 16; d >= 1; d >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, d);
     bitonic_sort_blocked<KeyT, E>(key);
     return warp_rle_store<KeyT, E>(key, nvalid, keys_out, counts_out, stage_k, stage_c);
+}
+
+template <typename KeyT, int E>
+__device__ __forceinline__ int warp_count_read(const WarpStream& st, int a, int k, bool grouped,
+                                               KeyT* __restrict__ keys_out, uint32_t* __restrict__ counts_out,
+                                               KeyT* __restrict__ stage_k, uint32_t* __restrict__ stage_c)
+{
+    const int lane = threadIdx.x & 31;
+    KeyT key[E];
+    const uint32_t valid = extract_windows<KeyT, E>(st, a + lane * E, k, key);
+    return warp_sort_rle<KeyT, E>(key, valid, grouped ? 2 * k - 3 : -1, keys_out, counts_out, stage_k, stage_c);
 }
 
 // E = keys per lane: the kernel handles the reads whose window count falls in its class
@@ -418,16 +429,166 @@ __host__ __device__ __forceinline__ int bucket_bits(int64_t nwin, int k)
 // scratch traffic and a 32-bit sorting network).
 __host__ __device__ __forceinline__ bool narrow_row(int64_t nwin, int k) { return 2 * k - bucket_bits(nwin, k) <= 32; }
 
-// long rows, listed from both ends of long_rows[cap]: narrow rows from the front, wide ones from the back
-__global__ void collect_long_kernel(const int32_t* __restrict__ length, int64_t nS, int k, bool split,
-                                    int64_t* __restrict__ long_rows, unsigned long long* __restrict__ n_long, int64_t cap)
+// ------------------------------------------------------------------------------------------
+// medium rows (513..4096 windows): ONE CTA per row, everything in shared memory.
+//   The row's bases are encoded into a CTA-wide stream, every thread extracts 16 consecutive windows,
+//   the keys are split by their top 3..5 bits into groups of <= 128 keys on average (ranks from
+//   shared atomics, tight packing after a scan of the group counts), every group is sorted and
+//   run-length encoded by one warp with the short-read machinery (including its 3-bit sub-groups), the
+//   pairs stay in shared memory until the distinct counts of all groups are known and then leave with
+//   coalesced stores.  HBM traffic = the bases in, the pairs out; no scratch, no global atomics.
+//   A row with a group above 256 keys (skew) is appended to the long-row lists instead.
+constexpr int kMedMaxWindows = 4096;
+constexpr int kMedThreads = 256;
+constexpr int kMedW = kMedMaxWindows / kMedThreads;      // 16 consecutive windows per thread
+constexpr int kMedBlocks = (15 + kMedMaxWindows + 30 + 15) / 16 + 3;
+constexpr int kMedGroupMean = 128;     // keys per group at most, on average
+constexpr int kMedMaxGroups = kMedMaxWindows / kMedGroupMean;   // 32
+
+__host__ __device__ __forceinline__ int medium_group_bits(int nwin)
+{
+    int b = 0;
+    while ((kMedGroupMean << b) < nwin) b++;
+    return b;
+}
+__host__ __device__ __forceinline__ bool medium_row(int64_t nwin, int k)
+{
+    return nwin > kShortMaxWindows && nwin <= kMedMaxWindows && 2 * k >= medium_group_bits((int)nwin);
+}
+
+// rows above 512 windows: medium rows into medium_rows[]; long rows into long_rows[cap] from both ends
+// (narrow rows from the front, wide ones from the back).  n[0] narrow, n[1] wide, n[2] medium.
+__global__ void collect_long_kernel(const int32_t* __restrict__ length, int64_t nS, int k, bool split, bool use_medium,
+                                    int64_t* __restrict__ long_rows, int64_t* __restrict__ medium_rows,
+                                    unsigned long long* __restrict__ n, int64_t cap)
 {
     for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < nS; r += (int64_t)gridDim.x * blockDim.x) {
         const int64_t nwin = (int64_t)length[r] - k + 1;
         if (nwin > kShortMaxWindows) {
-            const bool wide = split && !narrow_row(nwin, k);
-            const unsigned long long slot = atomicAdd(n_long + (wide ? 1 : 0), 1ull);
-            if ((int64_t)slot < cap) long_rows[wide ? cap - 1 - (int64_t)slot : (int64_t)slot] = r;
+            if (use_medium && medium_row(nwin, k)) {
+                const unsigned long long slot = atomicAdd(n + 2, 1ull);
+                if ((int64_t)slot < cap) medium_rows[slot] = r;
+            } else {
+                const bool wide = split && !narrow_row(nwin, k);
+                const unsigned long long slot = atomicAdd(n + (wide ? 1 : 0), 1ull);
+                if ((int64_t)slot < cap) long_rows[wide ? cap - 1 - (int64_t)slot : (int64_t)slot] = r;
+            }
+        }
+    }
+}
+
+template <typename KeyT, int FMT>
+__global__ void __launch_bounds__(kMedThreads) sparse_medium_kernel(
+    const uint8_t* __restrict__ bases, const int64_t* __restrict__ start, const int32_t* __restrict__ length, int k,
+    const int64_t* __restrict__ medium_rows, int64_t n_medium, const int64_t* __restrict__ row_begin,
+    int32_t* __restrict__ row_count, KeyT* __restrict__ keys, uint32_t* __restrict__ counts, bool split,
+    int64_t* __restrict__ long_rows, unsigned long long* __restrict__ n_long, int64_t cap)
+{
+    constexpr int T = kMedThreads, W = kMedW, WARPS = T / 32;
+    extern __shared__ __align__(16) unsigned char smem[];
+    KeyT* s_keys = reinterpret_cast<KeyT*>(smem);                                   // [4096] keys by group, then pairs
+    KeyT* s_stage_k = s_keys + kMedMaxWindows;                                      // [WARPS][256]
+    uint32_t* s_oc = reinterpret_cast<uint32_t*>(s_stage_k + WARPS * 256);          // [4096] counts of the pairs
+    uint32_t* s_stage_c = s_oc + kMedMaxWindows;                                    // [WARPS][256]
+    __shared__ uint32_t s_cw[kMedBlocks];
+    __shared__ __align__(4) uint16_t s_vh[2 * ((kMedBlocks + 1) / 2) + 2];
+    __shared__ uint32_t s_gcnt[kMedMaxGroups], s_gstart[kMedMaxGroups + 1], s_gdist[kMedMaxGroups], s_gdst[kMedMaxGroups + 1];
+    __shared__ int s_overflow;
+    WarpStream st{s_cw, s_vh};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t j = blockIdx.x; j < n_medium; j += gridDim.x) {
+        const int64_t r = medium_rows[j];
+        const int64_t s = start[r];
+        const int len = length[r];
+        const int nwin = len - k + 1;
+        const int gbits = medium_group_bits(nwin), ngroups = 1 << gbits;
+        const int a = (int)(s & 15);
+        const int nblocks = (a + len + 15) >> 4;
+        __syncthreads();   // the previous row is out of shared memory
+        for (int b = threadIdx.x; b < kMedBlocks; b += T) {
+            uint32_t c = 0, v = 0;
+            if (b < nblocks) {
+                encode16<FMT>(ld_block(bases + ((s >> 4) + b) * 16), c, v);
+                v &= from_pos(max(0, a - 16 * b)) & ~from_pos(min(16, max(0, a + len - 16 * b)));
+            }
+            st.cw[b] = c;
+            st.vh[b ^ 1] = (uint16_t)v;
+        }
+        if (threadIdx.x < kMedMaxGroups) s_gcnt[threadIdx.x] = 0u;
+        __syncthreads();
+        // 1. keys and their rank inside their group
+        KeyT key[W];
+        uint32_t rank[W];
+        const uint32_t valid = extract_windows<KeyT, W>(st, a + (int)threadIdx.x * W, k, key);
+        const int gsh = 2 * k - gbits;
+#pragma unroll
+        for (int e = 0; e < W; e++) {
+            rank[e] = 0;
+            if (valid >> e & 1u) rank[e] = atomicAdd(&s_gcnt[(uint32_t)(key[e] >> gsh)], 1u);
+        }
+        __syncthreads();
+        // 2. group starts; a group above 256 keys does not fit a warp's network
+        if (warp == 0) {
+            const uint32_t c = lane < ngroups ? s_gcnt[lane] : 0u;
+            uint32_t inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            s_gstart[lane] = inc - c;
+            const bool ovf = __any_sync(0xffffffffu, c > 256u);
+            if (lane == 0) s_overflow = ovf ? 1 : 0;
+        }
+        __syncthreads();
+        if (s_overflow) {   // skewed row: the long-row path takes it
+            if (threadIdx.x == 0) {
+                const bool wide = split && !narrow_row(nwin, k);
+                const unsigned long long slot = atomicAdd(n_long + (wide ? 1 : 0), 1ull);
+                if ((int64_t)slot < cap) long_rows[wide ? cap - 1 - (int64_t)slot : (int64_t)slot] = r;
+            }
+            continue;
+        }
+#pragma unroll
+        for (int e = 0; e < W; e++)
+            if (valid >> e & 1u) s_keys[s_gstart[(uint32_t)(key[e] >> gsh)] + rank[e]] = key[e];
+        __syncthreads();
+        // 3. one warp per group: sort + RLE, pairs back to the group's place in shared memory
+        for (int g = warp; g < ngroups; g += WARPS) {
+            const int ng = (int)s_gcnt[g];
+            const int g0 = (int)s_gstart[g];
+            KeyT gk[8];
+            const int nlive = min(8, max(0, ng - lane * 8));
+#pragma unroll
+            for (int e = 0; e < 8; e++) gk[e] = e < nlive ? s_keys[g0 + lane * 8 + e] : KeyMax<KeyT>::value;
+            __syncwarp();
+            const int sub = gsh - 3;     // sub-groups by the 3 bits below the group digit
+            const int nd = warp_sort_rle<KeyT, 8>(gk, (1u << nlive) - 1u, ng <= kGroupedMaxWindows && sub >= 0 ? sub : -1,
+                                                  s_keys + g0, s_oc + g0, s_stage_k + warp * 256, s_stage_c + warp * 256);
+            if (lane == 0) s_gdist[g] = (uint32_t)nd;
+        }
+        __syncthreads();
+        // 4. distinct counts -> place of every group's pairs in the row
+        if (warp == 0) {
+            const uint32_t c = lane < ngroups ? s_gdist[lane] : 0u;
+            uint32_t inc = c;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            s_gdst[lane] = inc - c;
+            if (lane == 31) { s_gdst[32] = inc; row_count[r] = (int32_t)inc; }
+        }
+        __syncthreads();
+        KeyT* ko = keys + row_begin[r];
+        uint32_t* co = counts + row_begin[r];
+        for (int g = warp; g < ngroups; g += WARPS) {
+            const int nd = (int)s_gdist[g], g0 = (int)s_gstart[g], d0 = (int)s_gdst[g];
+            for (int i = lane; i < nd; i += 32) {
+                ko[d0 + i] = s_keys[g0 + i];
+                co[d0 + i] = s_oc[g0 + i];
+            }
         }
     }
 }
@@ -1052,27 +1213,45 @@ static cudaError_t sparse_impl(const void* bases, const int64_t* start, const in
     }
 
     tr.mark("short reads");
-    // 3. long reads: narrow rows (32-bit suffixes) listed from the front, wide ones from the back
-    int64_t* long_rows = nullptr;
-    unsigned long long* d_nlong = nullptr;
-    const int64_t cap_long = total / kShortMaxWindows + 1;   // a long row has > 512 windows
+    // 3. rows above 512 windows: medium rows (one CTA per row, shared memory only), then the long rows --
+    // narrow ones (32-bit suffixes) listed from the front, wide ones from the back -- including the
+    // medium rows that turned out to be skewed
+    int64_t *long_rows = nullptr, *medium_rows = nullptr;
+    unsigned long long* d_n = nullptr;
+    const int64_t cap_long = total / kShortMaxWindows + 1;   // such a row has > 512 windows
+    const char* mev = getenv("CFRK_SPARSE_MEDIUM");          // 0: medium rows take the long-row path (A/B measurements)
+    const bool use_medium = !(mev && atoi(mev) == 0);
     if ((e = cudaMallocAsync(reinterpret_cast<void**>(&long_rows), (size_t)cap_long * 8, st)) != cudaSuccess) return e;
-    if ((e = cudaMallocAsync(reinterpret_cast<void**>(&d_nlong), 16, st)) != cudaSuccess) return e;
-    cudaMemsetAsync(d_nlong, 0, 16, st);
-    collect_long_kernel<<<num_sms * 4, 256, 0, st>>>(length, nS, k, sizeof(KeyT) == 8, long_rows, d_nlong, cap_long);
+    if ((e = cudaMallocAsync(reinterpret_cast<void**>(&medium_rows), (size_t)cap_long * 8, st)) != cudaSuccess) return e;
+    if ((e = cudaMallocAsync(reinterpret_cast<void**>(&d_n), 24, st)) != cudaSuccess) return e;
+    cudaMemsetAsync(d_n, 0, 24, st);
+    collect_long_kernel<<<num_sms * 4, 256, 0, st>>>(length, nS, k, sizeof(KeyT) == 8, use_medium, long_rows, medium_rows, d_n, cap_long);
     count_launch();
-    unsigned long long n_long[2] = {0, 0};
-    cudaMemcpyAsync(n_long, d_nlong, 16, cudaMemcpyDeviceToHost, st);
+    unsigned long long n_rows[3] = {0, 0, 0};
+    cudaMemcpyAsync(n_rows, d_n, 24, cudaMemcpyDeviceToHost, st);
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
     const uint8_t* b8 = static_cast<const uint8_t*>(bases);
-    if (n_long[0] > 0)
+    if (n_rows[2] > 0) {
+        const size_t dyn = (size_t)(kMedMaxWindows + (kMedThreads / 32) * 256) * (sizeof(KeyT) + 4);
+        auto kern = sparse_medium_kernel<KeyT, FMT>;
+        if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess) return e;
+        const int64_t nm = (int64_t)n_rows[2];
+        kern<<<(unsigned)std::min<int64_t>(nm, (int64_t)num_sms * 3), kMedThreads, dyn, st>>>(
+            b8, start, length, k, medium_rows, nm, row_begin, row_count, keys, counts, sizeof(KeyT) == 8, long_rows, d_n, cap_long);
+        count_launch();
+        cudaMemcpyAsync(n_rows, d_n, 16, cudaMemcpyDeviceToHost, st);   // skewed medium rows joined the long lists
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+        tr.mark("medium rows");
+    }
+    if (n_rows[0] > 0)
         e = sparse_long_rows<KeyT, uint32_t, FMT>(b8, start, length, k, row_begin, row_count, keys, counts, long_rows,
-                                                  (int64_t)n_long[0], num_sms, tr, st);
-    if (e == cudaSuccess && n_long[1] > 0)
+                                                  (int64_t)n_rows[0], num_sms, tr, st);
+    if (e == cudaSuccess && n_rows[1] > 0)
         e = sparse_long_rows<KeyT, KeyT, FMT>(b8, start, length, k, row_begin, row_count, keys, counts,
-                                              long_rows + (cap_long - (int64_t)n_long[1]), (int64_t)n_long[1], num_sms, tr, st);
+                                              long_rows + (cap_long - (int64_t)n_rows[1]), (int64_t)n_rows[1], num_sms, tr, st);
     cudaFreeAsync(long_rows, st);
-    cudaFreeAsync(d_nlong, st);
+    cudaFreeAsync(medium_rows, st);
+    cudaFreeAsync(d_n, st);
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 

@@ -51,7 +51,8 @@ def test_short_reads(k, key_bytes):
 @pytest.mark.parametrize("k,key_bytes", [(12, 4), (31, 8)])
 def test_repeats_and_all_same(k, key_bytes):
     """low-complexity reads: few distinct k-mers with large counts, incl. the all-T read (max key)"""
-    reads = ["T" * 150, "A" * 150, "AC" * 75, "ACGT" * 60, "T" * 40 + "N" + "T" * 60, "G" * 600, "TTTTTTTTTTTTTTTTTTTTTTTTTTTTTTT"]
+    reads = ["T" * 150, "A" * 150, "AC" * 75, "ACGT" * 60, "T" * 40 + "N" + "T" * 60, "G" * 600, "TTTTTTTTTTTTTTTTTTTTTTTTTTTTTTT",
+             "C" * 2000, "ACGT" * 700, "T" * 4000 + "N" + "ACG" * 30]      # medium rows whose groups overflow -> long-row path
     text = "".join(f">r{i}\n{r}\n" for i, r in enumerate(reads))
     data, start, length = ob.parse_fasta(text=text)
     check(data, start, length, k, key_bytes)
