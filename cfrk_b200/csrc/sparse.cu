@@ -478,7 +478,7 @@ __global__ void collect_long_kernel(const int32_t* __restrict__ length, int64_t 
 }
 
 template <typename KeyT, int FMT>
-__global__ void __launch_bounds__(kMedThreads) sparse_medium_kernel(
+__global__ void __launch_bounds__(kMedThreads, sizeof(KeyT) == 8 ? 3 : 4) sparse_medium_kernel(
     const uint8_t* __restrict__ bases, const int64_t* __restrict__ start, const int32_t* __restrict__ length, int k,
     const int64_t* __restrict__ medium_rows, int64_t n_medium, const int64_t* __restrict__ row_begin,
     int32_t* __restrict__ row_count, KeyT* __restrict__ keys, uint32_t* __restrict__ counts, bool split,
@@ -1236,7 +1236,7 @@ static cudaError_t sparse_impl(const void* bases, const int64_t* start, const in
         auto kern = sparse_medium_kernel<KeyT, FMT>;
         if ((e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess) return e;
         const int64_t nm = (int64_t)n_rows[2];
-        kern<<<(unsigned)std::min<int64_t>(nm, (int64_t)num_sms * 3), kMedThreads, dyn, st>>>(
+        kern<<<(unsigned)std::min<int64_t>(nm, (int64_t)num_sms * (sizeof(KeyT) == 8 ? 3 : 4)), kMedThreads, dyn, st>>>(
             b8, start, length, k, medium_rows, nm, row_begin, row_count, keys, counts, sizeof(KeyT) == 8, long_rows, d_n, cap_long);
         count_launch();
         cudaMemcpyAsync(n_rows, d_n, 16, cudaMemcpyDeviceToHost, st);   // skewed medium rows joined the long lists
