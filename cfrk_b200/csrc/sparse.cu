@@ -13,6 +13,8 @@
 //            network that lives entirely in registers (blocked layout: strides < E are register
 //            min/max, the others shfl.xor + compare-xor-select) and run-length encoded with two
 //            warp scans (all-distinct reads skip them).
+//   medium reads (513..4096 windows): ONE CTA per read, keys grouped, sorted by warps and run-length
+//            encoded entirely in shared memory (details at "medium rows" below).
 //   long reads: MSD bucket partition over the bases (counting pass with slab-private shared-memory
 //            counters, scatter pass with one L2 cursor per bucket), one warp sort + RLE per bucket
 //            with the same register network, compaction of the runs into the row; 32-bit suffixes
