@@ -761,7 +761,9 @@ __global__ void __launch_bounds__(T, SCATTER ? (ILP > 1 ? 4 : 5) : 1) partition_
 template <typename KeyT, int E>
 __global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) bucket_sort_kernel(
     const unsigned long long* __restrict__ bend, int64_t nb, KeyT* __restrict__ scratch, uint32_t* __restrict__ pc,
-    unsigned long long* __restrict__ distinct, int64_t* __restrict__ fb_list, unsigned long long* __restrict__ n_fb)
+    unsigned long long* __restrict__ distinct, int64_t* __restrict__ fb_list, unsigned long long* __restrict__ n_fb,
+    const int64_t* __restrict__ boff, int64_t j0, int64_t j1, const int64_t* __restrict__ long_rows,
+    const int32_t* __restrict__ length, int k)
 {
     constexpr int WARPS = SparseCta<E>::WARPS;
     __shared__ __align__(16) KeyT s_stage_k[WARPS][32 * E];
@@ -774,13 +776,23 @@ __global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) bucket_sort_kernel(
         if (n64 == 0 || n64 > 32 * E || (E > 4 && n64 <= 16 * E)) continue;
         const int n = (int)n64;
         KeyT key[E];
+        uint32_t valid = 0;
 #pragma unroll
         for (int e = 0; e < E; e++) {      // any placement will do: the network sorts it
             const int g = e * 32 + lane;
             key[e] = g < n ? scratch[beg + g] : KeyMax<KeyT>::value;
+            valid |= g < n ? 1u << e : 0u;
         }
-        bitonic_sort_blocked<KeyT, E>(key);
-        const int nd = warp_rle_store<KeyT, E>(key, n, scratch + beg, pc + beg, s_stage_k[warp], s_stage_c[warp]);
+        // 64-bit keys, buckets of <= 160 keys: sub-groups by the 3 key bits below the bucket digit (the row's
+        // shift).  Measured on 5 Mbp rows: k=31 (uint64 sort keys) 24.6-25.5 -> 26.1 Gbases/s; with 32-bit sort
+        // keys the split and the row lookup cost more than the smaller networks save (sort phase 1.70 -> 1.87 ms)
+        int gshift = -1;
+        if (E == 8 && sizeof(KeyT) == 8 && n <= kGroupedMaxWindows) {
+            const int64_t j = locate(boff, j0, j1, boff[j0] + b);
+            gshift = 2 * k - bucket_bits((int64_t)length[long_rows[j]] - k + 1, k) - 3;
+        }
+        __syncwarp();   // every lane has its keys: the bucket's place is rewritten below
+        const int nd = warp_sort_rle<KeyT, E>(key, valid, gshift, scratch + beg, pc + beg, s_stage_k[warp], s_stage_c[warp]);
         if (lane == 0) distinct[b] = (unsigned long long)nd;
     }
 }
@@ -1104,9 +1116,9 @@ static cudaError_t sparse_long_rows(const uint8_t* bases, const int64_t* start, 
         {
             const unsigned g4 = (unsigned)std::min<int64_t>((nb + SparseCta<4>::WARPS - 1) / SparseCta<4>::WARPS, (int64_t)num_sms * 8);
             const unsigned g16 = (unsigned)std::min<int64_t>((nb + SparseCta<16>::WARPS - 1) / SparseCta<16>::WARPS, (int64_t)num_sms * 8);
-            bucket_sort_kernel<SortT, 4><<<g4, SparseCta<4>::WARPS * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb);
-            bucket_sort_kernel<SortT, 8><<<g4, SparseCta<8>::WARPS * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb);
-            bucket_sort_kernel<SortT, 16><<<g16, SparseCta<16>::WARPS * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb);
+            bucket_sort_kernel<SortT, 4><<<g4, SparseCta<4>::WARPS * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb, boff, j0, j1, long_rows, length, k);
+            bucket_sort_kernel<SortT, 8><<<g4, SparseCta<8>::WARPS * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb, boff, j0, j1, long_rows, length, k);
+            bucket_sort_kernel<SortT, 16><<<g16, SparseCta<16>::WARPS * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb, boff, j0, j1, long_rows, length, k);
             count_launch(); count_launch(); count_launch();
         }
         unsigned long long nfb = 0;
