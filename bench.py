@@ -19,6 +19,16 @@ sharding, no data-path collective): weak scaling.
                 measured HBM copy bandwidth in MEASURED_PEAKS.json.
   cpu_baseline  the oracle's multithreaded CPU counter on the host cores (bounded sample).
 
+  configs       (outside the headline's timed region, each with its own CUDA events and an ON-GPU
+                CHECK in the same run): dense k = 1..3; C2 variant B (0.1 % N bases, seed 43: the
+                data-dependent spill path); C3 = 100 M x 150 bp sparse per-read rows, k = 12, the
+                read set SPLIT over the ranks (strong scaling); C4 = 1000 x 5 Mbp sparse rows,
+                k = 16 / 21 / 31, split over the ranks; C5 = 1 Gbase whole-dataset histogram,
+                k = 12, split over the ranks + NCCL all-reduce (count_ms / allreduce_ms).
+  checks        dense, every k of the run, over ALL 10 M rows: column sums of the rows ==
+                whole-dataset histogram of the visited windows + the spill total (computed from
+                the lengths), and a read prefix bit-exact against the CPU oracle.
+
 --impl reference runs the reference's own kmer_main (unmodified kmer_main.cu + kmer_kernel.cu
 built by oracle/Makefile into oracle/_ref/libcfrk_ref_gpu.so) through the same host-buffer
 contract on the same chunk; the reference is GPU-only, so this is its GPU path on the same
@@ -60,6 +70,13 @@ def parse_args():
                     help="packed: every step encodes the ASCII bases once (2-bit + validity) and counts every k from that")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="headline only: skip k=1..3, C2-B, C3, C4, C5")
+    ap.add_argument("--no-checks", action="store_true", help="skip the on-GPU checks of the dense rows")
+    ap.add_argument("--configs", default="small_k,c2b,c3,c4,c5", help="which extra configs to measure")
+    ap.add_argument("--c3-reads", type=int, default=100_000_000, help="C3: total reads over all ranks")
+    ap.add_argument("--c4-seqs", type=int, default=1000, help="C4: total sequences over all ranks")
+    ap.add_argument("--c4-len", type=int, default=5_000_000)
+    ap.add_argument("--c5-reads", type=int, default=6_666_667, help="C5: total reads over all ranks")
     return ap.parse_args()
 
 
@@ -198,6 +215,220 @@ def cpu_baseline(args, ks, L, budget_s):
                       f"{dt:.1f} s)"}
 
 
+# ------------------------------------------------------------------------------------------
+# On-GPU checks and the extra configs (every north-star config measured AND verified in
+# the driver's run).  `ob` (the oracle binding) is used here as the CHECKER only.
+def _oracle():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as ob
+    return ob
+
+
+def timed(torch, fn, warmup, reps):
+    """mean ms of fn() over `reps` calls after `warmup`, CUDA events on the current stream"""
+    for _ in range(warmup):
+        fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+
+def dense_check(torch, cf, flat, start, length, nN, nS, k, mode, ascii_fmt, ring, plan, launch, stream, prefix_reads):
+    """Over ALL rows of one k: column sums of the rows == histogram of the visited windows + the
+    spill total; and rows [0, P) bit-exact against the CPU oracle.
+    compat (src/kmer_kernel.cu:83-88): read i visits starts t < vis_i = min(len_i - 1, 1024); a visited
+    window is counted in its own row if its k bases are valid and inside the read, else it adds 1 to
+    the LAST bin of row i-1 (lost for i = 0).  So with tend_i = min(len_i, vis_i + k - 1):
+        colsum = hist(reads cut to tend_i)  +  e_last * sum_{i >= 1} (vis_i - valid_i)."""
+    bins = 4 ** k
+    len64 = length.to(torch.int64)
+    compat = mode == cf.MODE_COMPAT
+    if compat:
+        vis = torch.clamp(len64 - 1, min=0, max=1024)
+        tend = torch.where(vis > 0, torch.minimum(len64, vis + (k - 1)), torch.zeros_like(vis)).to(torch.int32)
+    else:
+        vis = None
+        tend = length
+    fmt = cf.FMT_ASCII if ascii_fmt else cf.FMT_CODES
+    hist = torch.zeros(bins, dtype=torch.int32, device=flat.device)
+    cf.global_hist_device(flat.data_ptr(), start.data_ptr(), tend.data_ptr(), nN, nS, k, hist.data_ptr(), fmt=fmt, stream=stream)
+    col = torch.zeros(bins, dtype=torch.int64, device=flat.device)
+    for a, b in plan:
+        launch(k, a, b)
+        col += ring[: (b - a) * bins].view(b - a, bins).sum(dim=0, dtype=torch.int64)
+    expect = hist.to(torch.int64)
+    spill = 0
+    if compat:
+        h0 = torch.zeros(bins, dtype=torch.int32, device=flat.device)
+        cf.global_hist_device(flat.data_ptr(), start.data_ptr(), tend.data_ptr(), nN, 1, k, h0.data_ptr(), fmt=fmt, stream=stream)
+        spill = int(vis[1:].sum()) - (int(expect.sum()) - int(h0.sum(dtype=torch.int64)))
+        expect[bins - 1] += spill
+    colsum_ok = bool(torch.equal(col, expect))
+    # prefix against the oracle (one kmer_main call: read 0 drops its spill, row P-1 takes read P's)
+    ob = _oracle()
+    P = int(min(prefix_reads, nS - 1, max(1, (1 << 30) // (bins * 4))))
+    launch(k, 0, P)
+    got = ring[: P * bins].view(P, bins).cpu().numpy()
+    nbytes = int(start[P + 1].item()) if P + 1 < nS else nN
+    hdata = flat[:nbytes].cpu().numpy()
+    want = ob.count_dense_fast(hdata.view("int8"), start[: P + 1].cpu().numpy(), length[: P + 1].cpu().numpy(), k,
+                               ob.MODE_COMPAT if compat else ob.MODE_EXACT, ascii=ascii_fmt)
+    prefix_ok = bool((got == want[:P]).all())
+    return {"k": k, "rows": int(nS), "colsum_eq_hist_plus_spill": colsum_ok, "spill_total": int(spill),
+            "windows_counted": int(col.sum()), "oracle_prefix_reads": P, "oracle_prefix_ok": prefix_ok}
+
+
+def valid_windows_per_read(torch, flat, nS, L, k, lo, hi):
+    """reads [lo, hi) of a uniform-length ASCII batch: number of windows without a non-ACGT byte"""
+    v = flat[lo * (L + 1): hi * (L + 1)].view(hi - lo, L + 1)[:, :L]
+    bad = ~((v == 65) | (v == 67) | (v == 71) | (v == 84))
+    csum = torch.cumsum(torch.nn.functional.pad(bad.to(torch.int32), (1, 0)), dim=1)
+    return ((csum[:, k:] - csum[:, :-k]) == 0).sum(dim=1)
+
+
+def sparse_rows_check(torch, flat, nS, L, k, key_bytes, rc, keys, cnt, lo, hi):
+    """rows [lo, hi) of a sparse result over uniform-length reads: counts sum to the valid windows of
+    the read, counts >= 1, keys strictly increasing and < 4^k"""
+    nwin = L - k + 1
+    valid = valid_windows_per_read(torch, flat, nS, L, k, lo, hi)
+    rc64 = rc[lo:hi].to(torch.int64)
+    K = keys[lo * nwin: hi * nwin].view(hi - lo, nwin)
+    Cn = cnt[lo * nwin: hi * nwin].view(hi - lo, nwin)
+    live = torch.arange(nwin, device=flat.device).unsqueeze(0) < rc64.unsqueeze(1)
+    ok = bool(torch.equal((Cn * live).sum(dim=1, dtype=torch.int64), valid))
+    ok = ok and bool((Cn[live] >= 1).all())
+    Kl = (K.to(torch.int64) & 0xFFFFFFFF) if key_bytes == 4 else K
+    ok = ok and bool(((Kl[:, 1:] > Kl[:, :-1]) | ~live[:, 1:]).all())
+    if bool(live.any()):
+        ok = ok and int(Kl[live].max()) < 4 ** k and int(Kl[live].min()) >= 0
+    return ok, int(valid.sum()), int(rc64.sum())
+
+
+def sparse_oracle_check(torch, flat, start, length, k, key_bytes, rb, rc, keys, cnt, nrows):
+    """rows [0, nrows) against the CPU oracle's sorted distinct k-mers and counts"""
+    ob = _oracle()
+    end = int(start[nrows - 1].item()) + int(length[nrows - 1].item()) + 1
+    h = flat[:end].cpu().numpy().view("int8")
+    orp, okeys, ocnt = ob.count_sparse(h, start[:nrows].cpu().numpy(), length[:nrows].cpu().numpy(), k, ascii=True)
+    hrb, hrc = rb[: nrows + 1].cpu().numpy(), rc[:nrows].cpu().numpy()
+    upto = int(hrb[nrows])
+    hk = keys[:upto].cpu().numpy().view("uint32" if key_bytes == 4 else "uint64").astype("uint64")
+    hc = cnt[:upto].cpu().numpy().view("uint32")
+    for r in range(nrows):
+        n = int(hrc[r])
+        if n != orp[r + 1] - orp[r]:
+            return False
+        a = int(hrb[r])
+        if not (np.array_equal(hk[a: a + n], okeys[orp[r]: orp[r + 1]]) and np.array_equal(hc[a: a + n], ocnt[orp[r]: orp[r + 1]])):
+            return False
+    return True
+
+
+def make_genome_like(torch, nseq, L, seed, device):
+    """C4: each sequence = 0.8 L uniform bases + 10 copies of a 0.02 L unit (so counts > 1
+    exist), '\n' separated, ASCII"""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    lut = torch.tensor([65, 67, 71, 84], dtype=torch.uint8, device=device)
+    unit = L // 50
+    body = L - 10 * unit
+    flat = torch.empty(nseq * (L + 1) + 16, dtype=torch.uint8, device=device)
+    flat[-16:] = 0
+    view = flat[: nseq * (L + 1)].view(nseq, L + 1)
+    for i in range(nseq):
+        view[i, :body] = lut[torch.randint(0, 4, (body,), dtype=torch.uint8, device=device, generator=g).long()]
+        u = lut[torch.randint(0, 4, (unit,), dtype=torch.uint8, device=device, generator=g).long()]
+        view[i, body:L] = u.repeat(10)
+    view[:, L] = 10
+    start = torch.arange(nseq, dtype=torch.int64, device=device) * (L + 1)
+    length = torch.full((nseq,), L, dtype=torch.int32, device=device)
+    return flat, start, length
+
+
+def split_even(total, world, rank):
+    return total // world + (1 if rank < total % world else 0)
+
+
+def run_sparse_config(torch, dist, cf, dev, rank, world, peak, name, flat, start, length, nS_local, L, k, key_bytes,
+                      batch_rows, total_units_all_ranks, warmup, reps, oracle_rows, check_rows):
+    """One sparse per-read config over this rank's rows in batches of `batch_rows` (the outputs of a
+    batch are reused by the next: rows do not stay).  Strong scaling: the read set is split over
+    the ranks, value = all bases / max-over-ranks time."""
+    stream = torch.cuda.current_stream().cuda_stream
+    nwin = L - k + 1
+    cap = batch_rows * nwin
+    rb = torch.zeros(batch_rows + 1, dtype=torch.int64, device=dev)
+    rc = torch.zeros(batch_rows, dtype=torch.int32, device=dev)
+    keys = torch.zeros(cap, dtype=torch.int32 if key_bytes == 4 else torch.int64, device=dev)
+    cnt = torch.zeros(cap, dtype=torch.int32, device=dev)
+    batches = [(a, min(nS_local, a + batch_rows)) for a in range(0, nS_local, batch_rows)]
+    distinct = [0]
+
+    def one_batch(a, b):
+        n = b - a
+        off = a * (L + 1)
+        # start[] of the batch is relative to the batch's first byte (16-byte aligned: (L+1)*a is not
+        # in general, so the batch keeps the GLOBAL buffer and a start[] slice instead)
+        cf.count_sparse_device(flat.data_ptr(), start[a:b].data_ptr(), length[a:b].data_ptr(), flat.numel() - 16, n, k,
+                               rb.data_ptr(), rc.data_ptr(), keys.data_ptr(), cnt.data_ptr(), cap, key_bytes=key_bytes,
+                               fmt=cf.FMT_ASCII, stream=stream)
+        return off
+
+    def one_pass():
+        for a, b in batches:
+            one_batch(a, b)
+
+    launches0 = cf.launch_count()
+    ms = timed(torch, one_pass, warmup, reps)
+    launches = (cf.launch_count() - launches0) // (warmup + reps)
+    # checks on the first batch (left in the buffers by a fresh call)
+    a, b = batches[0]
+    one_batch(a, b)
+    torch.cuda.synchronize()
+    n = b - a
+    ok_rows, nvalid, ndistinct = True, 0, 0
+    step = max(1, min(n, 1_000_000 if L <= 1000 else 8))
+    for lo in range(0, min(n, check_rows), step):
+        hi = min(n, lo + step)
+        okr, v, d = sparse_rows_check(torch, flat, nS_local, L, k, key_bytes, rc, keys, cnt, lo, hi)
+        ok_rows = ok_rows and okr
+        nvalid += v
+        ndistinct += d
+    ok_oracle = sparse_oracle_check(torch, flat, start, length, k, key_bytes, rb, rc, keys, cnt, min(oracle_rows, n))
+    # distinct pairs of the whole pass (for the algorithmic bytes): count per batch
+    total_distinct = 0
+    for a, b in batches:
+        one_batch(a, b)
+        total_distinct += int(rc[: b - a].sum(dtype=torch.int64))
+    t = torch.tensor([ms, float(total_distinct), 1.0 if (ok_rows and ok_oracle) else 0.0], dtype=torch.float64, device=dev)
+    if world > 1:
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = t.clone()
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        tn = t.clone()
+        dist.all_reduce(tn, op=dist.ReduceOp.MIN)
+        ms, total_distinct, all_ok = float(tm[0]), float(ts[1]), float(tn[2]) > 0.5
+    else:
+        all_ok = ok_rows and ok_oracle
+    del rb, rc, keys, cnt
+    bases = total_units_all_ranks * L
+    alg = total_units_all_ranks * (L + 8) + total_distinct * (key_bytes + 4)    # SURVEY 8(d)
+    return {"config": name, "k": k, "key_bytes": key_bytes, "rows_all_ranks": int(total_units_all_ranks), "row_len": L,
+            "rows_this_rank": int(nS_local), "batches_per_pass": len(batches), "ms_per_pass": round(ms, 3),
+            "gbases_s": round(bases / ms / 1e6, 2), "alg_bytes": int(alg), "alg_gb_s": round(alg / ms / 1e6, 1),
+            "frac_of_peak_per_gpu": round(alg / ms / 1e6 / peak / world, 4), "scaling": "strong",
+            "launches_per_pass": int(launches),
+            "check": {"rows_checked": int(min(n, check_rows)), "counts_sum_to_valid_windows_sorted_keys": bool(ok_rows),
+                      "oracle_rows": int(min(oracle_rows, n)), "oracle_ok": bool(ok_oracle), "all_ranks_ok": bool(all_ok),
+                      "valid_windows_checked": int(nvalid), "distinct_pairs_checked": int(ndistinct)}}
+
+
 def bind_to_gpu_numa_node(torch, local):
     """Run this rank on the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned buffer is
     allocated (first touch puts the pages there): the e2e leg moves gigabytes of rows per step over
@@ -263,20 +494,26 @@ def run_ours(args):
         per = max(rpt, (ring.numel() * 4 // row) // rpt * rpt)
         return [(a, min(nS, a + per)) for a in range(0, nS, per)]
 
-    plans = {k: plan(k) for k in ks}
+    want_cfg = set() if args.no_configs else set(x for x in args.configs.split(",") if x)
+    ks_small = [k for k in (1, 2, 3) if k not in ks] if "small_k" in want_cfg else []
+    plans = {k: plan(k) for k in ks + ks_small}
 
     def encode():
         if packed:
             cf.encode_2bit_device(flat.data_ptr(), nN, p_codes.data_ptr(), p_valid.data_ptr(), fmt=cf.FMT_ASCII, stream=stream)
 
-    def sweep_k(k):
+    def launch_rows(k, a, b, src=None):
+        fl, st_, ln = src if src is not None else (flat, start, length)
+        if packed and src is None:
+            cf.count_dense_packed_device(p_codes.data_ptr(), p_valid.data_ptr(), st_.data_ptr(), ln.data_ptr(),
+                                         nN, nS, k, ring.data_ptr(), mode=mode, read_begin=a, read_end=b, stream=stream)
+        else:
+            cf.count_dense_device(fl.data_ptr(), st_.data_ptr(), ln.data_ptr(), nN, nS, k,
+                                  ring.data_ptr(), mode=mode, fmt=fmt, read_begin=a, read_end=b, stream=stream)
+
+    def sweep_k(k, src=None):
         for a, b in plans[k]:
-            if packed:
-                cf.count_dense_packed_device(p_codes.data_ptr(), p_valid.data_ptr(), start.data_ptr(), length.data_ptr(),
-                                             nN, nS, k, ring.data_ptr(), mode=mode, read_begin=a, read_end=b, stream=stream)
-            else:
-                cf.count_dense_device(flat.data_ptr(), start.data_ptr(), length.data_ptr(), nN, nS, k,
-                                      ring.data_ptr(), mode=mode, fmt=fmt, read_begin=a, read_end=b, stream=stream)
+            launch_rows(k, a, b, src)
 
     def barrier():
         torch.cuda.synchronize()
@@ -326,13 +563,19 @@ def run_ours(args):
         wbest = min(wbest, w0.elapsed_time(w1))
     write_only_gbs = ring.numel() * 4 / wbest / 1e6
     peak, peak_src = measured_peak()
-    per_k = []
-    for k in ks:
-        ms = per_k_ms[k]
+    def per_k_entry(k, ms):
         bytes_k = nS * alg_bytes_per_read(L, k)
-        per_k.append({"k": k, "ms": round(ms, 3), "gbases_s": round(nS * L / ms / 1e6, 2),
-                      "alg_gb_s": round(bytes_k / ms / 1e6, 1), "frac_of_peak": round(bytes_k / ms / 1e6 / peak, 4),
-                      "launches": len(plans[k])})
+        return {"k": k, "ms": round(ms, 3), "gbases_s": round(nS * L / ms / 1e6, 2),
+                "alg_gb_s": round(bytes_k / ms / 1e6, 1), "frac_of_peak": round(bytes_k / ms / 1e6 / peak, 4),
+                "launches": len(plans[k])}
+
+    per_k = [per_k_entry(k, per_k_ms[k]) for k in ks]
+    # k = 1..3 (the reference's own test config is k = 2, test/test.sh:13): same reads, own events,
+    # not part of `value` (BASELINE configs[1] names k = 4..8)
+    for k in ks_small:
+        per_k.append(dict(per_k_entry(k, timed(torch, lambda: sweep_k(k), 3, 5)), in_value=False))
+    per_k.sort(key=lambda d: d["k"])
+    min_frac = min(d["frac_of_peak"] for d in per_k)
     dom = max(ks, key=lambda k: per_k_ms[k])
     dom_launches = len(plans[dom])
     dom_bytes_per_launch = nS * alg_bytes_per_read(L, dom) / dom_launches
@@ -384,11 +627,43 @@ def run_ours(args):
             t = torch.tensor([dt], device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
-        e2e = {"value": round(world * cn * L * len(ks) * steps / dt / 1e9, 4), "unit": UNIT,
+        host_v, host_ms = world * cn * L * len(ks) * steps / dt / 1e9, dt / steps * 1e3
+
+        # the same sweep through the EXPORTED REFERENCE SYMBOL kmer_main(struct read*, nN, nS, k, device)
+        # (src/kmer.cuh:6): the callee allocates rd->Freq pinned, exactly what the reference arm times;
+        # the rows go back to the library's pinned arena with cfrk_free_host (the reference arm frees
+        # with cudaFreeHost)
+        km = getattr(cf.lib(), "_Z9kmer_mainP4readllit")
+        km.argtypes = [C.POINTER(_RefRead), C.c_long, C.c_long, C.c_int, C.c_ushort]
+        km.restype = None
+
+        def km_sweep():
+            for k in ks:
+                rd = _RefRead(hb_t.data_ptr(), hl_t.data_ptr(), hs_t.data_ptr(), None, None)
+                km(C.byref(rd), hb.nbytes, cn, k, local)
+                if not rd.Freq:
+                    raise SystemExit("bench.py: kmer_main returned no rows")
+                cf.lib().cfrk_free_host(rd.Freq)
+        for _ in range(max(1, args.warmup)):
+            km_sweep()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            km_sweep()
+        torch.cuda.synchronize()
+        dtk = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dtk], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dtk = float(t.item())
+        e2e = {"value": round(world * cn * L * len(ks) * steps / dtk / 1e9, 4), "unit": UNIT,
                "h2d_bytes_per_step": int(len(ks) * (hb.nbytes + hs.nbytes + hl.nbytes)),
                "d2h_bytes_per_step": int(sum(cn * 4 ** k * 4 for k in ks)),
-               "sample": f"{cn} reads x {L} bp per k (one reference chunk), cfrk_count_dense_host, pinned host "
-                         f"buffers, codes layout", "ms_per_step": round(dt / steps * 1e3, 2)}
+               "sample": f"{cn} reads x {L} bp per k (one reference chunk) through the exported reference symbol kmer_main "
+                         f"(struct read in pinned host memory, rd->Freq allocated by the callee, returned with "
+                         f"cfrk_free_host), codes layout", "ms_per_step": round(dtk / steps * 1e3, 2),
+               "dense_host": {"value": round(host_v, 4), "ms_per_step": round(host_ms, 2),
+                              "what": "cfrk_count_dense_host with a caller-owned pinned output buffer"}}
 
     # ---- the same reference chunk resident in HBM: what sits next to the reference arm's kernels_only
     chunk_resident = None
@@ -412,6 +687,108 @@ def run_ours(args):
                           "what": f"{cn} reads x {L} bp (one reference chunk, codes layout) resident in HBM, rows left in HBM: "
                                   f"the counterpart of the reference arm's kernels_only"}
 
+    # ---- on-GPU checks of the dense rows: every k of this run, all nS rows of this rank -------------
+    checks = None
+    if not args.no_checks:
+        checks = {"dense": [], "what": "colsum over ALL rows == cfrk_global_hist_device(visited windows) + spill total "
+                                       "from the lengths; first rows bit-exact vs the CPU oracle (oracle_count_fast_mt)"}
+        for k in sorted(ks + ks_small):
+            checks["dense"].append(dense_check(torch, cf, flat, start, length, nN, nS, k, mode, args.fmt != "codes", ring,
+                                               plans[k], launch_rows, stream, 60000))
+        ok = all(c["colsum_eq_hist_plus_spill"] and c["oracle_prefix_ok"] for c in checks["dense"])
+        if world > 1:
+            t = torch.tensor([1.0 if ok else 0.0], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            ok = float(t.item()) > 0.5
+        checks["all_ok_all_ranks"] = ok
+
+    # ---- the other north-star configs ---------------------------------------------------------------
+    configs = {}
+    if "c2b" in want_cfg:
+        # C2 variant B: 0.1 % of the bases are N (seed 43): in-read invalid windows, data-dependent spill
+        fb, sb, lb = make_reads_device(torch, nS, L, 43 + rank, 0.001, "codes" if args.fmt == "codes" else "ascii", dev)
+        srcb = (fb, sb, lb)
+        entry = {"what": f"{nS} reads x {L} bp, 0.1 % N bases (seed 43+rank), same kernels, same ring", "per_k": []}
+        tot = 0.0
+        for k in ks:
+            ms = timed(torch, lambda: sweep_k(k, srcb), 1, 2)
+            tot += ms
+            entry["per_k"].append(per_k_entry(k, ms))
+        entry["gbases_s"] = round(nS * L * len(ks) / tot / 1e6, 3)
+        if not args.no_checks:
+            entry["check"] = [dense_check(torch, cf, fb, sb, lb, nN, nS, k, mode, args.fmt != "codes", ring, plans[k],
+                                          lambda kk, a, b: launch_rows(kk, a, b, srcb), stream, 60000) for k in ks]
+        configs["C2_variant_B"] = entry
+        del fb, sb, lb, srcb
+        torch.cuda.empty_cache()
+    del ring
+    if packed:
+        del p_codes, p_valid
+    torch.cuda.empty_cache()
+    if "c3" in want_cfg:
+        n3 = split_even(args.c3_reads, world, rank)
+        f3, s3, l3 = make_reads_device(torch, n3, L, 44 + rank, 0.001, "ascii", dev)
+        configs["C3_sparse_k12"] = run_sparse_config(torch, dist, cf, dev, rank, world, peak, "C3: 100 M x 150 bp, 0.1 % N, sparse "
+                                                     "per-read rows, read range split over the ranks", f3, s3, l3, n3, L, 12, 4,
+                                                     min(n3, 10_000_000), args.c3_reads, 1, 3, 20000, 2_000_000)
+        del f3, s3, l3
+        torch.cuda.empty_cache()
+    if "c4" in want_cfg:
+        n4 = split_even(args.c4_seqs, world, rank)
+        if n4 > 0:
+            f4, s4, l4 = make_genome_like(torch, n4, args.c4_len, 45 + rank, dev)
+            for k4 in (16, 21, 31):
+                configs[f"C4_sparse_k{k4}"] = run_sparse_config(
+                    torch, dist, cf, dev, rank, world, peak, "C4: 1000 x 5 Mbp (80 % uniform + 10 copies of a 2 % unit), sparse "
+                    "sort-compact rows, sequences split over the ranks", f4, s4, l4, n4, args.c4_len, k4, 4 if k4 <= 16 else 8,
+                    min(n4, 40), args.c4_seqs, 1, 2, 1, 40)
+            del f4, s4, l4
+            torch.cuda.empty_cache()
+    if "c5" in want_cfg:
+        k5 = 12
+        n5 = split_even(args.c5_reads, world, rank)
+        f5, s5, l5 = make_reads_device(torch, n5, L, 46 + rank, 0.0, "ascii", dev)
+        hist = torch.zeros(4 ** k5, dtype=torch.int32, device=dev)
+        W5, K5 = 3, 10
+        evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K5)]
+
+        def c5_step(ev=None):
+            hist.zero_()
+            if ev:
+                ev[0].record()
+            cf.global_hist_device(f5.data_ptr(), s5.data_ptr(), l5.data_ptr(), n5 * (L + 1), n5, k5, hist.data_ptr(),
+                                  fmt=cf.FMT_ASCII, stream=stream)
+            if ev:
+                ev[1].record()
+            if world > 1:
+                dist.all_reduce(hist, op=dist.ReduceOp.SUM)   # NCCL over NVLink: the path's one exchange step
+            if ev:
+                ev[2].record()
+        for _ in range(W5):
+            c5_step()
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for i in range(K5):
+            c5_step(evs[i])
+        c1.record()
+        barrier()
+        t = torch.tensor([c0.elapsed_time(c1) / K5, sum(e[0].elapsed_time(e[1]) for e in evs) / K5,
+                          sum(e[1].elapsed_time(e[2]) for e in evs) / K5], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms5, cnt5, red5 = (float(x) for x in t)
+        windows = args.c5_reads * (L - k5 + 1)
+        configs["C5_global_hist_k12"] = {
+            "config": "C5: 1 Gbase (6 666 667 x 150 bp) whole-dataset histogram, k = 12, reads split over the ranks, "
+                      "NCCL all-reduce of the 64 MiB table", "k": k5, "reads_all_ranks": args.c5_reads, "scaling": "strong",
+            "ms_per_step": round(ms5, 3), "count_ms": round(cnt5, 3), "allreduce_ms": round(red5, 3),
+            "gbases_s": round(args.c5_reads * L / ms5 / 1e6, 1), "red_global_per_s_per_gpu_G": round(windows / world / cnt5 / 1e6, 1),
+            "alg_bytes": int(args.c5_reads * (L + 8) + 4 ** k5 * 4),
+            "check": {"sum_eq_windows": int(hist.sum(dtype=torch.int64)) == windows}}
+        del f5, s5, l5, hist
+        torch.cuda.empty_cache()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -428,7 +805,8 @@ def run_ours(args):
                    "reads_per_gpu": nS, "read_len": L, "k": ks, "parallelism": f"read-range shards x{world}",
                    "host_numa_node_rank0": numa_node},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-        "clocks": clocks, "per_k": per_k, "chunk_resident": chunk_resident,
+        "clocks": clocks, "per_k": per_k, "min_frac": min_frac, "chunk_resident": chunk_resident,
+        "checks": checks, "configs": configs,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

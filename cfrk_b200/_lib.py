@@ -7,7 +7,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libcfrk_b200.so")
 
 # every symbol include/cfrk_b200.h declares (tests/test_abi.py checks header and library agree)
 SYMBOLS = [
-    "cfrk_version", "cfrk_last_error", "cfrk_device_count", "cfrk_launch_count",
+    "cfrk_version", "cfrk_last_error", "cfrk_device_count", "cfrk_launch_count", "cfrk_release", "cfrk_free_host",
     "cfrk_count_dense_host", "cfrk_count_dense_device", "cfrk_count_dense_packed_device",
     "cfrk_dense_reads_per_tile",
     "cfrk_encode_2bit_device", "cfrk_global_hist_device", "cfrk_count_sparse_device", "cfrk_scan_fasta_device",
@@ -31,6 +31,9 @@ def load():
     L.cfrk_last_error.restype = C.c_char_p
     L.cfrk_device_count.restype = i32
     L.cfrk_launch_count.restype = C.c_uint64
+    L.cfrk_release.restype = i32
+    L.cfrk_free_host.argtypes = [vp]
+    L.cfrk_free_host.restype = None
     L.cfrk_dense_reads_per_tile.argtypes = [i32]
     L.cfrk_count_dense_host.argtypes = [vp, i32, vp, vp, i64, i64, i32, i32, i32, vp]
     L.cfrk_count_dense_device.argtypes = [vp, i32, vp, vp, i64, i64, i64, i64, i32, i32, i64, i64, vp, vp]

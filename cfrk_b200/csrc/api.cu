@@ -16,7 +16,10 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <vector>
 
 namespace {
 
@@ -41,7 +44,13 @@ int fail_cuda(cudaError_t e, const char* where)
 constexpr size_t kRingSlotBytes = (size_t)256 << 20;  // rows per kernel launch of the host path
 
 // Per host thread: kmer_main is called concurrently from several pthreads in the reference
-// driver (src/main.cu:279-289), each needs its own streams and scratch.
+// driver (src/main.cu:279-289), each needs its own streams and scratch.  A context belongs to one
+// thread at a time; when the thread exits the context goes back to a process-wide idle list and
+// the next new thread takes it over, so thread churn does not grow the footprint (at most one
+// context per CONCURRENT caller).  Nothing is freed at process exit (the CUDA runtime may already
+// be gone); cfrk_release() frees the idle contexts, the calling thread's own and the pinned arena.
+// Cached per context: the bases buffer of the largest call, start/length arrays, up to
+// 2 x 256 MiB of row ring, 2 streams, 4 events.
 struct HostCtx {
     int device = -1;
     cudaStream_t compute = nullptr, copy = nullptr;
@@ -62,25 +71,52 @@ struct HostCtx {
         }
         if (compute) cudaStreamDestroy(compute);
         if (copy) cudaStreamDestroy(copy);
+        cudaGetLastError();
         *this = HostCtx();
     }
-    ~HostCtx() { /* process teardown: the CUDA context may already be gone; leak on purpose */ }
 };
-thread_local HostCtx t_ctx;
 
-int ensure_ctx(int device)
-{
-    HostCtx& c = t_ctx;
-    if (c.device == device) { CU(cudaSetDevice(device)); return CFRK_OK; }
-    c.release();
-    CU(cudaSetDevice(device));
-    CU(cudaStreamCreateWithFlags(&c.compute, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c.copy, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; i++) {
-        CU(cudaEventCreateWithFlags(&c.done[i], cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&c.drained[i], cudaEventDisableTiming));
+std::mutex g_ctx_mu;
+std::vector<HostCtx*> g_idle_ctx;   // contexts whose thread has exited
+
+struct CtxHolder {
+    HostCtx* c = nullptr;
+    ~CtxHolder()
+    {
+        if (!c) return;
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        g_idle_ctx.push_back(c);   // no CUDA call here: this runs during thread / process teardown
+        c = nullptr;
     }
-    c.device = device;
+};
+thread_local CtxHolder t_holder;
+
+int ensure_ctx(int device, HostCtx** out)
+{
+    HostCtx*& c = t_holder.c;
+    if (c && c->device == device) { CU(cudaSetDevice(device)); *out = c; return CFRK_OK; }
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        if (c) { g_idle_ctx.push_back(c); c = nullptr; }
+        for (size_t i = 0; i < g_idle_ctx.size(); i++)
+            if (g_idle_ctx[i]->device == device) {
+                c = g_idle_ctx[i];
+                g_idle_ctx.erase(g_idle_ctx.begin() + (long)i);
+                break;
+            }
+    }
+    CU(cudaSetDevice(device));
+    if (!c) {
+        c = new HostCtx();
+        CU(cudaStreamCreateWithFlags(&c->compute, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&c->copy, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            CU(cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&c->drained[i], cudaEventDisableTiming));
+        }
+        c->device = device;
+    }
+    *out = c;
     return CFRK_OK;
 }
 
@@ -108,7 +144,58 @@ int check_common(int fmt, int k, int kmax, int mode)
 
 namespace cfrk {
 void set_last_error(const std::string& msg) { t_err = msg; }
+
+// Pinned host memory for the rows kmer_main hands out (rd->Freq).  The reference pins a fresh
+// buffer per call (cudaMallocHost, src/kmer_main.cu:115: ~0.35 ms per MiB, i.e. 1 s for the 2.86 GB
+// of one k = 4..8 sweep over a chunk) and never frees it.  Here the buffers come from a process-wide
+// arena: cfrk_free_host() puts a buffer back and the next call of that size class takes it over, so
+// a caller that releases its rows pays the pinning once.  A caller that never frees (the reference
+// driver) gets exactly the reference's behaviour.
+namespace {
+std::mutex g_arena_mu;
+std::map<void*, size_t> g_arena_live;            // handed out: pointer -> capacity
+std::multimap<size_t, void*> g_arena_free;       // cached: capacity -> pointer
+constexpr size_t kArenaGrain = (size_t)2 << 20;
 }
+
+void* pinned_alloc(size_t bytes)
+{
+    const size_t cap = (std::max<size_t>(bytes, 1) + kArenaGrain - 1) / kArenaGrain * kArenaGrain;
+    {
+        std::lock_guard<std::mutex> lk(g_arena_mu);
+        auto it = g_arena_free.lower_bound(cap);
+        if (it != g_arena_free.end() && it->first <= cap + cap / 4) {   // close fit only: no 2.6 GB block for a 8 MB row set
+            void* p = it->second;
+            g_arena_live[p] = it->first;
+            g_arena_free.erase(it);
+            return p;
+        }
+    }
+    void* p = nullptr;
+    if (cudaMallocHost(&p, cap) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    g_arena_live[p] = cap;
+    return p;
+}
+
+void pinned_free(void* p)
+{
+    if (!p) return;
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    auto it = g_arena_live.find(p);
+    if (it == g_arena_live.end()) { cudaFreeHost(p); cudaGetLastError(); return; }   // not ours: plain pinned memory
+    g_arena_free.emplace(it->second, p);
+    g_arena_live.erase(it);
+}
+
+void pinned_release_cached()
+{
+    std::lock_guard<std::mutex> lk(g_arena_mu);
+    for (auto& kv : g_arena_free) cudaFreeHost(kv.second);
+    g_arena_free.clear();
+    cudaGetLastError();
+}
+}  // namespace cfrk
 
 extern "C" {
 
@@ -124,6 +211,26 @@ int cfrk_device_count(void)
 }
 
 int cfrk_dense_reads_per_tile(int k) { return cfrk::dense_reads_per_tile(k); }
+
+void cfrk_free_host(void* p) { cfrk::pinned_free(p); }
+
+int cfrk_release(void)
+{
+    std::vector<HostCtx*> victims;
+    {
+        std::lock_guard<std::mutex> lk(g_ctx_mu);
+        victims.swap(g_idle_ctx);
+        if (t_holder.c) { victims.push_back(t_holder.c); t_holder.c = nullptr; }
+    }
+    int dev = -1;
+    const bool have_dev = cudaGetDevice(&dev) == cudaSuccess;
+    for (HostCtx* c : victims) { c->release(); delete c; }
+    cfrk::release_stream_scratch();
+    cfrk::pinned_release_cached();
+    if (have_dev) cudaSetDevice(dev);
+    cudaGetLastError();
+    return CFRK_OK;
+}
 
 int cfrk_count_dense_device(const void* d_bases, int fmt, const int64_t* d_start, const int32_t* d_length,
                             int64_t nN, int64_t nS, int64_t read_begin, int64_t read_end, int k, int mode,
@@ -174,9 +281,10 @@ int cfrk_count_dense_host(const void* bases, int fmt, const int64_t* start, cons
     if (!bases || !start || !length || !freq_out) return fail(CFRK_EINVAL, "null pointer");
     if (cfrk_device_count() <= device || device < 0)
         return fail(CFRK_ECUDA, "no such CUDA device (this library has no CPU fallback)");
-    rc = ensure_ctx(device);
+    HostCtx* cp = nullptr;
+    rc = ensure_ctx(device, &cp);
     if (rc) return rc;
-    HostCtx& c = t_ctx;
+    HostCtx& c = *cp;
 
     const size_t fourk = (size_t)1 << (2 * k);
     const size_t row_bytes = fourk * 4;
@@ -271,9 +379,13 @@ int cfrk_count_sparse_device(const void* d_bases, int fmt, const int64_t* d_star
     if (!d_bases || !d_start || !d_length || !d_row_count || !d_keys || !d_counts)
         return fail(CFRK_EINVAL, "null device pointer");
     if (reinterpret_cast<uintptr_t>(d_bases) & 15) return fail(CFRK_EINVAL, "d_bases must be 16-byte aligned");
+    int64_t total = -1;
     cudaError_t e = cfrk::launch_sparse(d_bases, fmt, d_start, d_length, nS, k, d_row_begin, d_row_count, d_keys,
-                                        key_bytes, d_counts, capacity, total_windows, static_cast<cudaStream_t>(stream));
-    if (e == cudaErrorInvalidValue) return fail(CFRK_EINVAL, "capacity smaller than the number of windows");
+                                        key_bytes, d_counts, capacity, &total, static_cast<cudaStream_t>(stream));
+    if (total_windows) *total_windows = total < 0 ? 0 : total;
+    // the capacity case is recognised by the totals, not by the error code (cudaErrorInvalidValue can
+    // also come from a launch configuration or an attribute call)
+    if (total > capacity) { cudaGetLastError(); return fail(CFRK_EINVAL, "capacity smaller than the number of windows"); }
     if (e != cudaSuccess) return fail_cuda(e, "sparse path");
     return CFRK_OK;
 }
@@ -293,7 +405,7 @@ int cfrk_scan_fasta_device(const void* d_bytes, int64_t n, int is_final, int64_t
     if (n_headers) *n_headers = out[0];
     switch (out[1]) {
     case 0: return CFRK_OK;
-    case 1: return fail(CFRK_EFORMAT, "'>' inside a line (grep -c over-counts nS in the reference, src/fastaIO.h:16)");
+    case 1: return fail(CFRK_EFORMAT, "'>' inside a sequence line (grep -c over-counts nS in the reference, src/fastaIO.h:16)");
     case 2: return fail(CFRK_EFORMAT, "sequence text before the first '>' header (undefined in the reference, src/fastaIO.h:49-52)");
     case 3: return fail(CFRK_EFORMAT, "record longer than 2^31-1 bytes (length is int in the reference, src/tipos.h:26)");
     default: return fail(CFRK_EINVAL, "capacity smaller than the number of headers");

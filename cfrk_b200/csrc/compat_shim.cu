@@ -7,6 +7,7 @@
 // own kmer_main.cu/kmer_kernel.cu gives "reference driver, new hot path" (INTEGRATION.md).
 // The struct below is the reference's batch layout (src/tipos.h:23-30); it is the ABI.
 #include "../../include/cfrk_b200.h"
+#include "internal.h"
 
 #include <cuda_runtime.h>
 #include <cstdio>
@@ -26,10 +27,12 @@ void kmer_main(struct read* rd, lint nN, lint nS, int k, unsigned short device)
     static_assert(sizeof(lint) == sizeof(int64_t), "LP64 expected");
     const size_t bytes = (size_t)nS * ((size_t)1 << (2 * k)) * sizeof(int);
     cudaSetDevice(device);
-    if (cudaMallocHost(reinterpret_cast<void**>(&rd->Freq), bytes ? bytes : 4) != cudaSuccess) {
+    // pinned like the reference's (src/kmer_main.cu:115), but from the arena: a caller that hands the
+    // rows back with cfrk_free_host() pays the pinning once, not per call
+    rd->Freq = static_cast<int*>(cfrk::pinned_alloc(bytes ? bytes : 4));
+    if (!rd->Freq) {
         // same channel as the reference: report on stdout and carry on (src/kmer_main.cu:115)
-        printf("\n[Error 9] %s\n", cudaGetErrorString(cudaGetLastError()));
-        rd->Freq = nullptr;
+        printf("\n[Error 9] %s\n", "cudaMallocHost failed");
         return;
     }
     int rc = cfrk_count_dense_host(rd->data, CFRK_FMT_CODES, reinterpret_cast<const int64_t*>(rd->start),

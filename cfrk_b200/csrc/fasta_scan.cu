@@ -3,9 +3,9 @@
 // Replaces, for the file pipeline, popen("grep -c '>'") + the getline loop of the reference
 // reader (src/fastaIO.h:12-69): the raw file bytes are already in HBM for the count kernel, so
 // the record table is derived there and the host never looks at a base.
-//   pass 1  every thread inspects 16 bytes: '>' at a line start = header; '>' anywhere else is
-//           where the reference is undefined (grep over-counts nS) -> error flag.  Headers are
-//           counted per 4 KiB chunk.
+//   pass 1  every thread inspects 16 bytes: '>' at a line start = header; a '>' inside a header
+//           line is text; a '>' inside a sequence line is where the reference is undefined (grep
+//           over-counts nS) -> error flag.  Headers are counted per 4 KiB chunk.
 //   scan    exclusive sum of the chunk counts (cub::DeviceScan: plumbing).
 //   pass 2  header positions written in file order.
 //   pass 3  one thread per record: walk to the end of the header line; the record text is
@@ -35,8 +35,17 @@ __device__ __forceinline__ uint32_t header_mask16(const uint8_t* __restrict__ bu
     for (int j = 0; j < 16; j++) {
         const uint8_t c = (uint8_t)(w[j >> 2] >> (8 * (j & 3)));
         if (j < cnt && c == '>') {
-            if (prev == '\n') m |= 1u << j;
-            else *err = 1;   // '>' inside a line: nS over-counted in the reference (src/fastaIO.h:16)
+            if (prev == '\n') {
+                m |= 1u << j;
+            } else {
+                // '>' inside a line.  Inside a HEADER line (">s1 A>G variant") the reference is well
+                // defined: grep -c counts lines, and the parser only tests line[0] (src/fastaIO.h:16,
+                // 49).  Inside a sequence line grep over-counts nS: undefined.  Walk back to the start
+                // of the line (header lines are short; any other case is the error path).
+                int64_t q = p0 + j - 1;
+                while (q > 0 && buf[q - 1] != '\n') q--;
+                if (buf[q] != '>') *err = 1;
+            }
         }
         prev = c;
     }
@@ -182,7 +191,7 @@ cudaError_t launch_unwrap(const uint8_t* d_buf, int64_t n, const int64_t* d_head
 }
 
 // d_header: cap entries; d_start/d_length: cap entries; h_out[0] = number of headers in the span,
-// h_out[1] = error (0 ok, 1 '>' inside a line, 2 text before the first header, 3 record too long,
+// h_out[1] = error (0 ok, 1 '>' inside a sequence line, 2 text before the first header, 3 record too long,
 // 4 more headers than cap).  Synchronises the stream.
 cudaError_t launch_fasta_scan(const uint8_t* d_buf, int64_t n, int final_span, int64_t* d_header, int64_t* d_start,
                               int32_t* d_length, int64_t cap, int64_t* h_out, cudaStream_t st)

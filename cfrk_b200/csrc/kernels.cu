@@ -16,8 +16,11 @@
 #include "kernels.h"
 #include "kmer_device.cuh"
 
+#include "internal.h"
+
 #include <atomic>
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 namespace cfrk {
@@ -32,18 +35,23 @@ static int env_int(const char* name, int dflt)
     return e ? atoi(e) : dflt;
 }
 
-// Small device scratch that survives between launches: one buffer per (host thread, device, stream),
-// grown on demand.  Launches of one stream are ordered, so they can share it; different streams
-// and different host threads get their own.  (cudaMallocAsync per launch stalled the host for
-// about a millisecond per launch -- visible at k=4, where a whole sweep takes 2.6 ms.)
+// Small device scratch that survives between launches: one buffer per (device, stream), grown on
+// demand, process-wide.  Launches of one stream are ordered, so they can share it; different
+// streams get their own.  (cudaMallocAsync per launch stalled the host for about a millisecond per
+// launch -- visible at k=4, where a whole sweep takes 2.6 ms.)  cfrk_release() frees them.
+namespace {
+struct ScratchSlot { int dev; cudaStream_t st; void* p; size_t cap; };
+std::mutex g_scratch_mu;
+std::vector<ScratchSlot> g_scratch;
+}
+
 static cudaError_t stream_scratch(cudaStream_t st, size_t bytes, void** out)
 {
-    struct Slot { int dev; cudaStream_t st; void* p; size_t cap; };
-    static thread_local std::vector<Slot> slots;
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    for (Slot& s : slots) {
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    for (ScratchSlot& s : g_scratch) {
         if (s.dev == dev && s.st == st) {
             if (s.cap < bytes) {
                 if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;   // last user may still run
@@ -56,11 +64,22 @@ static cudaError_t stream_scratch(cudaStream_t st, size_t bytes, void** out)
             return cudaSuccess;
         }
     }
-    Slot s{dev, st, nullptr, bytes + bytes / 4};
+    ScratchSlot s{dev, st, nullptr, bytes + bytes / 4 + 256};
     if ((e = cudaMalloc(&s.p, s.cap)) != cudaSuccess) return e;
-    slots.push_back(s);
+    g_scratch.push_back(s);
     *out = s.p;
     return cudaSuccess;
+}
+
+void release_stream_scratch()
+{
+    std::lock_guard<std::mutex> lk(g_scratch_mu);
+    for (ScratchSlot& s : g_scratch) {
+        cudaSetDevice(s.dev);
+        cudaFree(s.p);   // implicit device synchronisation: no launch still uses it
+    }
+    g_scratch.clear();
+    cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------

@@ -425,7 +425,7 @@ struct Pipeline {
             if (out[1] != 4) break;
             if (!reserve(in_bytes, (size_t)out[0], 0, err)) return false;   // more records than guessed: grow, rescan
         }
-        if (out[1] == 1) { err.code = CFRK_EFORMAT; err.msg = "'>' inside a line (grep -c over-counts nS in the reference, src/fastaIO.h:16)"; return false; }
+        if (out[1] == 1) { err.code = CFRK_EFORMAT; err.msg = "'>' inside a sequence line (grep -c over-counts nS in the reference, src/fastaIO.h:16)"; return false; }
         if (out[1] == 2) { err.code = CFRK_EFORMAT; err.msg = "sequence text before the first '>' header (undefined in the reference, src/fastaIO.h:49-52)"; return false; }
         if (out[1] == 3) { err.code = CFRK_EFORMAT; err.msg = "record longer than 2^31-1 bytes (length is int in the reference, src/tipos.h:26)"; return false; }
         const size_t nh = (size_t)out[0];

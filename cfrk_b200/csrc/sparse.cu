@@ -1235,9 +1235,10 @@ static cudaError_t sparse_impl(const void* bases, const int64_t* start, const in
     const int64_t cap_long = total / kShortMaxWindows + 1;   // such a row has > 512 windows
     const char* mev = getenv("CFRK_SPARSE_MEDIUM");          // 0: medium rows take the long-row path (A/B measurements)
     const bool use_medium = !(mev && atoi(mev) == 0);
-    if ((e = cudaMallocAsync(reinterpret_cast<void**>(&long_rows), (size_t)cap_long * 8, st)) != cudaSuccess) return e;
-    if ((e = cudaMallocAsync(reinterpret_cast<void**>(&medium_rows), (size_t)cap_long * 8, st)) != cudaSuccess) return e;
-    if ((e = cudaMallocAsync(reinterpret_cast<void**>(&d_n), 24, st)) != cudaSuccess) return e;
+    PoolScratch lists(st);   // released on every return path
+    if ((e = lists.get(&long_rows, (size_t)cap_long)) != cudaSuccess) return e;
+    if ((e = lists.get(&medium_rows, (size_t)cap_long)) != cudaSuccess) return e;
+    if ((e = lists.get(&d_n, 3)) != cudaSuccess) return e;
     cudaMemsetAsync(d_n, 0, 24, st);
     collect_long_kernel<<<num_sms * 4, 256, 0, st>>>(length, nS, k, sizeof(KeyT) == 8, use_medium, long_rows, medium_rows, d_n, cap_long);
     count_launch();
@@ -1263,9 +1264,6 @@ static cudaError_t sparse_impl(const void* bases, const int64_t* start, const in
     if (e == cudaSuccess && n_rows[1] > 0)
         e = sparse_long_rows<KeyT, KeyT, FMT>(b8, start, length, k, row_begin, row_count, keys, counts,
                                               long_rows + (cap_long - (int64_t)n_rows[1]), (int64_t)n_rows[1], num_sms, tr, st);
-    cudaFreeAsync(long_rows, st);
-    cudaFreeAsync(medium_rows, st);
-    cudaFreeAsync(d_n, st);
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 

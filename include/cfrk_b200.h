@@ -62,6 +62,24 @@ int         cfrk_device_count(void);
 /* Number of kernels this library has launched since load (all threads). */
 uint64_t    cfrk_launch_count(void);
 
+/*
+ * Cached resources.  Per CONCURRENT calling thread of cfrk_count_dense_host / kmer_main the library
+ * keeps one context: the device copy of the largest batch seen, up to 2 x 256 MiB of row ring,
+ * 2 streams, 4 events (a thread that exits hands its context to the next new thread, so thread
+ * churn does not add up).  Per stream: a few KiB of launch scratch.  cfrk_release() frees the idle
+ * contexts, the calling thread's own, the scratch and the cached pinned buffers; call it when no
+ * other thread is inside the library.  Nothing is freed at process exit.
+ */
+int         cfrk_release(void);
+
+/*
+ * Give back a rows buffer that kmer_main allocated (rd->Freq).  The reference pins a fresh buffer
+ * per call and never frees it (src/kmer_main.cu:115); here the buffer returns to a pinned arena
+ * and the next call of that size reuses it.  Optional: a caller that never frees behaves exactly
+ * like the reference's.  Any other pinned pointer is passed to cudaFreeHost.
+ */
+void        cfrk_free_host(void *p);
+
 /* ---- the operator: replaces kmer_main (src/kmer_main.cu:20-128) --------------------- */
 
 /*
@@ -156,8 +174,8 @@ int cfrk_count_sparse_device(const void *d_bases, int fmt, const int64_t *d_star
  * semantics: text = all lines after the header up to the next header, length = text - 1 -- of
  * every record whose end is known: all of them if is_final, else all but the last.
  * *n_headers = headers found (records described = n_headers or n_headers - 1).
- * CFRK_EFORMAT where the reference is undefined ('>' inside a line, text before the first
- * header), CFRK_EINVAL if capacity is too small.  Synchronises the stream.
+ * CFRK_EFORMAT where the reference is undefined ('>' inside a sequence line, text before the
+ * first header; a '>' inside a header line is plain text, as in the reference), CFRK_EINVAL if capacity is too small.  Synchronises the stream.
  */
 int cfrk_scan_fasta_device(const void *d_bytes, int64_t n, int is_final, int64_t *d_header,
                            int64_t *d_start, int32_t *d_length, int64_t capacity,

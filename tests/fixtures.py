@@ -91,6 +91,14 @@ def fx_ragged(seed=10, n=300):
     return "".join(out)
 
 
+def fx_gt_in_header(seed=12, n=24, L=110):
+    """'>' INSIDE header lines (">s3 A>G variant"): well defined in the reference -- grep -c counts
+    lines, the parser only looks at line[0] (src/fastaIO.h:16,49)"""
+    rng = random.Random(seed)
+    heads = ["A>G variant", "x>y>z", ">", "trailing>", "chr1:100 C>T (rs1>2)"]
+    return "".join(f">s{i} {heads[i % len(heads)]}\n{_seq(rng, L + i, 'ACGTacgtN')}\n" for i in range(n))
+
+
 def fx_like_seq(n, L, seed=11):
     rng = random.Random(seed)
     return "".join(f">r{i} test\n{_seq(rng, L)}\n" for i in range(n))
@@ -106,6 +114,7 @@ EDGE_SET = [
     ("F_blank", fx_blank(), (1, 2, 3, 5)),
     ("G_short", fx_short(), (1, 2, 3, 5)),
     ("R_ragged", fx_ragged(), (1, 2, 3, 4, 5, 6, 7, 8)),
+    ("I_gtheader", fx_gt_in_header(), (2, 3, 5)),
 ]
 CHUNK_SET = [  # (name, text, ks, chunk sizes)
     ("E_chunk20", fx_chunk(20), (2, 3), (8, 1, 8192, 7, 3)),

@@ -164,7 +164,7 @@ def test_full_size_properties():
     assert torch.equal(out.sum(0, dtype=torch.int64), hist.to(torch.int64))
 
 
-@pytest.mark.parametrize("name", ["A_basic", "C_multiline", "F_crlf", "F_noeol", "F_blank", "G_short", "R_ragged"])
+@pytest.mark.parametrize("name", ["A_basic", "C_multiline", "F_crlf", "F_noeol", "F_blank", "G_short", "R_ragged", "I_gtheader"])
 @pytest.mark.parametrize("final", [True, False])
 def test_scan_fasta_device(name, final):
     """record table built on the GPU == the table the reference parser implies (fixtures.ascii_batch)"""
@@ -187,7 +187,7 @@ def test_scan_fasta_device(name, final):
 
 
 def test_scan_fasta_device_errors():
-    for bad, frag in ((b"ACGT\n>a\nAC\n", "before the first"), (b">a\nAC>GT\n", "inside a line")):
+    for bad, frag in ((b"ACGT\n>a\nAC\n", "before the first"), (b">a\nAC>GT\n", "inside a sequence line")):
         raw = np.frombuffer(bad, dtype=np.uint8)
         buf = padded_bases(raw, 0)
         z = torch.zeros(8, dtype=torch.int64, device="cuda")
