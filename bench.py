@@ -486,6 +486,7 @@ def run_ours(args):
     ring_bytes = int(args.ring_gib * (1 << 30))
     need = max(min(ring_bytes, nS * 4 ** k * 4) for k in ks)
     ring = torch.empty(need // 4, dtype=torch.int32, device=dev)
+    ring_gib = ring.numel() * 4 / 2 ** 30
     stream = torch.cuda.current_stream().cuda_stream
 
     def plan(k):
@@ -800,7 +801,7 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
         "config": {"workload": f"C2: {nS} reads x {L} bp uniform ACGT per GPU (seed 42+rank), dense per-read int32 "
                                f"counts, sweep k={ks}, {args.mode} semantics, {args.fmt} bases resident in HBM, rows to a "
-                               f"{ring.numel() * 4 / 2**30:.1f} GiB HBM ring",
+                               f"{ring_gib:.1f} GiB HBM ring",
                    "l2_policy": "inputs (1.5 GB) and outputs (>= 10 GB per k) larger than L2 (126 MB); no flush needed",
                    "reads_per_gpu": nS, "read_len": L, "k": ks, "parallelism": f"read-range shards x{world}",
                    "host_numa_node_rank0": numa_node},

@@ -15,6 +15,7 @@
 // Compile: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo
 #include "kernels.h"
 #include "kmer_device.cuh"
+#include "dense_args.h"
 
 #include "internal.h"
 
@@ -45,7 +46,7 @@ std::mutex g_scratch_mu;
 std::vector<ScratchSlot> g_scratch;
 }
 
-static cudaError_t stream_scratch(cudaStream_t st, size_t bytes, void** out)
+cudaError_t stream_scratch(cudaStream_t st, size_t bytes, void** out)
 {
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
@@ -121,23 +122,6 @@ struct DenseSink {
     }
 };
 
-struct DenseArgs {
-    const uint8_t* bases;
-    const uint16_t* valid;   // FMT_PACKED only: validity masks (bases = the uint32 codes)
-    const int64_t* start;
-    const int32_t* length;
-    int64_t nS;          // reads in the batch (halo / spill scope)
-    int64_t nN;          // bytes in the bases buffer
-    int64_t read_begin;  // rows [read_begin, read_end) are produced by this launch
-    int64_t read_end;
-    uint32_t* out;       // row read_begin at out[0]
-    int mode;
-    int64_t num_tiles;
-    int64_t chunk_size;   // compat: reads with (index_base + i) % chunk_size == 0 start a reference
-    int64_t index_base;   //         chunk (their spill is dropped); 0 = only read 0 does
-    int flags;            // bit 0: big-row path zeroes with plain stores instead of TMA (A/B switch)
-    uint32_t* handoff;    // warp tiles, compat: one word per tile boundary (zeroed), or null
-};
 
 template <int K, int FMT, int TILE_BINS_T, int NTHREADS, int NBUF>
 __global__ void __launch_bounds__(NTHREADS) dense_count_kernel(const DenseArgs a)
@@ -362,6 +346,14 @@ __global__ void spill_fixup_kernel(const uint32_t* __restrict__ handoff, int64_t
         const uint32_t v = handoff[t];
         if (v) out[(t + 1) * tile_bins - 1] += v;
     }
+}
+
+cudaError_t launch_spill_fixup(const uint32_t* handoff, int64_t ntiles, uint32_t* out, int64_t tile_bins, cudaStream_t st)
+{
+    const int64_t blocks = (ntiles + 255) / 256;
+    spill_fixup_kernel<<<(unsigned)(blocks < 2368 ? blocks : 2368), 256, 0, st>>>(handoff, ntiles, out, tile_bins);
+    g_launches.fetch_add(1);
+    return cudaGetLastError();
 }
 
 template <int K, int FMT, int RW, int WARPS, bool DIRECT = false, int MINB = 1>
@@ -747,6 +739,10 @@ static cudaError_t launch_dense_fmt(int k, const DenseArgs& a, cudaStream_t st)
     //   DIRECT = read-clear-store (one buffer) instead of TMA stores (two buffers).
     static const int k4_variant = env_int("CFRK_K4", 0);
     static const int k5_variant = env_int("CFRK_K5", 0);
+    // k <= 4: lane-per-read tiles with TMA-staged input (dense_lane.cu); CFRK_DENSE_LANE = 0 selects the
+    // round-1 kernels below for A/B runs, a bit mask selects per k (bit k-1)
+    static const int lane_mask = env_int("CFRK_DENSE_LANE", 15);
+    if (k <= 4 && (lane_mask >> (k - 1) & 1)) return launch_dense_lane(k, FMT, a, st);
     if (k == 4) {
         switch (k4_variant) {
         case 1: return launch_dense_k<4, FMT, 4096, 256>(a, st);      // CTA tiles 16 KiB            0.64
@@ -797,6 +793,8 @@ static cudaError_t launch_dense_fmt(int k, const DenseArgs& a, cudaStream_t st)
 
 int dense_reads_per_tile(int k)
 {
+    static const int lane_mask = env_int("CFRK_DENSE_LANE", 15);
+    if (k >= 1 && k <= 4 && (lane_mask >> (k - 1) & 1)) return dense_lane_reads_per_tile(k);
     switch (k) {
     case 1: return Geo<1, kTileBins>::RPT;
     case 2: return Geo<2, kTileBins>::RPT;
