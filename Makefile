@@ -21,7 +21,7 @@ $(OBJ)/%.o: $(CSRC)/%.cu $(HDRS)
 
 $(LIB): $(CU_OBJS)
 	@mkdir -p cfrk_b200/lib
-	$(NVCC) $(ARCH) -shared -o $@ $(CU_OBJS) -lpthread
+	$(NVCC) $(ARCH) -shared -o $@ $(CU_OBJS) -lpthread -lz
 
 $(CLI): $(CSRC)/cli_main.cpp $(LIB)
 	@mkdir -p bin

@@ -121,7 +121,13 @@ def scan_fasta_device(d_bytes, n, is_final, d_header, d_start, d_length, capacit
     return nh.value
 
 
-def run_file(fasta, out, k, nt=12, chunk_size=8192, flags=0, device=0):
-    """cfrk <fasta> <out> <k> [nt] [chunkSize] (reference src/main.cu:232-305)."""
+def run_file(fasta, out, k, nt=12, chunk_size=8192, flags=0, device=0, devices=None):
+    """cfrk <fasta> <out> <k> [nt] [chunkSize] (reference src/main.cu:232-305); devices=[0, 1, ...] spreads
+    the file over several GPUs (rows still in read order)."""
+    if devices is not None:
+        arr = (C.c_int * len(devices))(*devices)
+        _check(lib().cfrk_run_file_multi(os.fsencode(fasta), os.fsencode(out), k, nt, chunk_size, flags, arr, len(devices)),
+               "cfrk_run_file_multi")
+        return
     _check(lib().cfrk_run_file(os.fsencode(fasta), os.fsencode(out), k, nt, chunk_size, flags, device),
            "cfrk_run_file")

@@ -12,6 +12,8 @@
 //     --sparse     omit zero bins (the filter commented out at src/main.cu:51,56)
 //                  k = 9..31 needs --sparse --exact: rows of "kmer_index:count " for the k-mers present
 //     --device=N
+//     --devices=0,1,2 | --devices=all   spread the file over several GPUs (rows stay in read order)
+// The input may be gzip-compressed.
 // Legacy Swift form (swift/cfrk.swf:5): `cfrk <dataset> <k> <chunkSize>` with numeric 2nd/3rd
 // arguments writes the rows to stdout.
 #include "cfrk_b200.h"
@@ -32,14 +34,27 @@ static bool all_digits(const char* s)
 
 int main(int argc, char** argv)
 {
-    int flags = 0, device = 0;
+    int flags = 0;
+    std::vector<int> devices;
     std::vector<char*> pos;
     pos.push_back(argv[0]);
     for (int i = 1; i < argc; i++) {
         if (!strcmp(argv[i], "--all-rows")) flags |= CFRK_RUN_ALL_ROWS;
         else if (!strcmp(argv[i], "--exact")) flags |= CFRK_RUN_EXACT;
         else if (!strcmp(argv[i], "--sparse")) flags |= CFRK_RUN_SPARSE;
-        else if (!strncmp(argv[i], "--device=", 9)) device = atoi(argv[i] + 9);
+        else if (!strncmp(argv[i], "--device=", 9)) devices.assign(1, atoi(argv[i] + 9));
+        else if (!strcmp(argv[i], "--devices=all")) {
+            devices.clear();
+            for (int d = 0; d < cfrk_device_count(); d++) devices.push_back(d);
+        }
+        else if (!strncmp(argv[i], "--devices=", 10)) {
+            devices.clear();
+            for (const char* p = argv[i] + 10; *p;) {
+                devices.push_back(atoi(p));
+                while (*p && *p != ',') p++;
+                if (*p == ',') p++;
+            }
+        }
         else pos.push_back(argv[i]);
     }
     const int pc = (int)pos.size();
@@ -59,7 +74,8 @@ int main(int argc, char** argv)
         if (pc == 5) nt = atoi(pos[4]);
         if (pc == 6) chunk = atol(pos[5]);
     }
-    int rc = cfrk_run_file(pos[1], out, k, nt, chunk, flags, device);
+    if (devices.empty()) devices.push_back(0);
+    int rc = cfrk_run_file_multi(pos[1], out, k, nt, chunk, flags, devices.data(), (int)devices.size());
     if (rc != CFRK_OK) {
         fprintf(stderr, "cfrk: error %d: %s\n", rc, cfrk_last_error());
         return 1;

@@ -387,11 +387,14 @@ __global__ void __launch_bounds__(WARPS * 32) dense_lane_kernel(const DenseArgs 
             const int rounds = __reduce_max_sync(kFull, (nblk + SPLIT - 1) / SPLIT);
             uint32_t carry_c = 0, carry_v = 0;
             int nbad = 0;
+            uint4 raw_next = make_uint4(0u, 0u, 0u, 0u);
+            if (g < nblk) raw_next = fetch_block<FMT, true>(bases, sg, blk0 + g);
             for (int i = 0; i < rounds; i++) {
                 const int b = i * SPLIT + g;
                 const bool live = b < nblk;
-                uint4 raw = make_uint4(0u, 0u, 0u, 0u);
-                if (live) raw = fetch_block<FMT, true>(bases, sg, blk0 + b);
+                const uint4 raw = raw_next;
+                // the next round's block is on its way from shared memory while this one is counted
+                if (b + SPLIT < nblk) raw_next = fetch_block<FMT, true>(bases, sg, blk0 + b + SPLIT);
                 uint32_t codes, pcodes, good;
                 lane_block<K, FMT, SPLIT>(live, raw, b * 16 - off, tend, a.mode, carry_c, carry_v, codes, pcodes, good, nbad);
                 if constexpr (PLANES) count_planes<K>(codes, pcodes, good, cnt);

@@ -1,37 +1,52 @@
 // runfile.cu -- cfrk_run_file(): FASTA file -> GPU count -> .cfrk text, the whole of the
-// reference's main() (src/main.cu:232-305) re-designed around the GPU.
+// reference's main() (src/main.cu:232-305) re-designed around one or several GPUs.
 //
-//   reader   FastaStreamer: a thread preads the file into a ring of PINNED buffers; the raw
-//            bytes are what the GPU consumes (CFRK_FMT_ASCII).  The record text of the
-//            reference parser (src/fastaIO.h:38-69: every non-header line, '\n' included,
-//            minus the last byte) is a contiguous span of the file, so a record is described
-//            by (start, length) into the raw bytes and nothing is copied or encoded on the
-//            host -- newline-as-base, CRLF, missing final newline all fall out.
+//   reader   SpanReader: ONE thread reads the file (plain or gzip) into a pool of PINNED buffers and
+//            cuts it into SPANS at header lines, on the host, by looking at a few hundred bytes at the
+//            end of each window (the bases are never touched).  A span = complete records; its
+//            last >= 1088 text bytes of records are LOOKAHEAD: they get no rows in this span (they
+//            open the next one) but are uploaded with it, because the last row needs the spill of
+//            the read after it and an empty read walks up to 1024+k bytes into its successors
+//            (kmer_device.cuh read_extent).  A record larger than the window makes the buffer grow.
+//            The raw bytes are what the GPU consumes (CFRK_FMT_ASCII): the record text of the
+//            reference parser (src/fastaIO.h:38-69: every non-header line, '\n' included, minus the
+//            last byte) is a contiguous piece of the file, so a record is (start, length) into the
+//            raw bytes -- newline-as-base, CRLF, missing final newline all fall out.
 //            Replaces popen("grep -c") + getline + 3 malloc/record + strcat + per-base switch
 //            + ProcessData + SelectChunk (src/fastaIO.h:12-148, src/main.cu:110-206).
-//   scan     on the GPU (fasta_scan.cu): header positions, (start, length) per record; the host
-//            gets the small table back and never looks at a base.  A '>' that does not start a
-//            line, or text before the first header, is where the reference is undefined:
-//            CFRK_EFORMAT.
-//   count    dense_count_kernel over the buffer, rows through a two-slot device/pinned ring.
-//   writer   nt threads format rows ("bin:count ", src/main.cu:53-55) into private buffers
-//            that are written in order; "\n" before every row but the first, none at EOF.
+//   workers  two host threads per GPU (the reference: devCount pthreads on ONE GPU,
+//            src/main.cu:208-230,277-289), each with its own streams, device buffers and pinned row
+//            ring; spans are dealt out in file order.  Per span: H2D, record table built on the GPU
+//            (fasta_scan.cu), dense rows slice by slice (or sparse rows) into the ring.  While one
+//            worker formats and writes span i, the other has span i+1 uploaded, scanned and counting.
+//   order    rows reach the file in read order: the global index of a span's first read is handed
+//            from span to span as soon as a span is scanned (chunk openers depend on it), and the
+//            writer is entered span by span.
+//   writer   nt pooled threads format rows ("bin:count ", src/main.cu:53-55) into private buffers that
+//            are written in order; "\n" before every row but the first, none at EOF.  --sparse rows of
+//            k >= 5 are compacted ON THE DEVICE to (bin, count) pairs: dense rows never cross PCIe.
 //
 // Default (compat) output = only reads [ (nS/chunkSize)*chunkSize, nS ), because the reference
-// re-opens the output with "w" for the remainder chunk (src/main.cu:34,303-305): the file is
-// scanned once for headers and only that tail is uploaded.  CFRK_RUN_ALL_ROWS streams every read.
+// re-opens the output with "w" for the remainder chunk (src/main.cu:34,303-305): pass 1 scans the
+// file for headers only (all GPUs), pass 2 streams that tail.  CFRK_RUN_ALL_ROWS streams every read.
 #include "../../include/cfrk_b200.h"
 #include "kernels.h"
 #include "kmer_device.cuh"
 #include "internal.h"
 
+#include <cub/device/device_scan.cuh>
+
 #include <algorithm>
+#include <atomic>
+#include <cerrno>
 #include <chrono>
 #include <cstdlib>
 #include <condition_variable>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <fcntl.h>
+#include <functional>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -39,6 +54,11 @@
 #include <thread>
 #include <unistd.h>
 #include <vector>
+#include <zlib.h>
+
+namespace cfrk {
+extern void count_launch();
+}
 
 namespace {
 
@@ -51,16 +71,14 @@ struct Err {
 // commented-out time(NULL) probes, src/main.cu:259-268,302-306)
 struct Trace {
     bool on = getenv("CFRK_TRACE") != nullptr;
-    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now(), last = t0;
-    void mark(const char* what, size_t bytes = 0)
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    std::mutex mu;
+    void mark(const char* what, size_t a = 0, size_t b = 0)
     {
         if (!on) return;
         const auto now = std::chrono::steady_clock::now();
-        fprintf(stderr, "[cfrk trace] %9.3f ms (+%8.3f) %s", std::chrono::duration<double, std::milli>(now - t0).count(),
-                std::chrono::duration<double, std::milli>(now - last).count(), what);
-        if (bytes) fprintf(stderr, " %zu bytes", bytes);
-        fputc('\n', stderr);
-        last = now;
+        std::lock_guard<std::mutex> lk(mu);
+        fprintf(stderr, "[cfrk trace] %9.3f ms %s %zu %zu\n", std::chrono::duration<double, std::milli>(now - t0).count(), what, a, b);
     }
 };
 #define RF_CU(call)                                                                  \
@@ -73,51 +91,131 @@ struct Trace {
         }                                                                            \
     } while (0)
 
-// ------------------------------------------------------------------------------------------
-// Pinned, multi-buffered sequential file reader.  Each buffer has `headroom` bytes in front of
-// the region the reader fills, so the consumer can prepend the unfinished records of the
-// previous buffer and hand the GPU one contiguous span.
-class FastaStreamer {
-public:
-    static constexpr int NB = 3;
-    struct Buf { char* base = nullptr; size_t n = 0; bool eof = false; bool filled = false; };
+constexpr size_t kLookText = (size_t)cfrk::kRefBlockThreads + 64;   // text bytes of records held back as lookahead
 
-    bool open(const char* path, size_t chunk, size_t headroom, Err& err)
+// ------------------------------------------------------------------------------------------
+// Input: a plain file (pread) or a gzip file (zlib; the reference includes <zlib.h> but never uses it,
+// src/fastaIO.h:7).  Sequential reads plus a restart at an (uncompressed) offset for the tail pass.
+class Source {
+public:
+    bool open(const char* path, Err& err)
     {
         fd_ = ::open(path, O_RDONLY);
         if (fd_ < 0) { err.code = CFRK_EIO; err.msg = std::string("cannot open ") + path; return false; }
+        unsigned char magic[2] = {0, 0};
+        const ssize_t got = pread(fd_, magic, 2, 0);
         struct stat st;
         if (fstat(fd_, &st) != 0) { err.code = CFRK_EIO; err.msg = "fstat failed"; return false; }
         size_ = (size_t)st.st_size;
-        chunk_ = chunk; headroom_ = headroom;
-        for (int i = 0; i < NB; i++) {
-            if (cudaMallocHost(reinterpret_cast<void**>(&bufs_[i].base), headroom + chunk + CFRK_PAD) != cudaSuccess) {
-                cudaGetLastError();
-                err.code = CFRK_ENOMEM; err.msg = "cudaMallocHost(stream buffer)";
-                return false;
-            }
+        if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+            gz_ = gzdopen(dup(fd_), "rb");
+            if (!gz_) { err.code = CFRK_EIO; err.msg = "gzdopen failed"; return false; }
+            gzbuffer(gz_, 1 << 20);
         }
-        th_ = std::thread([this] { run(); });
         return true;
     }
-    // i-th buffer of the file (blocks until read). The new bytes are at base+headroom.
-    Buf* acquire(size_t i)
+    bool is_gzip() const { return gz_ != nullptr; }
+    size_t size_hint() const { return gz_ ? size_ * 4 : size_; }   // a guess for gzip; only sizes the buffers
+    bool restart(size_t off, Err& err)
+    {
+        pos_ = off;
+        if (gz_ && gzseek(gz_, (z_off_t)off, SEEK_SET) < 0) { err.code = CFRK_EIO; err.msg = "gzseek failed"; return false; }
+        return true;
+    }
+    // up to n bytes; *eof when the input ends inside or right after them.  false = I/O error.
+    bool read(char* dst, size_t n, size_t* got, bool* eof, Err& err)
+    {
+        *got = 0; *eof = false;
+        while (*got < n) {
+            ssize_t r;
+            if (gz_) {
+                r = gzread(gz_, dst + *got, (unsigned)std::min<size_t>(n - *got, (size_t)1 << 30));
+                if (r < 0) { int en = 0; err.code = CFRK_EIO; err.msg = std::string("gzread: ") + gzerror(gz_, &en); return false; }
+            } else {
+                r = pread(fd_, dst + *got, n - *got, (off_t)(pos_ + *got));
+                if (r < 0) { err.code = CFRK_EIO; err.msg = std::string("read error: ") + strerror(errno); return false; }
+            }
+            if (r == 0) { *eof = true; break; }
+            *got += (size_t)r;
+        }
+        pos_ += *got;
+        if (!gz_) {
+            // a file that shrank under us is an error, not an end: the rows would be silently truncated
+            if (*eof && pos_ < size_) { err.code = CFRK_EIO; err.msg = "input file was truncated while reading"; return false; }
+            if (pos_ >= size_) *eof = true;
+        }
+        return true;
+    }
+    ~Source()
+    {
+        if (gz_) gzclose(gz_);
+        if (fd_ >= 0) ::close(fd_);
+    }
+
+private:
+    int fd_ = -1;
+    gzFile gz_ = nullptr;
+    size_t size_ = 0, pos_ = 0;
+};
+
+// ------------------------------------------------------------------------------------------
+struct Span {
+    char* buf = nullptr;       // pinned
+    size_t cap = 0;
+    size_t n = 0;              // bytes [0, n): complete records, uploaded
+    size_t rows_end = 0;       // records whose header lies before rows_end get rows; the rest is lookahead
+    size_t file_off = 0;       // (uncompressed) file offset of buf[0]
+    bool final = false;
+    int64_t index = 0;
+};
+
+// last q in [lo, p) with buf[q] == '>' at a line start, or SIZE_MAX
+inline size_t prev_header(const char* buf, size_t lo, size_t p)
+{
+    while (p > lo) {
+        const void* m = memrchr(buf + lo, '>', p - lo);
+        if (!m) return SIZE_MAX;
+        const size_t q = (size_t)(static_cast<const char*>(m) - buf);
+        if (q == 0 || buf[q - 1] == '\n') return q;
+        p = q;
+    }
+    return SIZE_MAX;
+}
+
+class SpanReader {
+public:
+    // window: bytes read per span; nslots: pinned buffers in flight
+    bool open(Source* src, size_t window, int nslots, Err& err)
+    {
+        src_ = src; window_ = window;
+        slots_.resize(nslots);
+        for (Span& s : slots_)
+            if (!grow(s, window + ((size_t)1 << 16), err)) return false;
+        for (int i = 0; i < nslots; i++) free_.push_back(i);
+        return true;
+    }
+    void start(size_t file_off)
+    {
+        file_off_ = file_off;
+        th_ = std::thread([this] { run(); });
+    }
+    // next span in file order (nullptr: end of input or error -- see error())
+    Span* next()
     {
         std::unique_lock<std::mutex> lk(mu_);
-        cv_.wait(lk, [&] { return bufs_[i % NB].filled && seq_[i % NB] == i; });
-        return &bufs_[i % NB];
+        cv_.wait(lk, [&] { return !ready_.empty() || done_; });
+        if (ready_.empty()) return nullptr;
+        Span* s = ready_.front();
+        ready_.pop_front();
+        return s;
     }
-    void release(size_t i)
+    void release(Span* s)
     {
         std::lock_guard<std::mutex> lk(mu_);
-        bufs_[i % NB].filled = false;
+        free_.push_back((int)(s - slots_.data()));
         cv_.notify_all();
     }
-    char* next_base(size_t i) { return bufs_[(i + 1) % NB].base; }
-    size_t headroom() const { return headroom_; }
-    size_t file_size() const { return size_; }
-    int fd() const { return fd_; }
-    ~FastaStreamer()
+    void stop()
     {
         {
             std::lock_guard<std::mutex> lk(mu_);
@@ -125,52 +223,166 @@ public:
             cv_.notify_all();
         }
         if (th_.joinable()) th_.join();
-        for (int i = 0; i < NB; i++) if (bufs_[i].base) cudaFreeHost(bufs_[i].base);
-        if (fd_ >= 0) ::close(fd_);
+    }
+    const Err& error() const { return err_; }
+    ~SpanReader()
+    {
+        stop();
+        for (Span& s : slots_) if (s.buf) cudaFreeHost(s.buf);
     }
 
 private:
+    // (re)allocate the pinned buffer of a span, keeping its first `keep` bytes
+    static bool grow(Span& s, size_t cap, Err& err, size_t keep = 0)
+    {
+        char* nb = nullptr;
+        if (cudaMallocHost(reinterpret_cast<void**>(&nb), cap + CFRK_PAD) != cudaSuccess) {
+            cudaGetLastError();
+            err.code = CFRK_ENOMEM; err.msg = "cudaMallocHost(stream buffer)";
+            return false;
+        }
+        if (s.buf) { memcpy(nb, s.buf, keep); cudaFreeHost(s.buf); }
+        s.buf = nb; s.cap = cap;
+        return true;
+    }
+    void finish()
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        done_ = true;
+        cv_.notify_all();
+    }
     void run()
     {
-        size_t off = 0;
-        for (size_t i = 0;; i++) {
-            Buf& b = bufs_[i % NB];
+        std::vector<char> carry;      // bytes that open the next span
+        int64_t index = 0;
+        bool eof = false;
+        while (!eof) {
+            int si;
             {
                 std::unique_lock<std::mutex> lk(mu_);
-                cv_.wait(lk, [&] { return stop_ || !b.filled; });
-                if (stop_) return;
+                cv_.wait(lk, [&] { return stop_ || !free_.empty(); });
+                if (stop_) { done_ = true; cv_.notify_all(); return; }
+                si = free_.back(); free_.pop_back();
             }
-            size_t want = std::min(chunk_, size_ - off), got = 0;
-            while (got < want) {
-                ssize_t r = pread(fd_, b.base + headroom_ + got, want - got, (off_t)(off + got));
-                if (r <= 0) break;
-                got += (size_t)r;
+            Span& s = slots_[si];
+            s.n = 0; s.final = false; s.index = index; s.file_off = file_off_;
+            if (carry.size() + window_ > s.cap && !grow(s, carry.size() + window_ + ((size_t)1 << 16), err_)) return finish();
+            memcpy(s.buf, carry.data(), carry.size());
+            size_t fill = carry.size();
+            for (;;) {
+                size_t got = 0;
+                if (!src_->read(s.buf + fill, s.cap - fill, &got, &eof, err_)) return finish();
+                fill += got;
+                if (eof) { s.n = fill; s.rows_end = fill; s.final = true; break; }
+                // cut at the last header line; hold back >= kLookText text bytes of complete records
+                const size_t h_last = prev_header(s.buf, 1, fill);
+                size_t cut = SIZE_MAX;
+                if (h_last != SIZE_MAX) {
+                    size_t held = 0, next = h_last, h = h_last;
+                    while (h > 0) {
+                        h = prev_header(s.buf, 0, h);
+                        if (h == SIZE_MAX) break;
+                        const void* eol = memchr(s.buf + h, '\n', next - h);
+                        held += eol ? next - ((size_t)(static_cast<const char*>(eol) - s.buf) + 1) : 0;
+                        next = h;
+                        if (held >= kLookText) { cut = h; break; }
+                    }
+                }
+                if (cut != SIZE_MAX && cut > 0) {
+                    s.n = h_last; s.rows_end = cut;
+                    carry.assign(s.buf + cut, s.buf + fill);
+                    file_off_ += cut;
+                    break;
+                }
+                // one record (plus its lookahead) larger than the buffer: make room and read on
+                if (!grow(s, s.cap * 2, err_, fill)) return finish();
             }
-            off += got;
+            if (s.final) carry.clear();
+            index++;
             {
                 std::lock_guard<std::mutex> lk(mu_);
-                b.n = got; b.eof = (off >= size_) || got < want; b.filled = true; seq_[i % NB] = i;
+                ready_.push_back(&s);
                 cv_.notify_all();
             }
-            if (b.eof) return;
         }
+        finish();
     }
-    int fd_ = -1;
-    size_t size_ = 0, chunk_ = 0, headroom_ = 0;
-    Buf bufs_[NB];
-    size_t seq_[NB] = {0, 0, 0};
+    Source* src_ = nullptr;
+    size_t window_ = 0, file_off_ = 0;
+    std::vector<Span> slots_;
+    std::vector<int> free_;
+    std::deque<Span*> ready_;
     std::thread th_;
     std::mutex mu_;
     std::condition_variable cv_;
-    bool stop_ = false;
+    bool stop_ = false, done_ = false;
+    Err err_;
 };
 
 // ------------------------------------------------------------------------------------------
 // Record table of a span, as fasta_scan.cu produces it on the device.
 struct RecordIndex {
-    std::vector<int64_t> start;   // records whose end is known: all of them in a final span, else all but the last
+    std::vector<int64_t> start;   // every record of the span (spans end at a header line or at EOF)
     std::vector<int32_t> length;
     std::vector<size_t> header;   // position of each header's '>'
+};
+
+// ------------------------------------------------------------------------------------------
+// persistent formatting threads (the writer used to create and join nt threads per slice)
+class ThreadPool {
+public:
+    explicit ThreadPool(int n)
+    {
+        for (int i = 0; i < n; i++) th_.emplace_back([this, i] { loop(i); });
+    }
+    int size() const { return (int)th_.size(); }
+    // fn(part) for part in [0, nparts), nparts <= size(); returns when all are done
+    void run(int nparts, const std::function<void(int)>& fn)
+    {
+        std::unique_lock<std::mutex> lk(mu_);
+        fn_ = &fn; nparts_ = nparts; pending_ = nparts; gen_++;
+        cv_.notify_all();
+        done_cv_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+    }
+    ~ThreadPool()
+    {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            quit_ = true;
+            cv_.notify_all();
+        }
+        for (auto& t : th_) t.join();
+    }
+
+private:
+    void loop(int id)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)>* fn;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return quit_ || gen_ != seen; });
+                if (quit_) return;
+                seen = gen_;
+                if (id >= nparts_) continue;
+                fn = fn_;
+            }
+            (*fn)(id);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--pending_ == 0) done_cv_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_;
+    const std::function<void(int)>* fn_ = nullptr;
+    int nparts_ = 0, pending_ = 0;
+    uint64_t gen_ = 0;
+    bool quit_ = false;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -195,7 +407,7 @@ struct BinLabels {
 struct RawBuf {
     char* data = nullptr;
     size_t size = 0, cap = 0;
-    void reserve(size_t n)
+    bool reserve(size_t n)
     {
         if (n > cap) {
             free(data);
@@ -203,6 +415,7 @@ struct RawBuf {
             cap = data ? n : 0;
         }
         size = 0;
+        return data != nullptr;
     }
     RawBuf() = default;
     RawBuf(const RawBuf&) = delete;
@@ -223,11 +436,11 @@ inline char* put_int(char* p, int32_t v)
     return p;
 }
 
-void format_rows(const int32_t* rows, size_t nrows, size_t bins, const BinLabels& lab, bool sparse,
+bool format_rows(const int32_t* rows, size_t nrows, size_t bins, const BinLabels& lab, bool sparse,
                  bool first_row_of_file, RawBuf& out)
 {
     // worst case per token: 8-byte label store + 11 digits + space
-    out.reserve(nrows * (bins * 20 + 1) + 16);
+    if (!out.reserve(nrows * (bins * 20 + 1) + 16)) return false;
     char* p = out.data;
     for (size_t r = 0; r < nrows; r++) {
         if (!(first_row_of_file && r == 0)) *p++ = '\n';
@@ -242,6 +455,7 @@ void format_rows(const int32_t* rows, size_t nrows, size_t bins, const BinLabels
         }
     }
     out.size = (size_t)(p - out.data);
+    return true;
 }
 
 class CfrkWriter {
@@ -254,6 +468,8 @@ public:
         bins_ = k <= CFRK_CLI_DENSE_MAX_K ? (size_t)1 << (2 * k) : 0;
         if (bins_) labels_.reset(new BinLabels(bins_));
         nt_ = std::max(1, std::min(nt, 64));
+        pool_.reset(new ThreadPool(nt_));
+        parts_ = std::vector<RawBuf>(nt_);
         sparse_ = sparse;
         return true;
     }
@@ -261,79 +477,74 @@ public:
     {
         if (!nrows) return true;
         const int nt = (int)std::min<size_t>((size_t)nt_, nrows);
-        if (parts_.size() < (size_t)nt_) parts_ = std::vector<RawBuf>(nt_);
-        std::vector<std::thread> th;
-        for (int t = 0; t < nt; t++) {
+        std::vector<char> good(nt, 1);
+        const bool first_file = first_;
+        pool_->run(nt, [&](int t) {
             const size_t a = nrows * t / nt, b = nrows * (t + 1) / nt;
-            const bool first = first_ && a == 0;
-            th.emplace_back([=] { format_rows(rows + a * bins_, b - a, bins_, *labels_, sparse_, first, parts_[t]); });
-        }
-        for (auto& x : th) x.join();
+            good[t] = format_rows(rows + a * bins_, b - a, bins_, *labels_, sparse_, first_file && a == 0, parts_[t]);
+        });
         first_ = false;
+        for (char g : good) if (!g) { err.code = CFRK_ENOMEM; err.msg = "out of memory for the text of a row slice"; return false; }
         return flush_parts(nt, err);
     }
     // rows given as (key, count) pairs: the same "bin:count " tokens, non-zero bins only
-    bool write_pairs(const int64_t* row_begin, const int32_t* row_count, const uint64_t* keys,
+    template <typename KeyT>
+    bool write_pairs(const int64_t* row_begin, const int32_t* row_count, const KeyT* keys,
                      const uint32_t* counts, size_t nrows, Err& err)
     {
         if (!nrows) return true;
         const int nt = (int)std::min<size_t>((size_t)nt_, nrows);
-        if (parts_.size() < (size_t)nt_) parts_ = std::vector<RawBuf>(nt_);
-        std::vector<std::thread> th;
-        for (int t = 0; t < nt; t++) {
+        std::vector<char> good(nt, 1);
+        const bool first_file = first_;
+        pool_->run(nt, [&](int t) {
             const size_t a = nrows * t / nt, b = nrows * (t + 1) / nt;
-            const bool first = first_ && a == 0;
-            th.emplace_back([=] {
-                size_t npairs = 0;
-                for (size_t r = a; r < b; r++) npairs += (size_t)row_count[r];
-                RawBuf& out = parts_[t];
-                out.reserve(npairs * 33 + (b - a) + 1);   // 20 + 1 + 10 + 1 per token, '\n' per row
-                char* p = out.data;
-                for (size_t r = a; r < b; r++) {
-                    if (!(first && r == a)) *p++ = '\n';
-                    const uint64_t* kk = keys + row_begin[r];
-                    const uint32_t* cc = counts + row_begin[r];
-                    for (int32_t i = 0; i < row_count[r]; i++) {
-                        char tmp[24];
-                        int l = 0;
-                        uint64_t u = kk[i];
-                        do { tmp[l++] = (char)('0' + u % 10); u /= 10; } while (u);
-                        while (l) *p++ = tmp[--l];
-                        *p++ = ':';
-                        p = put_int(p, (int32_t)cc[i]);
-                        *p++ = ' ';
-                    }
+            const bool first = first_file && a == 0;
+            size_t npairs = 0;
+            for (size_t r = a; r < b; r++) npairs += (size_t)row_count[r];
+            RawBuf& out = parts_[t];
+            if (!out.reserve(npairs * 33 + (b - a) + 1)) { good[t] = 0; return; }   // 20 + 1 + 10 + 1 per token, '\n' per row
+            char* p = out.data;
+            for (size_t r = a; r < b; r++) {
+                if (!(first && r == a)) *p++ = '\n';
+                const KeyT* kk = keys + row_begin[r];
+                const uint32_t* cc = counts + row_begin[r];
+                for (int32_t i = 0; i < row_count[r]; i++) {
+                    char tmp[24];
+                    int l = 0;
+                    uint64_t u = (uint64_t)kk[i];
+                    do { tmp[l++] = (char)('0' + u % 10); u /= 10; } while (u);
+                    while (l) *p++ = tmp[--l];
+                    *p++ = ':';
+                    p = put_int(p, (int32_t)cc[i]);
+                    *p++ = ' ';
                 }
-                out.size = (size_t)(p - out.data);
-            });
-        }
-        for (auto& x : th) x.join();
+            }
+            out.size = (size_t)(p - out.data);
+        });
         first_ = false;
+        for (char g : good) if (!g) { err.code = CFRK_ENOMEM; err.msg = "out of memory for the text of a row slice"; return false; }
         return flush_parts(nt, err);
     }
     ~CfrkWriter() { if (fd_ >= 0) ::close(fd_); }
 
 private:
     // formatted parts -> file, in order.  Regular files: every part is written at its own offset
-    // by its own thread (pwrite); pipes (the Swift stdout form): sequential write.
+    // by its own pool thread (pwrite); pipes (the Swift stdout form): sequential write.
     bool flush_parts(int nparts, Err& err)
     {
         bool ok = true;
         if (seekable_) {
             std::vector<off_t> at(nparts);
             for (int i = 0; i < nparts; i++) { at[i] = off_; off_ += (off_t)parts_[i].size; }
-            std::vector<std::thread> th;
             std::vector<char> good(nparts, 1);
-            for (int i = 0; i < nparts; i++)
-                th.emplace_back([&, i] {
-                    size_t done = 0;
-                    while (done < parts_[i].size) {
-                        ssize_t w = pwrite(fd_, parts_[i].data + done, parts_[i].size - done, at[i] + (off_t)done);
-                        if (w <= 0) { good[i] = 0; break; }
-                        done += (size_t)w;
-                    }
-                });
-            for (auto& x : th) x.join();
+            pool_->run(nparts, [&](int i) {
+                size_t done = 0;
+                while (done < parts_[i].size) {
+                    ssize_t w = pwrite(fd_, parts_[i].data + done, parts_[i].size - done, at[i] + (off_t)done);
+                    if (w <= 0) { good[i] = 0; break; }
+                    done += (size_t)w;
+                }
+            });
             for (char g : good) ok = ok && g;
         } else {
             for (int i = 0; i < nparts; i++) {
@@ -348,6 +559,7 @@ private:
         return ok;
     }
     std::vector<RawBuf> parts_;
+    std::unique_ptr<ThreadPool> pool_;
     int fd_ = -1;
     bool seekable_ = false;
     off_t off_ = 0;
@@ -358,9 +570,106 @@ private:
 };
 
 // ------------------------------------------------------------------------------------------
-// GPU side of the file pipeline: input double buffer + row ring.
+// Spans are processed by several workers but their effects are ordered: a value handed from span i
+// to span i+1 (index of the first read), and a turn (the writer).
+class Sequencer {
+public:
+    // blocks until span `i` may go; false if the run was aborted
+    bool wait_turn(int64_t i)
+    {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return abort_ || turn_ == i; });
+        return !abort_;
+    }
+    void end_turn(int64_t i)
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        if (turn_ == i) turn_ = i + 1;
+        cv_.notify_all();
+    }
+    bool get_reads_before(int64_t i, int64_t* v)
+    {
+        std::unique_lock<std::mutex> lk(mu_);
+        cv_.wait(lk, [&] { return abort_ || known_ >= i; });
+        if (abort_) return false;
+        *v = reads_[(size_t)(i % kRing)];
+        return true;
+    }
+    void set_reads_before(int64_t i, int64_t v)     // called in span order (span i-1's worker, after its scan)
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        reads_[(size_t)(i % kRing)] = v;
+        known_ = i;
+        cv_.notify_all();
+    }
+    void reset(int64_t first_read)
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        turn_ = 0; known_ = 0; reads_[0] = first_read; abort_ = false;
+    }
+    void abort()
+    {
+        std::lock_guard<std::mutex> lk(mu_);
+        abort_ = true;
+        cv_.notify_all();
+    }
+
+private:
+    static constexpr int kRing = 256;   // far more than the spans in flight (<= 2 per GPU + 1)
+    std::mutex mu_;
+    std::condition_variable cv_;
+    int64_t turn_ = 0, known_ = 0;
+    int64_t reads_[kRing] = {0};
+    bool abort_ = false;
+};
+
+// ------------------------------------------------------------------------------------------
+// dense rows -> (bin, count) pairs on the device (--sparse, k >= 5): one warp per row
+__global__ void row_nnz_kernel(const int32_t* __restrict__ rows, int64_t nrows, int bins, int64_t* __restrict__ nnz)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r <= nrows; r += warps) {
+        if (r == nrows) { if (lane == 0) nnz[r] = 0; continue; }
+        const int4* row = reinterpret_cast<const int4*>(rows + r * bins);
+        int c = 0;
+        for (int i = lane; i < bins / 4; i += 32) {
+            const int4 v = row[i];
+            c += (v.x != 0) + (v.y != 0) + (v.z != 0) + (v.w != 0);
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        if (lane == 0) nnz[r] = c;
+    }
+}
+
+__global__ void row_compact_kernel(const int32_t* __restrict__ rows, int64_t nrows, int bins, const int64_t* __restrict__ begin,
+                                   uint32_t* __restrict__ keys, uint32_t* __restrict__ counts, int32_t* __restrict__ row_count)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += warps) {
+        const int32_t* row = rows + r * bins;
+        int64_t at = begin[r];
+        for (int i0 = 0; i0 < bins; i0 += 32) {
+            const int v = row[i0 + lane];
+            const uint32_t m = __ballot_sync(0xffffffffu, v != 0);
+            if (v != 0) {
+                const int64_t p = at + __popc(m & ((1u << lane) - 1u));
+                keys[p] = (uint32_t)(i0 + lane);
+                counts[p] = (uint32_t)v;
+            }
+            at += __popc(m);
+        }
+        if (lane == 0) row_count[r] = (int32_t)(at - begin[r]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// GPU side of one worker: device input buffer + row ring.
 struct Pipeline {
     static constexpr size_t kSlotBytes = (size_t)128 << 20;
+    int device = 0;
     cudaStream_t compute = nullptr, copy = nullptr;
     cudaEvent_t done[2] = {}, drained[2] = {};
     char* d_in = nullptr; size_t cap_in = 0;
@@ -372,9 +681,17 @@ struct Pipeline {
     const char* cur_bases = nullptr; const int64_t* cur_start = nullptr; const int32_t* cur_length = nullptr;
     size_t n_headers = 0;
     int32_t* d_rows[2] = {}; int32_t* h_rows[2] = {}; size_t cap_rows = 0;
+    // pooled scratch of the sparse outputs (device + pinned mirrors), grown on demand
+    void* d_pool[4] = {}; size_t cap_pool[4] = {};
+    void* h_pool[4] = {}; size_t cap_hpool[4] = {};
+    char* h_hdr = nullptr; size_t cap_hhdr = 0;     // pinned staging of the record table
+    Sequencer* seq = nullptr;
 
-    bool init(Err& err)
+    bool init(int dev, Sequencer* s, Err& err)
     {
+        device = dev; seq = s;
+        RF_CU(cudaSetDevice(dev));
+        cfrk::keep_pool_memory(dev);
         RF_CU(cudaStreamCreateWithFlags(&compute, cudaStreamNonBlocking));
         RF_CU(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) {
@@ -383,15 +700,35 @@ struct Pipeline {
         }
         return true;
     }
+    bool dev_pool(int i, size_t bytes, Err& err)
+    {
+        if (bytes <= cap_pool[i]) return true;
+        cudaFree(d_pool[i]); d_pool[i] = nullptr; cap_pool[i] = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        RF_CU(cudaMalloc(&d_pool[i], want));
+        cap_pool[i] = want;
+        return true;
+    }
+    bool host_pool(int i, size_t bytes, Err& err)
+    {
+        if (bytes <= cap_hpool[i]) return true;
+        if (h_pool[i]) cudaFreeHost(h_pool[i]);
+        h_pool[i] = nullptr; cap_hpool[i] = 0;
+        const size_t want = bytes + bytes / 4 + 256;
+        RF_CU(cudaMallocHost(&h_pool[i], want));
+        cap_hpool[i] = want;
+        return true;
+    }
     bool reserve(size_t in_bytes, size_t nreads, size_t row_bytes, Err& err)
     {
         if (in_bytes && in_bytes + CFRK_PAD > cap_in) {
-            cudaFree(d_in);
+            cudaFree(d_in); d_in = nullptr;
             cap_in = in_bytes + CFRK_PAD + in_bytes / 8;
             RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_in), cap_in));
         }
         if (nreads > cap_reads) {
             cudaFree(d_start); cudaFree(d_length); cudaFree(d_header);
+            d_start = nullptr; d_length = nullptr; d_header = nullptr;
             cap_reads = nreads + nreads / 4 + 64;
             RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_start), cap_reads * 8));
             RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_length), cap_reads * 4));
@@ -401,6 +738,10 @@ struct Pipeline {
         if (row_bytes && need > cap_rows) {
             for (int i = 0; i < 2; i++) {
                 cudaFree(d_rows[i]); if (h_rows[i]) cudaFreeHost(h_rows[i]);
+                d_rows[i] = nullptr; h_rows[i] = nullptr;
+            }
+            cap_rows = 0;
+            for (int i = 0; i < 2; i++) {
                 RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_rows[i]), need));
                 RF_CU(cudaMallocHost(reinterpret_cast<void**>(&h_rows[i]), need));
             }
@@ -409,17 +750,19 @@ struct Pipeline {
         return true;
     }
     // Span of raw file bytes -> HBM, record table built THERE (fasta_scan.cu); the host gets the
-    // (small) table back for its bookkeeping and never looks at a base.
-    bool upload_and_scan(const char* h_in, size_t in_bytes, bool final_span, RecordIndex& ri, Err& err)
+    // (small) table back for its bookkeeping and never looks at a base.  Spans end at a header
+    // line or at the end of the input, so every record of the span is complete.
+    bool upload_and_scan(const char* h_in, size_t in_bytes, RecordIndex& ri, Err& err)
     {
         ri.start.clear(); ri.length.clear(); ri.header.clear();
+        n_headers = 0;
         if (in_bytes == 0) return true;
         if (!reserve(in_bytes, std::max<size_t>(cap_reads, in_bytes / 64 + 64), 0, err)) return false;
         RF_CU(cudaMemcpyAsync(d_in, h_in, in_bytes, cudaMemcpyHostToDevice, compute));
         RF_CU(cudaMemsetAsync(d_in + in_bytes, 0, CFRK_PAD, compute));
         int64_t out[2];
         for (;;) {
-            cudaError_t e = cfrk::launch_fasta_scan(reinterpret_cast<const uint8_t*>(d_in), (int64_t)in_bytes, final_span,
+            cudaError_t e = cfrk::launch_fasta_scan(reinterpret_cast<const uint8_t*>(d_in), (int64_t)in_bytes, 1,
                                                     d_header, d_start, d_length, (int64_t)cap_reads, out, compute);
             if (e != cudaSuccess) { err.code = CFRK_ECUDA; err.msg = std::string("fasta scan: ") + cudaGetErrorString(e); return false; }
             if (out[1] != 4) break;
@@ -431,16 +774,25 @@ struct Pipeline {
         const size_t nh = (size_t)out[0];
         n_headers = nh;
         cur_bases = d_in; cur_start = d_start; cur_length = d_length;
-        const size_t complete = final_span ? nh : (nh ? nh - 1 : 0);
-        ri.header.resize(nh); ri.start.resize(complete); ri.length.resize(complete);
-        std::vector<int64_t> hdr(nh);
-        if (nh) RF_CU(cudaMemcpyAsync(hdr.data(), d_header, nh * 8, cudaMemcpyDeviceToHost, compute));
-        if (complete) {
-            RF_CU(cudaMemcpyAsync(ri.start.data(), d_start, complete * 8, cudaMemcpyDeviceToHost, compute));
-            RF_CU(cudaMemcpyAsync(ri.length.data(), d_length, complete * 4, cudaMemcpyDeviceToHost, compute));
+        ri.header.resize(nh); ri.start.resize(nh); ri.length.resize(nh);
+        if (nh) {
+            // pinned staging: a pageable destination makes these copies synchronous and slow
+            const size_t need = nh * 20;
+            if (need > cap_hhdr) {
+                if (h_hdr) cudaFreeHost(h_hdr);
+                h_hdr = nullptr; cap_hhdr = 0;
+                RF_CU(cudaMallocHost(reinterpret_cast<void**>(&h_hdr), need + need / 4));
+                cap_hhdr = need + need / 4;
+            }
+            RF_CU(cudaMemcpyAsync(h_hdr, d_header, nh * 8, cudaMemcpyDeviceToHost, compute));
+            RF_CU(cudaMemcpyAsync(h_hdr + nh * 8, d_start, nh * 8, cudaMemcpyDeviceToHost, compute));
+            RF_CU(cudaMemcpyAsync(h_hdr + nh * 16, d_length, nh * 4, cudaMemcpyDeviceToHost, compute));
+            RF_CU(cudaStreamSynchronize(compute));
+            const int64_t* hh = reinterpret_cast<const int64_t*>(h_hdr);
+            for (size_t i = 0; i < nh; i++) ri.header[i] = (size_t)hh[i];
+            memcpy(ri.start.data(), h_hdr + nh * 8, nh * 8);
+            memcpy(ri.length.data(), h_hdr + nh * 16, nh * 4);
         }
-        RF_CU(cudaStreamSynchronize(compute));
-        for (size_t i = 0; i < nh; i++) ri.header[i] = (size_t)hdr[i];
         return true;
     }
     // Exact mode: k-mers do not stop at line ends.  Replace the span by its unwrapped copy.
@@ -448,12 +800,12 @@ struct Pipeline {
     {
         if (nreads == 0) return true;
         if (in_bytes + CFRK_PAD > cap_packed) {
-            cudaFree(d_packed);
+            cudaFree(d_packed); d_packed = nullptr;
             cap_packed = in_bytes + CFRK_PAD + in_bytes / 8;
             RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_packed), cap_packed));
         }
         if (nreads + 1 > cap_reads2) {
-            cudaFree(d_start2); cudaFree(d_length2);
+            cudaFree(d_start2); cudaFree(d_length2); d_start2 = nullptr; d_length2 = nullptr;
             cap_reads2 = nreads + nreads / 4 + 64;
             RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_start2), cap_reads2 * 8));
             RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_length2), cap_reads2 * 4));
@@ -467,103 +819,106 @@ struct Pipeline {
         return true;
     }
     // Rows [0, nrows) of the span that upload_and_scan() left in HBM.
-    bool count_scanned(const char* h_in, size_t in_bytes, const RecordIndex& ri, size_t nrows, int k, int mode,
+    bool count_scanned(const Span& sp, const RecordIndex& ri, size_t nrows, int k, int mode, bool sparse,
                        int64_t chunk_size, int64_t index_base, CfrkWriter& w, Err& err)
     {
-        if (nrows == 0) return true;
-        if (mode == CFRK_MODE_COMPAT && std::find(ri.length.begin(), ri.length.end(), 0) != ri.length.end())
-            return run(h_in, in_bytes, ri, nrows, k, mode, chunk_size, index_base, w, err);   // needs the packed layout
-        if (mode == CFRK_MODE_EXACT && !unwrap_scanned(in_bytes, ri.start.size(), err)) return false;
-        return count_rows(in_bytes, ri.start.size(), nrows, k, mode, chunk_size, index_base, w, err);
-    }
-    // k > 8: sparse rows (exact semantics) of the span that upload_and_scan() left in HBM
-    bool count_scanned_sparse(size_t in_bytes, const RecordIndex& ri, size_t nrows, int k, CfrkWriter& w, Err& err)
-    {
-        if (nrows == 0) return true;
-        const size_t nreads = ri.start.size();
-        if (!unwrap_scanned(in_bytes, nreads, err)) return false;   // k > 8 is exact mode only
-        int64_t cap = 0;
-        for (int32_t l : ri.length) cap += std::max(0, l + 1 - k + 1);   // unwrapped text <= raw length + 1
-        int64_t* d_rb = nullptr; int32_t* d_rc = nullptr; uint64_t* d_k = nullptr; uint32_t* d_c = nullptr;
-        RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_rb), (nreads + 1) * 8));
-        RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_rc), nreads * 4));
-        RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_k), (size_t)std::max<int64_t>(cap, 1) * 8));
-        RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_c), (size_t)std::max<int64_t>(cap, 1) * 4));
-        int64_t total = 0;
-        cudaError_t e = cfrk::launch_sparse(cur_bases, cfrk::FMT_ASCII, cur_start, cur_length, (int64_t)nreads, k, d_rb, d_rc, d_k, 8,
-                                            d_c, cap, &total, compute);
-        bool ok = e == cudaSuccess;
-        if (!ok) { err.code = CFRK_ECUDA; err.msg = std::string("sparse path: ") + cudaGetErrorString(e); }
-        std::vector<int64_t> rb(nrows + 1);
-        std::vector<int32_t> rc(nrows);
-        std::vector<uint64_t> kk;
-        std::vector<uint32_t> cc;
-        if (ok) {
-            ok = cudaMemcpyAsync(rb.data(), d_rb, (nrows + 1) * 8, cudaMemcpyDeviceToHost, compute) == cudaSuccess &&
-                 cudaMemcpyAsync(rc.data(), d_rc, nrows * 4, cudaMemcpyDeviceToHost, compute) == cudaSuccess &&
-                 cudaStreamSynchronize(compute) == cudaSuccess;
-            const size_t used = (size_t)rb[nrows];
-            kk.resize(std::max<size_t>(used, 1)); cc.resize(std::max<size_t>(used, 1));
-            ok = ok && cudaMemcpy(kk.data(), d_k, used * 8, cudaMemcpyDeviceToHost) == cudaSuccess &&
-                 cudaMemcpy(cc.data(), d_c, used * 4, cudaMemcpyDeviceToHost) == cudaSuccess;
-            if (!ok) { err.code = CFRK_ECUDA; err.msg = "sparse path: device to host copy failed"; }
-        }
-        cudaFree(d_rb); cudaFree(d_rc); cudaFree(d_k); cudaFree(d_c);
-        return ok && w.write_pairs(rb.data(), rc.data(), kk.data(), cc.data(), nrows, err);
-    }
-    // Host-side record table (the rare packed layout): upload bytes + table, then count.
-    bool run(const char* h_in, size_t in_bytes, const RecordIndex& ri_in, size_t nrows, int k, int mode,
-             int64_t chunk_size, int64_t index_base, CfrkWriter& w, Err& err)
-    {
-        if (nrows == 0) return true;
-        // An EMPTY read makes the reference walk over the bytes that FOLLOW it in its batch layout
-        // (kmer_device.cuh read_extent).  Raw file bytes have header lines there, so for such a
-        // (rare) span the records are first compacted into the reference layout: text, one
-        // separator, next text, ...
-        const RecordIndex* rip = &ri_in;
-        RecordIndex packed;
-        std::vector<char> pack_buf;
-        if (mode == CFRK_MODE_COMPAT &&
-            std::find(ri_in.length.begin(), ri_in.length.end(), 0) != ri_in.length.end()) {
+        size_t in_bytes = sp.n;
+        if (nrows > 0 && mode == CFRK_MODE_COMPAT && std::find(ri.length.begin(), ri.length.end(), 0) != ri.length.end()) {
+            // An EMPTY read makes the reference walk over the bytes that FOLLOW it in its batch layout
+            // (kmer_device.cuh read_extent).  Raw file bytes have header lines there, so for such a
+            // (rare) span the records are first compacted into the reference layout: text, one
+            // separator, next text, ...
             size_t total = 0;
-            for (int32_t l : ri_in.length) total += (size_t)l + 1;
-            pack_buf.resize(total + CFRK_PAD);
+            for (int32_t l : ri.length) total += (size_t)l + 1;
+            std::vector<char> pack_buf(total + CFRK_PAD);
+            std::vector<int64_t> pstart(ri.start.size());
             size_t wpos = 0;
-            for (size_t i = 0; i < ri_in.start.size(); i++) {
-                packed.start.push_back((int64_t)wpos);
-                packed.length.push_back(ri_in.length[i]);
-                memcpy(pack_buf.data() + wpos, h_in + ri_in.start[i], (size_t)ri_in.length[i]);
-                wpos += (size_t)ri_in.length[i];
+            for (size_t i = 0; i < ri.start.size(); i++) {
+                pstart[i] = (int64_t)wpos;
+                memcpy(pack_buf.data() + wpos, sp.buf + ri.start[i], (size_t)ri.length[i]);
+                wpos += (size_t)ri.length[i];
                 pack_buf[wpos++] = '\n';
             }
-            h_in = pack_buf.data();
             in_bytes = wpos;
-            rip = &packed;
+            if (!reserve(in_bytes, ri.start.size(), 0, err)) return false;
+            RF_CU(cudaMemcpyAsync(d_in, pack_buf.data(), in_bytes, cudaMemcpyHostToDevice, compute));
+            RF_CU(cudaMemsetAsync(d_in + in_bytes, 0, CFRK_PAD, compute));
+            RF_CU(cudaMemcpyAsync(d_start, pstart.data(), pstart.size() * 8, cudaMemcpyHostToDevice, compute));
+            RF_CU(cudaStreamSynchronize(compute));   // pageable sources
+            cur_bases = d_in; cur_start = d_start; cur_length = d_length;
         }
-        const RecordIndex& ri = *rip;
+        if (nrows > 0 && mode == CFRK_MODE_EXACT && !unwrap_scanned(in_bytes, ri.start.size(), err)) return false;
+        return count_rows(sp.index, in_bytes, ri.start.size(), nrows, k, mode, sparse, chunk_size, index_base, w, err);
+    }
+    // k > 8: sparse rows (exact semantics) of the span that upload_and_scan() left in HBM
+    bool count_scanned_sparse(const Span& sp, const RecordIndex& ri, size_t nrows, int k, CfrkWriter& w, Err& err)
+    {
         const size_t nreads = ri.start.size();
-        if (!reserve(in_bytes, nreads, 0, err)) return false;
-        RF_CU(cudaMemcpyAsync(d_in, h_in, in_bytes, cudaMemcpyHostToDevice, compute));
-        RF_CU(cudaMemsetAsync(d_in + in_bytes, 0, CFRK_PAD, compute));
-        RF_CU(cudaMemcpyAsync(d_start, ri.start.data(), nreads * 8, cudaMemcpyHostToDevice, compute));
-        RF_CU(cudaMemcpyAsync(d_length, ri.length.data(), nreads * 4, cudaMemcpyHostToDevice, compute));
-        cur_bases = d_in; cur_start = d_start; cur_length = d_length;
-        const bool ok = count_rows(in_bytes, nreads, nrows, k, mode, chunk_size, index_base, w, err);
-        RF_CU(cudaStreamSynchronize(compute));   // pack_buf / ri must outlive the copies
+        if (nrows > 0) {
+            if (!unwrap_scanned(sp.n, nreads, err)) return false;   // k > 8 is exact mode only
+            int64_t cap = 0;
+            for (int32_t l : ri.length) cap += std::max(0, l + 1 - k + 1);   // unwrapped text <= raw length + 1
+            cap = std::max<int64_t>(cap, 1);
+            if (!dev_pool(0, (nreads + 1) * 8, err) || !dev_pool(1, nreads * 4, err) || !dev_pool(2, (size_t)cap * 8, err) ||
+                !dev_pool(3, (size_t)cap * 4, err)) return false;
+            int64_t total = 0;
+            cudaError_t e = cfrk::launch_sparse(cur_bases, cfrk::FMT_ASCII, cur_start, cur_length, (int64_t)nreads, k,
+                                                static_cast<int64_t*>(d_pool[0]), static_cast<int32_t*>(d_pool[1]), d_pool[2], 8,
+                                                static_cast<uint32_t*>(d_pool[3]), cap, &total, compute);
+            if (e != cudaSuccess) { err.code = CFRK_ECUDA; err.msg = std::string("sparse path: ") + cudaGetErrorString(e); return false; }
+            if (!host_pool(0, (nrows + 1) * 8, err) || !host_pool(1, nrows * 4, err)) return false;
+            RF_CU(cudaMemcpyAsync(h_pool[0], d_pool[0], (nrows + 1) * 8, cudaMemcpyDeviceToHost, compute));
+            RF_CU(cudaMemcpyAsync(h_pool[1], d_pool[1], nrows * 4, cudaMemcpyDeviceToHost, compute));
+            RF_CU(cudaStreamSynchronize(compute));
+            const size_t used = (size_t)static_cast<int64_t*>(h_pool[0])[nrows];
+            if (!host_pool(2, std::max<size_t>(used, 1) * 8, err) || !host_pool(3, std::max<size_t>(used, 1) * 4, err)) return false;
+            RF_CU(cudaMemcpyAsync(h_pool[2], d_pool[2], used * 8, cudaMemcpyDeviceToHost, compute));
+            RF_CU(cudaMemcpyAsync(h_pool[3], d_pool[3], used * 4, cudaMemcpyDeviceToHost, compute));
+            RF_CU(cudaStreamSynchronize(compute));
+        }
+        if (!seq->wait_turn(sp.index)) { err.code = CFRK_EIO; err.msg = "aborted"; return false; }
+        bool ok = true;
+        if (nrows > 0)
+            ok = w.write_pairs<uint64_t>(static_cast<int64_t*>(h_pool[0]), static_cast<int32_t*>(h_pool[1]),
+                                         static_cast<uint64_t*>(h_pool[2]), static_cast<uint32_t*>(h_pool[3]), nrows, err);
+        seq->end_turn(sp.index);
         return ok;
     }
-    // d_in / d_start / d_length hold the span: kernels slice by slice, rows through the ring to the writer.
-    bool count_rows(size_t in_bytes, size_t nreads, size_t nrows, int k, int mode, int64_t chunk_size,
-                    int64_t index_base, CfrkWriter& w, Err& err)
+    // d_in / d_start / d_length hold the span: kernels slice by slice, rows through the ring to the
+    // writer (entered when it is this span's turn; the kernels of the first slices run before that).
+    bool count_rows(int64_t span_index, size_t in_bytes, size_t nreads, size_t nrows, int k, int mode, bool sparse,
+                    int64_t chunk_size, int64_t index_base, CfrkWriter& w, Err& err)
     {
+        bool have_turn = false;
+        const bool ok = count_rows_inner(span_index, in_bytes, nreads, nrows, k, mode, sparse, chunk_size, index_base, w, err,
+                                         have_turn);
+        if (ok && !have_turn && !seq->wait_turn(span_index)) { err.code = CFRK_EIO; err.msg = "aborted"; return false; }
+        if (ok) seq->end_turn(span_index);
+        return ok;     // on failure the run is aborted by the caller: nobody waits for this turn
+    }
+    bool count_rows_inner(int64_t span_index, size_t in_bytes, size_t nreads, size_t nrows, int k, int mode, bool sparse,
+                          int64_t chunk_size, int64_t index_base, CfrkWriter& w, Err& err, bool& have_turn)
+    {
+        if (nrows == 0) return true;
         const size_t bins = (size_t)1 << (2 * k), row_bytes = bins * 4;
+        const bool compact = sparse && k >= 5;   // (bin, count) pairs instead of dense rows over PCIe
         // ring slots: as large as the span needs, at most kSlotBytes
         if (!reserve(0, 0, std::max(row_bytes, std::min(kSlotBytes, nrows * row_bytes)), err)) return false;
         const size_t rpt = (size_t)cfrk::dense_reads_per_tile(k);
         size_t slice = std::max<size_t>(1, cap_rows / row_bytes);
         slice = std::max(rpt, slice / rpt * rpt);
-
+        slice = std::min(slice, (nrows + rpt - 1) / rpt * rpt);
         const size_t nslices = (nrows + slice - 1) / slice;
+        // compact slot layout: begin[slice+1] int64 | row_count[slice] int32 | keys | counts
+        const size_t per_row = std::min<size_t>(bins, (size_t)cfrk::kRefBlockThreads + 2);
+        const size_t tab_bytes = ((slice + 1) * 8 + slice * 4 + 15) & ~(size_t)15;
+        const size_t pair_cap = slice * per_row;
+        const size_t slot_bytes = tab_bytes + 2 * pair_cap * 4;
+        size_t scan_bytes = 0;
+        if (compact) {
+            cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (int64_t*)nullptr, (int64_t*)nullptr, (int64_t)slice + 1, compute);
+            if (!dev_pool(0, 2 * slot_bytes, err) || !dev_pool(1, scan_bytes + 16, err) || !host_pool(0, 2 * slot_bytes, err)) return false;
+        }
         for (size_t s = 0; s <= nslices; s++) {
             if (s < nslices) {
                 const int slot = (int)(s & 1);
@@ -575,17 +930,57 @@ struct Pipeline {
                                                    (int64_t)r0, (int64_t)r1, k, mode, chunk_size, index_base,
                                                    d_rows[slot], compute);
                 if (e != cudaSuccess) { err.code = CFRK_ECUDA; err.msg = std::string("dense_count_kernel: ") + cudaGetErrorString(e); return false; }
-                RF_CU(cudaEventRecord(done[slot], compute));
-                RF_CU(cudaStreamWaitEvent(copy, done[slot], 0));
-                RF_CU(cudaMemcpyAsync(h_rows[slot], d_rows[slot], (r1 - r0) * row_bytes, cudaMemcpyDeviceToHost, copy));
-                RF_CU(cudaEventRecord(drained[slot], copy));
+                if (compact) {
+                    char* db = static_cast<char*>(d_pool[0]) + (size_t)slot * slot_bytes;
+                    char* hb = static_cast<char*>(h_pool[0]) + (size_t)slot * slot_bytes;
+                    int64_t* nnz = reinterpret_cast<int64_t*>(db);
+                    int32_t* rcnt = reinterpret_cast<int32_t*>(db + (slice + 1) * 8);
+                    uint32_t* ck = reinterpret_cast<uint32_t*>(db + tab_bytes);
+                    uint32_t* cc = ck + pair_cap;
+                    const int64_t n = (int64_t)(r1 - r0);
+                    const unsigned g = (unsigned)std::min<int64_t>((n + 8) / 8 + 1, 148 * 8);
+                    row_nnz_kernel<<<g, 256, 0, compute>>>(d_rows[slot], n, (int)bins, nnz);
+                    cfrk::count_launch();
+                    cub::DeviceScan::ExclusiveSum(d_pool[1], scan_bytes, nnz, nnz, n + 1, compute);
+                    row_compact_kernel<<<g, 256, 0, compute>>>(d_rows[slot], n, (int)bins, nnz, ck, cc, rcnt);
+                    cfrk::count_launch();
+                    RF_CU(cudaGetLastError());
+                    RF_CU(cudaEventRecord(done[slot], compute));
+                    RF_CU(cudaStreamWaitEvent(copy, done[slot], 0));
+                    // the pairs are dense in [0, total): the table first, then exactly the pairs
+                    RF_CU(cudaMemcpyAsync(hb, db, tab_bytes, cudaMemcpyDeviceToHost, copy));
+                    RF_CU(cudaStreamSynchronize(copy));
+                    const size_t used = (size_t)reinterpret_cast<int64_t*>(hb)[n];
+                    if (used > pair_cap) { err.code = CFRK_ECUDA; err.msg = "sparse compaction overflow"; return false; }
+                    RF_CU(cudaMemcpyAsync(hb + tab_bytes, ck, used * 4, cudaMemcpyDeviceToHost, copy));
+                    RF_CU(cudaMemcpyAsync(hb + tab_bytes + pair_cap * 4, cc, used * 4, cudaMemcpyDeviceToHost, copy));
+                    RF_CU(cudaEventRecord(drained[slot], copy));
+                } else {
+                    RF_CU(cudaEventRecord(done[slot], compute));
+                    RF_CU(cudaStreamWaitEvent(copy, done[slot], 0));
+                    RF_CU(cudaMemcpyAsync(h_rows[slot], d_rows[slot], (r1 - r0) * row_bytes, cudaMemcpyDeviceToHost, copy));
+                    RF_CU(cudaEventRecord(drained[slot], copy));
+                }
             }
             if (s >= 1) {  // format slice s-1 while slice s is on the GPU
                 const size_t q = s - 1;
                 const int slot = (int)(q & 1);
                 const size_t r0 = q * slice, r1 = std::min(nrows, r0 + slice);
+                if (!have_turn) {
+                    if (!seq->wait_turn(span_index)) { err.code = CFRK_EIO; err.msg = "aborted"; return false; }
+                    have_turn = true;
+                }
                 RF_CU(cudaEventSynchronize(drained[slot]));
-                if (!w.write_rows(h_rows[slot], r1 - r0, err)) return false;
+                bool ok;
+                if (compact) {
+                    char* hb = static_cast<char*>(h_pool[0]) + (size_t)slot * slot_bytes;
+                    ok = w.write_pairs<uint32_t>(reinterpret_cast<int64_t*>(hb), reinterpret_cast<int32_t*>(hb + (slice + 1) * 8),
+                                                 reinterpret_cast<uint32_t*>(hb + tab_bytes),
+                                                 reinterpret_cast<uint32_t*>(hb + tab_bytes + pair_cap * 4), r1 - r0, err);
+                } else {
+                    ok = w.write_rows(h_rows[slot], r1 - r0, err);
+                }
+                if (!ok) return false;
             }
         }
         RF_CU(cudaStreamSynchronize(compute));
@@ -593,6 +988,9 @@ struct Pipeline {
     }
     ~Pipeline()
     {
+        cudaSetDevice(device);
+        if (compute) cudaStreamSynchronize(compute);
+        if (copy) cudaStreamSynchronize(copy);
         cudaFree(d_in); cudaFree(d_start); cudaFree(d_length); cudaFree(d_header);
         cudaFree(d_packed); cudaFree(d_start2); cudaFree(d_length2);
         for (int i = 0; i < 2; i++) {
@@ -601,123 +999,139 @@ struct Pipeline {
             if (done[i]) cudaEventDestroy(done[i]);
             if (drained[i]) cudaEventDestroy(drained[i]);
         }
+        for (int i = 0; i < 4; i++) {
+            cudaFree(d_pool[i]);
+            if (h_pool[i]) cudaFreeHost(h_pool[i]);
+        }
+        if (h_hdr) cudaFreeHost(h_hdr);
         if (compute) cudaStreamDestroy(compute);
         if (copy) cudaStreamDestroy(copy);
+        cudaGetLastError();
     }
 };
 
-bool run_file(const char* fasta, const char* out_path, int k, int nt, int64_t chunk_size, int flags, int device,
-              Err& err)
+// ------------------------------------------------------------------------------------------
+struct RunCfg {
+    int k, nt, mode, flags;
+    int64_t chunk_size;
+    std::vector<int> devices;
+};
+
+struct PassResult {
+    int64_t reads = 0;          // records seen by the pass
+    int64_t tail_off = -1;      // file offset of the header of the last read that opens a chunk
+    int64_t tail_index = -1;
+};
+
+// One pass over the input from `file_off`: every span is uploaded and scanned; with `rows` its reads are
+// counted and written.  first_read = global index of the first read of the pass.
+bool run_pass(Source& src, size_t file_off, int64_t first_read, bool rows, const RunCfg& cfg, CfrkWriter* w, Trace& tr,
+              PassResult& res, Err& err)
 {
-    const bool all_rows = flags & CFRK_RUN_ALL_ROWS;
-    const int mode = (flags & CFRK_RUN_EXACT) ? CFRK_MODE_EXACT : CFRK_MODE_COMPAT;
-    RF_CU(cudaSetDevice(device));
-
-    Trace tr;
-    tr.mark("cudaSetDevice");
-    // 64 MiB streaming window (+ as much headroom for carried records); small files get small
-    // pinned buffers: pinning costs ~0.5 ms/MiB and test-sized inputs should start instantly
+    if (!src.restart(file_off, err)) return false;
+    // 64 MiB streaming window; small inputs get small pinned buffers: pinning costs ~0.35 ms/MiB and
+    // test-sized inputs should start instantly
     size_t window = (size_t)64 << 20;
-    {
-        struct stat st0;
-        if (stat(fasta, &st0) == 0 && (size_t)st0.st_size < window)
-            window = std::max<size_t>((size_t)1 << 20, ((size_t)st0.st_size + 4095) & ~(size_t)4095);
-    }
-    const size_t kChunk = window, kHeadroom = window;
-    FastaStreamer rd;
-    if (!rd.open(fasta, kChunk, kHeadroom, err)) return false;
-    tr.mark("streamer open (pinned ring)");
-    CfrkWriter w;
-    if (!w.open(out_path, k, nt, flags & CFRK_RUN_SPARSE, err)) return false;
-    Pipeline gpu;
-    if (!gpu.init(err)) return false;
-    tr.mark("pipeline init");
+    if (const char* ev = getenv("CFRK_WINDOW_BYTES")) window = std::max<size_t>(4096, (size_t)atoll(ev));   // tests: many spans from small files
+    const size_t left = src.size_hint() > file_off ? src.size_hint() - file_off : 0;
+    if (left < window) window = std::max<size_t>((size_t)1 << 16, (left + 4095) & ~(size_t)4095);
+    const int nworkers = (int)cfg.devices.size() * 2;
+    const size_t spans_guess = left / window + 1;
+    const int nslots = (int)std::min<size_t>((size_t)nworkers + 1, spans_guess + 1);
+    SpanReader rd;
+    if (!rd.open(&src, window, std::max(2, nslots), err)) return false;
+    tr.mark("reader open (pinned buffers, window)", (size_t)nslots, window);
+    Sequencer seq;
+    seq.reset(first_read);
+    rd.start(file_off);
 
-    RecordIndex ri;
-    size_t carry = 0;            // bytes of unfinished records prepended to the current buffer
-    int64_t reads_done = 0;      // index of the first record of the current span
-    int64_t tail_off = -1;       // file offset of the header that opens the last (partial) chunk
-    size_t span_file_off = 0;    // file offset of data[0]
-    for (size_t i = 0;; i++) {
-        FastaStreamer::Buf* b = rd.acquire(i);
-        char* data = b->base + rd.headroom() - carry;
-        const size_t n = carry + b->n;
-        tr.mark("buffer acquired", n);
-        if (!gpu.upload_and_scan(data, n, b->eof, ri, err)) return false;
-        tr.mark("uploaded + scanned on device");
-        const size_t m = ri.start.size();  // records whose end is known
-
-        size_t keep_from;  // data[keep_from, n) goes in front of the next buffer
-        if (all_rows) {
-            // Rows for all complete records but a held-back tail: the record after the last row
-            // is needed for its spill into that row, and an empty read walks up to 1024+k bytes
-            // into its successors (kmer_device.cuh read_extent).  The held-back records are
-            // counted again at the head of the next span.
-            size_t nrows = m;
-            if (!b->eof) {
-                size_t held = 0;
-                while (nrows > 0 && (nrows == m || held < (size_t)cfrk::kRefBlockThreads + 64)) {
-                    nrows--;
-                    held += (size_t)ri.length[nrows] + 1;
+    std::mutex res_mu;
+    Err first_err;
+    std::atomic<bool> failed{false};
+    auto fail = [&](const Err& e) {
+        {
+            std::lock_guard<std::mutex> lk(res_mu);
+            if (!failed.exchange(true)) first_err = e;
+        }
+        seq.abort();
+        rd.stop();
+    };
+    const int nthreads = (int)std::min<size_t>((size_t)nworkers, std::max<size_t>(1, spans_guess));
+    std::vector<std::thread> th;
+    for (int t = 0; t < nthreads; t++) {
+        th.emplace_back([&, t] {
+            Err e;
+            Pipeline gpu;
+            if (!gpu.init(cfg.devices[(size_t)t % cfg.devices.size()], &seq, e)) { fail(e); return; }
+            RecordIndex ri;
+            for (;;) {
+                if (failed.load()) return;
+                Span* sp = rd.next();
+                if (!sp) return;
+                bool ok = gpu.upload_and_scan(sp->buf, sp->n, ri, e);
+                size_t nrows = 0;
+                int64_t before = 0;
+                if (ok) {
+                    nrows = (size_t)(std::lower_bound(ri.header.begin(), ri.header.end(), sp->rows_end) - ri.header.begin());
+                    ok = seq.get_reads_before(sp->index, &before);
+                    if (ok) seq.set_reads_before(sp->index + 1, before + (int64_t)nrows);
+                    else { e.code = CFRK_EIO; e.msg = "aborted"; }
                 }
+                tr.mark("span scanned (index, rows)", (size_t)sp->index, nrows);
+                if (ok) {
+                    std::lock_guard<std::mutex> lk(res_mu);
+                    res.reads = std::max(res.reads, before + (int64_t)nrows - first_read);
+                    // the last read of this span that opens a reference chunk
+                    if (nrows > 0) {
+                        const int64_t last = before + (int64_t)nrows - 1;
+                        const int64_t opener = last - last % cfg.chunk_size;
+                        if (opener >= before && opener > res.tail_index) {
+                            res.tail_index = opener;
+                            res.tail_off = (int64_t)(sp->file_off + ri.header[(size_t)(opener - before)]);
+                        }
+                    }
+                }
+                if (ok && rows) {
+                    ok = cfg.k > CFRK_CLI_DENSE_MAX_K
+                             ? gpu.count_scanned_sparse(*sp, ri, nrows, cfg.k, *w, e)
+                             : gpu.count_scanned(*sp, ri, nrows, cfg.k, cfg.mode, (cfg.flags & CFRK_RUN_SPARSE) != 0, cfg.chunk_size, before, *w, e);
+                    tr.mark("span rows written (index)", (size_t)sp->index);
+                }
+                rd.release(sp);
+                if (!ok) { fail(e); return; }
             }
-            if (k > CFRK_CLI_DENSE_MAX_K ? !gpu.count_scanned_sparse(n, ri, nrows, k, w, err)
-                                     : !gpu.count_scanned(data, n, ri, nrows, k, mode, chunk_size, reads_done, w, err)) return false;
-            reads_done += (int64_t)nrows;
-            tr.mark("rows counted + written");
-            keep_from = b->eof ? n : (m ? ri.header[nrows] : 0);
-        } else {
-            for (size_t r = 0; r < m; r++)
-                if ((reads_done + (int64_t)r) % chunk_size == 0) tail_off = (int64_t)(span_file_off + ri.header[r]);
-            reads_done += (int64_t)m;
-            keep_from = b->eof ? n : (ri.header.empty() ? 0 : ri.header[m]);
-        }
-        if (b->eof) { rd.release(i); break; }
-        carry = n - keep_from;
-        if (carry > rd.headroom()) {
-            err.code = CFRK_EFORMAT;
-            err.msg = "a single FASTA record (plus the records held back with it) exceeds the streaming window";
-            return false;
-        }
-        memcpy(rd.next_base(i) + rd.headroom() - carry, data + keep_from, carry);
-        span_file_off += keep_from;
-        rd.release(i);
+        });
     }
-
-    if (!all_rows) {
-        // reference: only the remainder chunk reaches the file; nothing when nS % chunkSize == 0
-        const int64_t nS = reads_done;
-        if (nS % chunk_size != 0 && tail_off >= 0) {
-            const size_t bytes = rd.file_size() - (size_t)tail_off;
-            char* h = nullptr;
-            if (cudaMallocHost(reinterpret_cast<void**>(&h), bytes + CFRK_PAD) != cudaSuccess) {
-                cudaGetLastError();
-                err.code = CFRK_ENOMEM; err.msg = "cudaMallocHost(tail chunk)"; return false;
-            }
-            size_t got = 0;
-            while (got < bytes) {
-                ssize_t r = pread(rd.fd(), h + got, bytes - got, (off_t)((size_t)tail_off + got));
-                if (r <= 0) break;
-                got += (size_t)r;
-            }
-            bool ok = got == bytes && gpu.upload_and_scan(h, bytes, true, ri, err);
-            if (got != bytes) { err.code = CFRK_EIO; err.msg = "short read of the tail chunk"; }
-            tr.mark("tail chunk scanned", bytes);
-            if (ok) ok = k > CFRK_CLI_DENSE_MAX_K
-                             ? gpu.count_scanned_sparse(bytes, ri, ri.start.size(), k, w, err)
-                             : gpu.count_scanned(h, bytes, ri, ri.start.size(), k, mode, chunk_size, (nS / chunk_size) * chunk_size, w, err);
-            tr.mark("tail rows counted + written");
-            cudaFreeHost(h);
-            if (!ok) return false;
-        }
-    }
+    for (auto& x : th) x.join();
+    rd.stop();
+    if (failed.load()) { err = first_err; return false; }
+    if (rd.error().code != CFRK_OK) { err = rd.error(); return false; }
     return true;
+}
+
+bool run_file(const char* fasta, const char* out_path, const RunCfg& cfg, Err& err)
+{
+    Trace tr;
+    Source src;
+    if (!src.open(fasta, err)) return false;
+    CfrkWriter w;
+    if (!w.open(out_path, cfg.k, cfg.nt, cfg.flags & CFRK_RUN_SPARSE, err)) return false;
+    tr.mark("opened");
+    PassResult res;
+    if (cfg.flags & CFRK_RUN_ALL_ROWS) return run_pass(src, 0, 0, true, cfg, &w, tr, res, err);
+    // reference: only the remainder chunk reaches the file; nothing when nS % chunkSize == 0
+    if (!run_pass(src, 0, 0, false, cfg, nullptr, tr, res, err)) return false;
+    tr.mark("pass 1 done (reads, tail offset)", (size_t)res.reads, (size_t)std::max<int64_t>(res.tail_off, 0));
+    const int64_t nS = res.reads;
+    if (nS % cfg.chunk_size == 0 || res.tail_off < 0) return true;
+    PassResult res2;
+    return run_pass(src, (size_t)res.tail_off, res.tail_index, true, cfg, &w, tr, res2, err);
 }
 
 }  // namespace
 
-extern "C" int cfrk_run_file(const char* fasta_path, const char* out_path, int k, int nt, int64_t chunk_size,
-                             int flags, int device)
+extern "C" int cfrk_run_file_multi(const char* fasta_path, const char* out_path, int k, int nt, int64_t chunk_size,
+                                   int flags, const int* devices, int n_devices)
 {
     Err err;
     if (!fasta_path || !out_path) { err.code = CFRK_EINVAL; err.msg = "null path"; }
@@ -727,15 +1141,27 @@ extern "C" int cfrk_run_file(const char* fasta_path, const char* out_path, int k
         err.msg = "k > 8: rows have 4^k bins; pass --sparse --exact (non-zero bins only, intended semantics)";
     }
     else if (chunk_size <= 0) { err.code = CFRK_EINVAL; err.msg = "chunkSize must be positive"; }
+    else if (n_devices < 1 || n_devices > 64 || !devices) { err.code = CFRK_EINVAL; err.msg = "need 1..64 devices"; }
     else {
         int ndev = 0;
-        if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
-            cudaGetLastError();
-            err.code = CFRK_ECUDA; err.msg = "no such CUDA device (this library has no CPU fallback)";
-        } else {
-            run_file(fasta_path, out_path, k, nt, chunk_size, flags, device, err);
+        if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); ndev = 0; }
+        RunCfg cfg;
+        cfg.k = k; cfg.nt = nt; cfg.flags = flags; cfg.chunk_size = chunk_size;
+        cfg.mode = (flags & CFRK_RUN_EXACT) ? CFRK_MODE_EXACT : CFRK_MODE_COMPAT;
+        bool ok = true;
+        for (int i = 0; i < n_devices; i++) {
+            if (devices[i] < 0 || devices[i] >= ndev) ok = false;
+            cfg.devices.push_back(devices[i]);
         }
+        if (!ok) { err.code = CFRK_ECUDA; err.msg = "no such CUDA device (this library has no CPU fallback)"; }
+        else run_file(fasta_path, out_path, cfg, err);
     }
     if (err.code != CFRK_OK) cfrk::set_last_error(err.msg);
     return err.code;
+}
+
+extern "C" int cfrk_run_file(const char* fasta_path, const char* out_path, int k, int nt, int64_t chunk_size,
+                             int flags, int device)
+{
+    return cfrk_run_file_multi(fasta_path, out_path, k, nt, chunk_size, flags, &device, 1);
 }

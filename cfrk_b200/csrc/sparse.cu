@@ -358,7 +358,7 @@ template <typename KeyT, int FMT, int E>
 __global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) sparse_short_kernel(
     const uint8_t* __restrict__ bases, const int64_t* __restrict__ start, const int32_t* __restrict__ length,
     int64_t nS, int k, const int64_t* __restrict__ row_begin, int32_t* __restrict__ row_count,
-    KeyT* __restrict__ keys, uint32_t* __restrict__ counts, bool group_split)
+    KeyT* __restrict__ keys, uint32_t* __restrict__ counts, bool group_split, int min_windows)
 {
     constexpr int WARPS = SparseCta<E>::WARPS;
     __shared__ uint32_t s_cw[WARPS][kStreamBlocks];
@@ -371,8 +371,8 @@ __global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) sparse_short_kernel(
     for (int64_t r = (int64_t)blockIdx.x * WARPS + warp; r < nS; r += nwarps) {
         const int len = length[r];
         const int nwin = len - k + 1;
-        if (nwin <= 0) { if (E == 4 && lane == 0) row_count[r] = 0; continue; }
-        if (nwin > 32 * E || (E > 4 && nwin <= 16 * E)) continue;  // another class, or the long path
+        if (nwin <= 0) { if (min_windows <= 1 && lane == 0) row_count[r] = 0; continue; }
+        if (nwin > 32 * E || nwin < min_windows) continue;  // another class, or the long path
         const int64_t s = start[r];
         const int a = (int)(s & 15);
         const int nblocks = (a + len + 15) >> 4;
@@ -393,6 +393,196 @@ __global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) sparse_short_kernel(
         const bool grouped = E == 8 && group_split && nwin <= kGroupedMaxWindows && k >= 2;
         const int nd = warp_count_read<KeyT, E>(st, a, k, grouped, ko, co, s_stage_k[warp], s_stage_c[warp]);
         if (lane == 0) row_count[r] = nd;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Reads of <= 144 windows (150-bp reads at k >= 7: the short-read configs): TWO reads per warp, 16 lanes
+// x 9 keys each.  The 256-slot network above sorts 139 windows with 46 % padding and 15 cross-lane
+// stages; 16 x 9 = 144 slots fit them with 3 %: in-lane 9-input network (25 comparators), then four
+// merge levels over 2, 4, 8, 16 lanes -- a mirrored compare, the remaining lane strides, and the lane's 9
+// keys (a bitonic sequence by then) through the same 25 comparators -- 10 cross-lane stages in all, and
+// both halves of the warp run the same instructions on their own read.  ncu, round 1: the grouped
+// 256-slot path issued 976 warp-instructions per 150-bp read on the integer pipe at 80 %; this one
+// issues about 420 (profiles/r2_notes.md).
+constexpr int kHalfE = 9;
+constexpr int kHalfSlots = 16 * kHalfE;              // 144
+constexpr int kHalfBlocks = 16;                      // 16-base blocks per half-warp stream
+
+template <typename KeyT>
+__device__ __forceinline__ void sort9(KeyT (&k)[kHalfE])
+{
+#define CFRK_CE(i, j) { const KeyT a_ = k[i], b_ = k[j]; k[i] = a_ < b_ ? a_ : b_; k[j] = a_ < b_ ? b_ : a_; }
+    CFRK_CE(0, 3) CFRK_CE(1, 7) CFRK_CE(2, 5) CFRK_CE(4, 8)
+    CFRK_CE(0, 7) CFRK_CE(2, 4) CFRK_CE(3, 8) CFRK_CE(5, 6)
+    CFRK_CE(0, 2) CFRK_CE(1, 3) CFRK_CE(4, 5) CFRK_CE(7, 8)
+    CFRK_CE(1, 4) CFRK_CE(3, 6) CFRK_CE(5, 7)
+    CFRK_CE(0, 1) CFRK_CE(2, 4) CFRK_CE(3, 5) CFRK_CE(6, 8)
+    CFRK_CE(2, 3) CFRK_CE(4, 5) CFRK_CE(6, 7)
+    CFRK_CE(1, 2) CFRK_CE(3, 4) CFRK_CE(5, 6)
+#undef CFRK_CE
+}
+
+// 16 lanes x 9 keys, blocked layout (lane hl holds elements 9*hl .. 9*hl+8), ascending; both halves of
+// the warp at once (lane masks < 16 never cross the halves)
+template <typename KeyT>
+__device__ __forceinline__ void half_sort(KeyT (&key)[kHalfE])
+{
+    const int hl = threadIdx.x & 15;
+    sort9<KeyT>(key);
+#pragma unroll
+    for (int m = 2; m <= 16; m <<= 1) {
+        {   // mirrored compare: element e with element 8-e of lane hl ^ (m-1)
+            const bool upper = (hl & (m >> 1)) != 0;
+            KeyT other[kHalfE];
+#pragma unroll
+            for (int e = 0; e < kHalfE; e++) other[e] = __shfl_xor_sync(0xffffffffu, key[kHalfE - 1 - e], m - 1);
+#pragma unroll
+            for (int e = 0; e < kHalfE; e++) key[e] = keep_minmax<KeyT>(key[e], other[e], upper);
+        }
+#pragma unroll
+        for (int st = m >> 2; st >= 1; st >>= 1) {
+            const bool upper = (hl & st) != 0;
+#pragma unroll
+            for (int e = 0; e < kHalfE; e++) {
+                const KeyT other = __shfl_xor_sync(0xffffffffu, key[e], st);
+                key[e] = keep_minmax<KeyT>(key[e], other, upper);
+            }
+        }
+        sort9<KeyT>(key);
+    }
+}
+
+// sorted keys of one half (first nvalid slots real) -> (key, count) pairs; both halves run in lockstep
+// (every shuffle is a full-mask shuffle of width 16).  Returns the number of pairs of this half.
+template <typename KeyT>
+__device__ __forceinline__ int half_rle_store(const KeyT (&key)[kHalfE], int nvalid, KeyT* __restrict__ keys_out,
+                                              uint32_t* __restrict__ counts_out, KeyT* __restrict__ stage_k,
+                                              uint32_t* __restrict__ stage_c)
+{
+    constexpr int E = kHalfE;
+    const int hl = threadIdx.x & 15;
+    const int vpos0 = hl * E;
+    const int nlive = min(E, max(0, nvalid - vpos0));
+    const uint32_t live = (1u << nlive) - 1u;
+    KeyT prev = __shfl_up_sync(0xffffffffu, key[E - 1], 1, 16);
+    uint32_t heads = 0;
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const bool head = (live >> e & 1u) && ((e == 0 && hl == 0) || key[e] != prev);
+        heads |= head ? (1u << e) : 0u;
+        prev = key[e];
+    }
+    // common case: every key of BOTH reads is distinct -> element v goes to slot v with count 1
+    if (__all_sync(0xffffffffu, heads == live)) {
+#pragma unroll
+        for (int e = 0; e < E; e++) stage_k[vpos0 + e] = key[e];      // stride 9 words: conflict-free
+        __syncwarp();
+        for (int i = hl; i < nvalid; i += 16) {
+            keys_out[i] = stage_k[i];
+            counts_out[i] = 1u;
+        }
+        __syncwarp();
+        return nvalid;
+    }
+    const int hc = __popc(heads);
+    int inc = hc;
+#pragma unroll
+    for (int d = 1; d < 16; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, inc, d, 16);
+        if (hl >= d) inc += o;
+    }
+    int off = inc - hc;
+    const int total = __shfl_sync(0xffffffffu, inc, 15, 16);
+    // position of the next head after this lane: suffix-min of every lane's first head
+    int first = heads ? vpos0 + (__ffs(heads) - 1) : nvalid;
+    int nxt = __shfl_down_sync(0xffffffffu, first, 1, 16);
+    if (hl == 15) nxt = nvalid;
+#pragma unroll
+    for (int d = 1; d < 16; d <<= 1) {
+        const int o = __shfl_down_sync(0xffffffffu, nxt, d, 16);
+        if (hl + d < 16) nxt = min(nxt, o);
+    }
+    nxt = min(nxt, nvalid);
+    uint32_t cnt[E];
+#pragma unroll
+    for (int e = E - 1; e >= 0; e--) {
+        cnt[e] = (uint32_t)(nxt - (vpos0 + e));
+        if (heads & (1u << e)) nxt = vpos0 + e;
+    }
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        if (heads & (1u << e)) {
+            stage_k[off] = key[e];
+            stage_c[off] = cnt[e];
+            off++;
+        }
+    }
+    __syncwarp();
+    for (int i = hl; i < total; i += 16) {
+        keys_out[i] = stage_k[i];
+        counts_out[i] = stage_c[i];
+    }
+    __syncwarp();
+    return total;
+}
+
+template <typename KeyT, int FMT>
+__global__ void __launch_bounds__(kSparseWarps * 32) sparse_half_kernel(
+    const uint8_t* __restrict__ bases, const uint16_t* __restrict__ packed_valid, const int64_t* __restrict__ start,
+    const int32_t* __restrict__ length, int64_t nS, int k, const int64_t* __restrict__ row_begin,
+    int32_t* __restrict__ row_count, KeyT* __restrict__ keys, uint32_t* __restrict__ counts)
+{
+    constexpr int WARPS = kSparseWarps;
+    __shared__ uint32_t s_cw[WARPS][2][kHalfBlocks];
+    __shared__ __align__(4) uint16_t s_vh[WARPS][2][kHalfBlocks + 4];
+    __shared__ __align__(16) KeyT s_stage_k[WARPS][2][kHalfSlots];
+    __shared__ uint32_t s_stage_c[WARPS][2][kHalfSlots];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int h = lane >> 4, hl = lane & 15;
+    WarpStream st{s_cw[warp][h], s_vh[warp][h]};
+    const BasesRef src{bases, packed_valid};
+    const int64_t nwarps = (int64_t)gridDim.x * WARPS;
+    const int64_t npairs = (nS + 1) >> 1;
+    for (int64_t pair = (int64_t)blockIdx.x * WARPS + warp; pair < npairs; pair += nwarps) {
+        const int64_t r = 2 * pair + h;
+        const bool in = r < nS;
+        const int len = in ? length[r] : 0;
+        const int nwin = len - k + 1;
+        if (in && nwin <= 0 && hl == 0) row_count[r] = 0;
+        const bool mine = in && nwin > 0 && nwin <= kHalfSlots;     // longer reads: the other classes
+        if (!__any_sync(0xffffffffu, mine)) continue;
+        const int64_t s = mine ? start[r] : 0;
+        const int a = (int)(s & 15);
+        const int nblocks = mine ? (a + len + 15) >> 4 : 0;          // <= 12 for len <= 143 + 31
+        __syncwarp();
+        {
+            uint32_t c = 0, v = 0;
+            if (hl < nblocks) {
+                const uint4 raw = load_block<FMT>(src, (s >> 4) + hl);
+                if (FMT == FMT_PACKED) { c = raw.x; v = raw.y; }
+                else encode16<FMT == FMT_PACKED ? FMT_CODES : FMT>(raw, c, v);
+                v &= from_pos(max(0, a - 16 * hl)) & ~from_pos(min(16, max(0, a + len - 16 * hl)));
+            }
+            st.cw[hl] = c;
+            st.vh[hl ^ 1] = (uint16_t)v;
+            if (hl < 4) st.vh[kHalfBlocks + hl] = 0;
+        }
+        __syncwarp();
+        KeyT key[kHalfE];
+        uint32_t valid = extract_windows<KeyT, kHalfE>(st, a + hl * kHalfE, k, key);
+        if (!mine) {
+            valid = 0;
+#pragma unroll
+            for (int e = 0; e < kHalfE; e++) key[e] = KeyMax<KeyT>::value;
+        }
+        int nvalid = __popc(valid);
+#pragma unroll
+        for (int d = 8; d >= 1; d >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, d);
+        half_sort<KeyT>(key);
+        const int64_t rb = mine ? row_begin[r] : 0;
+        const int nd = half_rle_store<KeyT>(key, nvalid, keys + rb, counts + rb, s_stage_k[warp][h], s_stage_c[warp][h]);
+        if (mine && hl == 0) row_count[r] = nd;
     }
 }
 
@@ -1219,9 +1409,20 @@ static cudaError_t sparse_impl(const void* bases, const int64_t* start, const in
         const uint8_t* b8 = static_cast<const uint8_t*>(bases);
         const char* gev = getenv("CFRK_SPARSE_GROUPS");          // 0: always the full network (A/B measurements)
         const bool group_split = !(gev && atoi(gev) == 0);
-        sparse_short_kernel<KeyT, FMT, 4><<<grid, SparseCta<4>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts, group_split);
-        sparse_short_kernel<KeyT, FMT, 8><<<grid, SparseCta<8>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts, group_split);
-        sparse_short_kernel<KeyT, FMT, 16><<<grid, SparseCta<16>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts, group_split);
+        const char* hev = getenv("CFRK_SPARSE_HALF");            // 0: round-1 classes (one warp per read for every length)
+        const bool use_half = !(hev && atoi(hev) == 0);
+        if (use_half) {
+            // reads of <= 144 windows: two per warp (sparse_half_kernel); 145..256 and 257..512: one warp each
+            const int64_t hctas = ((nS + 1) / 2 + kSparseWarps - 1) / kSparseWarps;
+            const unsigned hgrid = (unsigned)(hctas < (int64_t)num_sms * 8 ? hctas : (int64_t)num_sms * 8);
+            sparse_half_kernel<KeyT, FMT><<<hgrid, kSparseWarps * 32, 0, st>>>(b8, nullptr, start, length, nS, k, row_begin, row_count, keys, counts);
+            sparse_short_kernel<KeyT, FMT, 8><<<grid, SparseCta<8>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts, group_split, kHalfSlots + 1);
+            sparse_short_kernel<KeyT, FMT, 16><<<grid, SparseCta<16>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts, group_split, 257);
+        } else {
+            sparse_short_kernel<KeyT, FMT, 4><<<grid, SparseCta<4>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts, group_split, 1);
+            sparse_short_kernel<KeyT, FMT, 8><<<grid, SparseCta<8>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts, group_split, 129);
+            sparse_short_kernel<KeyT, FMT, 16><<<grid, SparseCta<16>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts, group_split, 257);
+        }
         count_launch(); count_launch(); count_launch();
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }

@@ -192,13 +192,26 @@ int cfrk_scan_fasta_device(const void *d_bytes, int64_t n, int is_final, int64_t
                                   src/main.cu:51,56)                                    */
 
 /*
- * cfrk <fasta> <out> <k> [nt] [chunkSize] as a function: pinned double-buffered FASTA
- * streamer -> GPU record scan + count -> multi-threaded .cfrk writer.  nt = host writer threads.
+ * cfrk <fasta> <out> <k> [nt] [chunkSize] as a function: pinned multi-buffered FASTA
+ * streamer (plain or gzip; records of any size) -> GPU record scan + count -> multi-threaded .cfrk
+ * writer.  nt = host writer threads.  CFRK_EIO on a read error or a file truncated under the run.
  * k <= 8: dense rows (reference format).  k = 9..31 needs CFRK_RUN_SPARSE | CFRK_RUN_EXACT:
  * each row lists "kmer_index:count " for the k-mers that occur, in increasing index order.
  */
 int cfrk_run_file(const char *fasta_path, const char *out_path, int k, int nt,
                   int64_t chunk_size, int flags, int device);
+
+/*
+ * The same over several GPUs of one box (the reference fans its chunks out over devCount pthreads --
+ * all on one GPU -- and prints them in order, src/main.cu:208-230,277-289,303-305).  The file is cut
+ * into spans at header lines; two host threads per listed device take spans in file order (each with
+ * its own streams, device buffers and pinned row ring); per-read rows are gathered on the host and
+ * reach the output in read order, byte-identical to the one-GPU run.  No collective: reads are
+ * independent, and the compat spill across a span boundary is covered by each span's lookahead.
+ * The input may be gzip-compressed (detected by its magic bytes).
+ */
+int cfrk_run_file_multi(const char *fasta_path, const char *out_path, int k, int nt,
+                        int64_t chunk_size, int flags, const int *devices, int n_devices);
 
 #ifdef __cplusplus
 }

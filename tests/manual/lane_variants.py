@@ -46,7 +46,7 @@ def pad(raw, fill):
 def parity(k):
     ok = True
     texts = [t for _, t, _ in fx.EDGE_SET]
-    big = "".join(texts)
+    big = "".join(t if t.endswith("\n") else t + "\n" for t in texts)   # (a '>' may not land inside a line)
     for mode, omode in ((cf.MODE_COMPAT, ob.MODE_COMPAT), (cf.MODE_EXACT, ob.MODE_EXACT)):
         # codes layout (reference batch), whole edge set in one batch
         data, start, length = ob.parse_fasta(text=big)

@@ -79,6 +79,33 @@ def test_window_count_boundaries_and_long_reads(k, key_bytes):
     check(data, start, length, k, key_bytes)
 
 
+@pytest.mark.parametrize("k,key_bytes", [(7, 4), (12, 4), (16, 4), (12, 8), (21, 8), (31, 8)])
+def test_two_reads_per_warp_class(k, key_bytes):
+    """reads of <= 144 windows go two to a warp (sparse_half_kernel: 16 lanes x 9 keys each); window counts around
+    the class border (143..146 -> the one-warp classes), odd read count (a half without a read), pairs of unequal
+    length, reads without a valid window, low-complexity reads (the general run-length path) and all-distinct
+    reads (its fast path) in one launch"""
+    import random
+    rng = random.Random(31 * k + key_bytes)
+    reads = []
+    for nwin in [1, 2, 8, 9, 10, 17, 18, 19, 63, 64, 100, 135, 139, 143, 144, 145, 146, 200, 256, 257, 300, 143, 144]:
+        L = nwin + k - 1
+        reads.append("".join(rng.choice("ACGT") for _ in range(L)))
+    reads += ["A" * 150, "T" * (143 + k), "ACG" * 50, "N" * 150, "ACGT" * 30 + "N" + "TTGCA" * 6, "", "AC",
+              "".join(rng.choice("ACGT") for _ in range(150)), ("AC" * 40 + "N") * 2]
+    for _ in range(600):
+        L = rng.choice([150, 151, 100, 144 + k - 1, 145 + k - 1, rng.randint(k, 175)])
+        s_ = [rng.choice("ACGT") for _ in range(L)]
+        if rng.random() < 0.3:
+            s_[rng.randrange(L)] = "N"
+        reads.append("".join(s_))
+    if len(reads) % 2 == 0:
+        reads.append("".join(rng.choice("ACGT") for _ in range(150)))     # odd count: the last warp has one read
+    text = "".join(f">r{i}\n{r}\n" for i, r in enumerate(reads))
+    data, start, length = ob.parse_fasta(text=text)
+    check(data, start, length, k, key_bytes)
+
+
 @pytest.mark.parametrize("k,key_bytes,batch", [(16, 4, 4000), (18, 8, 25000), (31, 8, 1)])
 def test_long_rows_in_many_batches(k, key_bytes, batch, monkeypatch):
     """the long-row scratch is bounded by batches of rows: force tiny batches (several rows per batch,
