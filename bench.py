@@ -66,7 +66,7 @@ def parse_args():
     ap.add_argument("--e2e-reads", type=int, default=8192)
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--mode", default="compat", choices=["compat", "exact"])
-    ap.add_argument("--fmt", default="ascii", choices=["ascii", "codes", "packed"],
+    ap.add_argument("--fmt", default="packed", choices=["ascii", "codes", "packed"],
                     help="packed: every step encodes the ASCII bases once (2-bit + validity) and counts every k from that")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")

@@ -8,7 +8,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libcfrk_b200.so")
 # every symbol include/cfrk_b200.h declares (tests/test_abi.py checks header and library agree)
 SYMBOLS = [
     "cfrk_version", "cfrk_last_error", "cfrk_device_count", "cfrk_launch_count", "cfrk_release", "cfrk_free_host",
-    "cfrk_count_dense_host", "cfrk_count_dense_device", "cfrk_count_dense_packed_device",
+    "cfrk_count_dense_host", "cfrk_set_host_threads", "cfrk_count_dense_device", "cfrk_count_dense_packed_device",
     "cfrk_dense_reads_per_tile",
     "cfrk_encode_2bit_device", "cfrk_global_hist_device", "cfrk_count_sparse_device", "cfrk_scan_fasta_device",
     "cfrk_run_file", "cfrk_run_file_multi",
@@ -32,6 +32,8 @@ def load():
     L.cfrk_device_count.restype = i32
     L.cfrk_launch_count.restype = C.c_uint64
     L.cfrk_release.restype = i32
+    L.cfrk_set_host_threads.argtypes = [i32]
+    L.cfrk_set_host_threads.restype = None
     L.cfrk_free_host.argtypes = [vp]
     L.cfrk_free_host.restype = None
     L.cfrk_dense_reads_per_tile.argtypes = [i32]

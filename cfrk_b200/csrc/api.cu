@@ -7,6 +7,8 @@
 //   * rows leave the device through a two-slot ring so that the device->host copy of slice i
 //     overlaps the kernel of slice i+1 (the reference does one synchronous cudaMemcpy of the
 //     whole Freq, src/kmer_main.cu:116),
+//   * part of the rows is written by host threads from index lists (HostExpand below), so that the
+//     PCIe link is not the only path into the caller's buffer,
 //   * errors are returned, not printed.
 #include "../../include/cfrk_b200.h"
 #include "kernels.h"
@@ -14,7 +16,16 @@
 #include "internal.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
+#include <functional>
+#include <thread>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -58,6 +69,12 @@ struct HostCtx {
     void* d_bases = nullptr;  size_t cap_bases = 0;
     int64_t* d_start = nullptr; int32_t* d_length = nullptr; size_t cap_reads = 0;
     int32_t* d_ring[2] = {nullptr, nullptr}; size_t cap_ring = 0;
+    // host-expanded part of a call: index lists (device + pinned mirror), their offsets, timing events
+    uint32_t* d_idx = nullptr; size_t cap_idx = 0;
+    int64_t* d_ibeg = nullptr; size_t cap_ibeg = 0;
+    uint32_t* h_idx = nullptr; size_t cap_hidx = 0;
+    cudaEvent_t idx_ready = nullptr, t0 = nullptr, t1 = nullptr;
+    double dma_frac[CFRK_DENSE_MAX_K + 1] = {0};   // share of the rows that goes through the DMA engine, per k (adaptive)
 
     void release()
     {
@@ -65,6 +82,11 @@ struct HostCtx {
         cudaSetDevice(device);
         cudaFree(d_bases); cudaFree(d_start); cudaFree(d_length);
         cudaFree(d_ring[0]); cudaFree(d_ring[1]);
+        cudaFree(d_idx); cudaFree(d_ibeg);
+        if (h_idx) cudaFreeHost(h_idx);
+        if (idx_ready) cudaEventDestroy(idx_ready);
+        if (t0) cudaEventDestroy(t0);
+        if (t1) cudaEventDestroy(t1);
         for (int i = 0; i < 2; i++) {
             if (done[i]) cudaEventDestroy(done[i]);
             if (drained[i]) cudaEventDestroy(drained[i]);
@@ -114,6 +136,9 @@ int ensure_ctx(int device, HostCtx** out)
             CU(cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&c->drained[i], cudaEventDisableTiming));
         }
+        CU(cudaEventCreateWithFlags(&c->idx_ready, cudaEventDisableTiming));
+        CU(cudaEventCreate(&c->t0));
+        CU(cudaEventCreate(&c->t1));
         c->device = device;
     }
     *out = c;
@@ -130,6 +155,169 @@ int grow(T*& p, size_t& cap, size_t need)
     if (e != cudaSuccess) { t_err = std::string("cudaMalloc: ") + cudaGetErrorString(e); return CFRK_ENOMEM; }
     cap = want;
     return CFRK_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side of the host-buffer operator.  The output of kmer_main's contract is 4^k int32 PER READ in
+// HOST memory (256 KiB per 150-bp read at k = 8, of which <= 150 words are not zero) and a PCIe Gen5
+// link moves 55 GB/s: with every row crossing the bus the operator ran at 0.12 Gbases/s on a k = 4..8
+// sweep, below a 16-thread CPU counter.  So the rows are split: one share is written by
+// the GPU's DMA engine as before, for the other share only the k-mer index of every visited window
+// crosses the bus (dense_index.cu: 4 bytes per window) and `nt` host threads write those rows -- zeros
+// and counts in one pass of streaming stores, no read-for-ownership.  The split adapts per k to
+// whichever side finishes first.  The k-mers are still computed on the GPU only.
+std::atomic<int> g_host_threads{-2};    // -2: not configured yet
+
+int host_threads()
+{
+    int n = g_host_threads.load();
+    if (n == -2) {
+        const char* e = getenv("CFRK_HOST_THREADS");
+        n = e ? atoi(e) : (int)std::min<unsigned>(std::max(1u, std::thread::hardware_concurrency()), 16u);
+        if (n < 0) n = 0;
+        g_host_threads.store(n);
+    }
+    return n < 0 ? 0 : n;
+}
+
+inline int64_t visited_windows(int len, int k, int mode)
+{
+    const int v = mode == CFRK_MODE_COMPAT ? std::min(len - 1, cfrk::kRefBlockThreads) : len - k + 1;
+    return v > 0 ? v : 0;
+}
+
+class HostPool {
+public:
+    void run(int nparts, const std::function<void(int)>& fn)
+    {
+        std::unique_lock<std::mutex> lk(mu_);
+        while ((int)th_.size() < nparts) {
+            const int id = (int)th_.size();
+            th_.emplace_back([this, id] { loop(id); });
+        }
+        busy_cv_.wait(lk, [&] { return fn_ == nullptr; });     // one batch at a time (several caller threads share the pool)
+        fn_ = &fn; nparts_ = nparts; pending_ = nparts; gen_++;
+        cv_.notify_all();
+        done_cv_.wait(lk, [&] { return pending_ == 0; });
+        fn_ = nullptr;
+        busy_cv_.notify_one();
+    }
+
+private:
+    void loop(int id)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)>* fn;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (id >= nparts_) continue;
+                fn = fn_;
+            }
+            (*fn)(id);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--pending_ == 0) done_cv_.notify_all();
+            }
+        }
+    }
+    std::vector<std::thread> th_;    // never joined: the pool lives as long as the process
+    std::mutex mu_;
+    std::condition_variable cv_, done_cv_, busy_cv_;
+    const std::function<void(int)>* fn_ = nullptr;
+    int nparts_ = 0, pending_ = 0;
+    uint64_t gen_ = 0;
+};
+HostPool* g_pool = nullptr;
+std::once_flag g_pool_once;
+
+inline void stream_zero_line(int32_t* p)      // 64 bytes, 64-byte aligned
+{
+#if defined(__SSE2__)
+    const __m128i z = _mm_setzero_si128();
+    _mm_stream_si128(reinterpret_cast<__m128i*>(p), z);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(p) + 1, z);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(p) + 2, z);
+    _mm_stream_si128(reinterpret_cast<__m128i*>(p) + 3, z);
+#else
+    memset(p, 0, 64);
+#endif
+}
+
+// one row from its index list: bins[v]++ for every valid entry; returns the number of invalid entries
+// (compat: they are owed to the previous row's last bin).  Rows of >= 16 KiB are written in one
+// streaming pass (sorted indices, zero lines with non-temporal stores, the few lines that hold counts
+// built in a register buffer); smaller rows are cleared and counted in cache.
+int expand_one(const uint32_t* idx, int64_t n, size_t fourk, int32_t* row, uint32_t* tmp)
+{
+    int invalid = 0;
+    const bool aligned = (reinterpret_cast<uintptr_t>(row) & 63) == 0;
+    if (fourk < 4096 || !aligned) {
+        memset(row, 0, fourk * 4);
+        for (int64_t t = 0; t < n; t++) {
+            const uint32_t v = idx[t];
+            if (v < fourk) row[v]++; else invalid++;
+        }
+        return invalid;
+    }
+    int64_t m = 0;
+    for (int64_t t = 0; t < n; t++) {
+        const uint32_t v = idx[t];
+        if (v < fourk) tmp[m++] = v; else invalid++;
+    }
+    std::sort(tmp, tmp + m);
+    size_t line = 0;                        // next 16-word line to write
+    const size_t nlines = fourk / 16;
+    int64_t i = 0;
+    while (i < m) {
+        const size_t l = tmp[i] >> 4;
+        for (; line < l; line++) stream_zero_line(row + line * 16);
+        alignas(64) int32_t buf[16] = {0};
+        while (i < m && (tmp[i] >> 4) == l) buf[tmp[i++] & 15]++;
+#if defined(__SSE2__)
+        for (int q = 0; q < 4; q++)
+            _mm_stream_si128(reinterpret_cast<__m128i*>(row + l * 16) + q, _mm_load_si128(reinterpret_cast<const __m128i*>(buf) + q));
+#else
+        memcpy(row + l * 16, buf, 64);
+#endif
+        line = l + 1;
+    }
+    for (; line < nlines; line++) stream_zero_line(row + line * 16);
+    return invalid;
+}
+
+// rows [nD, nS) of freq_out from the index lists (h_idx, ibeg relative to read nD)
+void expand_rows(const uint32_t* h_idx, const int64_t* ibeg, int64_t nD, int64_t nS, size_t fourk, int mode,
+                 int32_t* freq_out, int nt)
+{
+    std::call_once(g_pool_once, [] { g_pool = new HostPool(); });
+    const int64_t nH = nS - nD;
+    const int parts = (int)std::max<int64_t>(1, std::min<int64_t>(nt, nH / 4));
+    const std::function<void(int)> fn = [&](int p) {
+        const int64_t a = nH * p / parts, b = nH * (p + 1) / parts;
+        std::vector<uint32_t> tmp((size_t)cfrk::kRefBlockThreads + 64);
+        for (int64_t i = a; i < b; i++) {
+            const int64_t n = ibeg[i + 1] - ibeg[i];
+            if ((size_t)n > tmp.size()) tmp.resize((size_t)n);
+            expand_one(h_idx + ibeg[i], n, fourk, freq_out + (size_t)(nD + i) * fourk, tmp.data());
+        }
+#if defined(__SSE2__)
+        _mm_sfence();
+#endif
+        if (mode == CFRK_MODE_COMPAT) {
+            // spill: the invalid windows of read i+1 land in the last bin of row i (src/kmer_kernel.cu:84-87).
+            // Row nD-1 is the GPU's (it scans read nD itself); the thread that owns row i looks at list i+1.
+            for (int64_t i = a; i < b; i++) {
+                if (i + 1 >= nH) break;
+                int inv = 0;
+                for (int64_t t = ibeg[i + 1]; t < ibeg[i + 2]; t++) inv += h_idx[t] >= fourk;
+                if (inv) freq_out[(size_t)(nD + i) * fourk + fourk - 1] += inv;
+            }
+        }
+    };
+    g_pool->run(parts, fn);
 }
 
 int check_common(int fmt, int k, int kmax, int mode)
@@ -289,10 +477,40 @@ int cfrk_count_dense_host(const void* bases, int fmt, const int64_t* start, cons
     const size_t fourk = (size_t)1 << (2 * k);
     const size_t row_bytes = fourk * 4;
     const int rpt = cfrk::dense_reads_per_tile(k);
+
+    // ---- split: rows [0, nD) leave as dense rows through the DMA engine, rows [nD, nS) as index lists
+    // that host threads expand (see HostExpand above).  Not for tiny rows / batches (nothing to win) and
+    // not when a compat batch holds an empty read (its walk over the following reads stays on the GPU).
+    const int nt = host_threads();
+    int64_t nD = nS;
+    std::vector<int64_t> ibeg;
+    if (nt > 0 && row_bytes >= 4096 && (size_t)nS * row_bytes >= ((size_t)32 << 20)) {
+        bool ok = true;
+        if (mode == CFRK_MODE_COMPAT)
+            for (int64_t i = 0; i < nS && ok; i++) ok = length[i] != 0;
+        if (ok) {
+            double f = c.dma_frac[k];
+            if (f <= 0.0) f = 0.40;
+            nD = (int64_t)((double)nS * f);
+            nD = std::max<int64_t>(0, std::min<int64_t>(nS, nD / rpt * rpt));
+            if (nS - nD < 64) nD = nS;
+        }
+    }
+    const int64_t nH = nS - nD;                     // rows expanded on the host
+    int64_t idx_total = 0;
+    if (nH > 0) {
+        ibeg.resize((size_t)nH + 1);
+        for (int64_t i = 0; i < nH; i++) {
+            ibeg[(size_t)i] = idx_total;
+            idx_total += visited_windows(length[nD + i], k, mode);
+        }
+        ibeg[(size_t)nH] = idx_total;
+    }
+
     int64_t slice = (int64_t)std::max<size_t>(1, kRingSlotBytes / row_bytes);
     slice = std::max<int64_t>(rpt, slice / rpt * rpt);
-    if (slice > nS) slice = (nS + rpt - 1) / rpt * rpt;
-    const int64_t nslices = (nS + slice - 1) / slice;
+    if (slice > nD) slice = std::max<int64_t>(rpt, (nD + rpt - 1) / rpt * rpt);
+    const int64_t nslices = nD > 0 ? (nD + slice - 1) / slice : 0;
 
     if ((rc = grow(c.d_bases, c.cap_bases, (size_t)nN + CFRK_PAD))) return rc;
     {
@@ -308,8 +526,8 @@ int cfrk_count_dense_host(const void* bases, int fmt, const int64_t* start, cons
             c.cap_reads = want;
         }
     }
-    {
-        size_t need = (size_t)std::min<int64_t>(slice, nS) * row_bytes;
+    if (nD > 0) {
+        size_t need = (size_t)std::min<int64_t>(slice, nD) * row_bytes;
         if (need > c.cap_ring) {
             cudaFree(c.d_ring[0]); cudaFree(c.d_ring[1]); c.d_ring[0] = c.d_ring[1] = nullptr; c.cap_ring = 0;
             const int slots = nslices > 1 ? 2 : 1;
@@ -326,6 +544,20 @@ int cfrk_count_dense_host(const void* bases, int fmt, const int64_t* start, cons
             }
         }
     }
+    if (nH > 0) {
+        if ((rc = grow(c.d_idx, c.cap_idx, (size_t)std::max<int64_t>(idx_total, 1) * 4))) return rc;
+        if ((rc = grow(c.d_ibeg, c.cap_ibeg, ((size_t)nH + 1) * 8))) return rc;
+        const size_t need = (size_t)std::max<int64_t>(idx_total, 1) * 4;
+        if (need > c.cap_hidx) {
+            if (c.h_idx) cudaFreeHost(c.h_idx);
+            c.h_idx = nullptr; c.cap_hidx = 0;
+            if (cudaMallocHost(reinterpret_cast<void**>(&c.h_idx), need + need / 4) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(CFRK_ENOMEM, "cudaMallocHost(index lists)");
+            }
+            c.cap_hidx = need + need / 4;
+        }
+    }
 
     CU(cudaMemcpyAsync(c.d_bases, bases, (size_t)nN, cudaMemcpyHostToDevice, c.compute));
     // the kernel loads whole 16-byte blocks: define the tail
@@ -333,9 +565,18 @@ int cfrk_count_dense_host(const void* bases, int fmt, const int64_t* start, cons
     CU(cudaMemcpyAsync(c.d_start, start, (size_t)nS * 8, cudaMemcpyHostToDevice, c.compute));
     CU(cudaMemcpyAsync(c.d_length, length, (size_t)nS * 4, cudaMemcpyHostToDevice, c.compute));
 
+    if (nH > 0) {
+        // index lists first: they are small, and the host threads can start while the dense rows move
+        CU(cudaMemcpyAsync(c.d_ibeg, ibeg.data(), ((size_t)nH + 1) * 8, cudaMemcpyHostToDevice, c.compute));
+        cudaError_t e = cfrk::launch_dense_index(c.d_bases, fmt, c.d_start, c.d_length, c.d_ibeg, nD, nS, k, mode, c.d_idx, c.compute);
+        if (e != cudaSuccess) return fail_cuda(e, "dense_index_kernel launch");
+        CU(cudaMemcpyAsync(c.h_idx, c.d_idx, (size_t)idx_total * 4, cudaMemcpyDeviceToHost, c.compute));
+        CU(cudaEventRecord(c.idx_ready, c.compute));
+    }
+    CU(cudaEventRecord(c.t0, c.compute));
     for (int64_t s = 0; s < nslices; s++) {
         const int slot = (int)(s & 1);
-        const int64_t r0 = s * slice, r1 = std::min(nS, r0 + slice);
+        const int64_t r0 = s * slice, r1 = std::min(nD, r0 + slice);
         if (s >= 2) CU(cudaStreamWaitEvent(c.compute, c.drained[slot], 0));
         cudaError_t e = cfrk::launch_dense(c.d_bases, fmt, c.d_start, c.d_length, nN, nS, r0, r1, k, mode,
                                            0, 0, c.d_ring[slot], c.compute);
@@ -346,9 +587,32 @@ int cfrk_count_dense_host(const void* bases, int fmt, const int64_t* start, cons
                            cudaMemcpyDeviceToHost, c.copy));
         CU(cudaEventRecord(c.drained[slot], c.copy));
     }
+    CU(cudaEventRecord(c.t1, c.copy));
+    double host_ms = 0.0;
+    if (nH > 0) {
+        CU(cudaEventSynchronize(c.idx_ready));
+        const auto h0 = std::chrono::steady_clock::now();
+        expand_rows(c.h_idx, ibeg.data(), nD, nS, fourk, mode, freq_out, nt);
+        host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+    }
     CU(cudaStreamSynchronize(c.copy));
     CU(cudaStreamSynchronize(c.compute));
+    if (nH > 0 && nD > 0) {
+        // steer the split towards equal finishing times of the DMA side and the host side
+        float dma_ms = 0.f;
+        if (cudaEventElapsedTime(&dma_ms, c.t0, c.t1) == cudaSuccess && dma_ms > 0.f && host_ms > 0.0) {
+            const double rate_d = (double)nD / dma_ms, rate_h = (double)nH / host_ms;
+            const double target = rate_d / (rate_d + rate_h);
+            c.dma_frac[k] = std::min(0.95, std::max(0.05, 0.5 * ((double)nD / (double)nS) + 0.5 * target));
+        }
+        cudaGetLastError();
+    }
     return CFRK_OK;
+}
+
+void cfrk_set_host_threads(int n)
+{
+    g_host_threads.store(n < 0 ? -2 : std::min(n, 256));    // negative: back to the default
 }
 
 int cfrk_encode_2bit_device(const void* d_bases, int fmt, int64_t n, uint32_t* d_codes, uint16_t* d_valid,

@@ -202,9 +202,13 @@ __device__ __forceinline__ void lane_block(bool live, const uint4 raw, int t0, i
     codes = 0;
     if (live) {
         encode16_s<FMT>(raw, codes, valid);
-        const uint32_t upto = ~from_pos_s(min(16, tend - t0));
-        valid &= from_pos_s(max(0, -t0)) & upto;                        // bases of this read only
-        cmask = from_pos_s(min(16, max(0, K - 1 - t0))) & upto;         // window ends that are visited
+        if (t0 >= K - 1 && t0 + 16 <= tend) {
+            cmask = kEven;                                                  // a block inside the read: every window end counts
+        } else {
+            const uint32_t upto = ~from_pos_s(min(16, tend - t0));
+            valid &= from_pos_s(max(0, -t0)) & upto;                        // bases of this read only
+            cmask = from_pos_s(min(16, max(0, K - 1 - t0))) & upto;         // window ends that are visited
+        }
     }
     uint32_t pvalid;
     if (W == 1) {
@@ -222,7 +226,10 @@ __device__ __forceinline__ void lane_block(bool live, const uint4 raw, int t0, i
 #pragma unroll
     for (int i = 1; i < K; i++) ok &= __funnelshift_r(valid, pvalid, 2 * i);
     good = ok & cmask;
-    if (mode == MODE_COMPAT) nbad += __popc(~ok & cmask);
+    if (mode == MODE_COMPAT) {
+        const uint32_t bad = ~ok & cmask;
+        if (bad) nbad += __popc(bad);       // (clean reads: only the windows that reach the terminator)
+    }
 }
 
 struct Stage {            // where the tile's blocks are: shared memory (staged) or the global buffer
@@ -297,7 +304,8 @@ __global__ void __launch_bounds__(WARPS * 32) dense_lane_kernel(const DenseArgs 
         const int nrows = (int)min((int64_t)R, a.read_end - r0);
         const bool have = q < nrows;
         int tend = 0, extra = 0;
-        if (have) read_extent<K>(a.mode, len, a.nN - s, tend, extra);
+        const ChunkScope cs{a.start, a.nS, a.nN, a.chunk_size, a.index_base};
+        if (have) read_extent<K>(a.mode, len, compat_avail(cs, r0 + q, s, len, a.mode), tend, extra);
         const int64_t blk0 = s >> 4;
         const int off = (int)(s & 15);
         const int nblk = tend > 0 ? (int)(((s + tend - 1) >> 4) - blk0 + 1) : 0;
@@ -311,12 +319,14 @@ __global__ void __launch_bounds__(WARPS * 32) dense_lane_kernel(const DenseArgs 
         } else if (r0 == 0) {
             first = 0; period = 1 << 20;
         }
-        auto opens = [&](int qq) { return first >= 0 && qq >= first && (qq - first) % period == 0; };
+        // (one opener per tile unless the chunks are shorter than a tile: no division in the common case)
+        const bool many = period <= R;
+        auto opens = [&](int qq) { return qq == first || (many && first >= 0 && qq > first && (qq - first) % period == 0); };
         // the read after the tile: its spill lands in the tile's last row
         const bool has_next = compat && (r0 + nrows < a.nS) && !opens(nrows);
         const bool scan_next = has_next && (a.handoff == nullptr || tile == a.num_tiles - 1);
         int ex_next = 0, tend_next = 0;
-        if (lane == 0 && has_next) read_extent<K>(a.mode, len_next, a.nN - s_next, tend_next, ex_next);
+        if (lane == 0 && has_next) read_extent<K>(a.mode, len_next, compat_avail(cs, r0 + nrows, s_next, len_next, a.mode), tend_next, ex_next);
         const int64_t sn = __shfl_sync(kFull, s_next, 0);
         tend_next = __shfl_sync(kFull, tend_next, 0);
         ex_next = __shfl_sync(kFull, ex_next, 0);

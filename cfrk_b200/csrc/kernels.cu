@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(NTHREADS) dense_count_kernel(const DenseArgs a
 
         // the TMA store that last used this buffer (NBUF tiles ago) must have read it out
         if (threadIdx.x == 0) bulk_wait_read<NBUF - 1>();
-        fill_read_table<K>(tb, a.start, a.length, r0, nreads, a.mode, a.nN);
+        fill_read_table<K>(tb, a.start, a.length, r0, nreads, a.mode, a.nN, a.nS, a.chunk_size, a.index_base);
         __syncthreads();
 
         {   // zero the tile (replaces SetMatrix(d_Freq, 0), src/kmer_main.cu:108) ...
@@ -282,7 +282,9 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dense_warp_kernel(const Dens
         // read is scanned here as a halo read instead.
         const bool scan_halo = halo && (a.handoff == nullptr || tile == a.num_tiles - 1);
         const int nreads = nrows + (scan_halo ? 1 : 0);
-        const LaneRead lr = make_lane_read<K>(lane < nrows + (halo ? 1 : 0), lane < nreads, s, len, a.mode, a.nN);
+        const ChunkScope cs{a.start, a.nS, a.nN, a.chunk_size, a.index_base};
+        const LaneRead lr = make_lane_read<K>(lane < nrows + (halo ? 1 : 0), lane < nreads, s, len, a.mode,
+                                              compat_avail(cs, r0 + lane, s, len, a.mode));
 
         const int64_t next_tile = tile + nwarps;
         if (next_tile < a.num_tiles) {  // prefetch the next tile's offsets
@@ -453,7 +455,7 @@ __global__ void __launch_bounds__(kRowThreads) dense_row_kernel(const DenseArgs 
         const bool scan_halo = halo && (a.handoff == nullptr || row == nrows_total - 1);
         const int nreads = 1 + (scan_halo ? 1 : 0);
         if (threadIdx.x == 0) s_carry = 0;
-        fill_read_table<K>(tb, a.start, a.length, r, 1 + (halo ? 1 : 0), a.mode, a.nN);
+        fill_read_table<K>(tb, a.start, a.length, r, 1 + (halo ? 1 : 0), a.mode, a.nN, a.nS, a.chunk_size, a.index_base);
         __syncthreads();
         if (threadIdx.x == 0) {   // 2-entry "scan"
             const uint32_t n0 = tb.cum[0], n1 = scan_halo ? tb.cum[1] : 0u;
@@ -632,7 +634,7 @@ __global__ void __launch_bounds__(kBigThreads) dense_bigrow_kernel(const DenseAr
             }
             bulk_commit();
         }
-        fill_read_table<K>(tb, a.start, a.length, r0, nreads, a.mode, a.nN);
+        fill_read_table<K>(tb, a.start, a.length, r0, nreads, a.mode, a.nN, a.nS, a.chunk_size, a.index_base);
         __syncthreads();
         if (threadIdx.x < 32) scan_read_table(tb, nreads);
         __syncthreads();

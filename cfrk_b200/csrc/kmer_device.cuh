@@ -141,18 +141,36 @@ __device__ __forceinline__ void read_extent(int mode, int len, int64_t avail, in
     extra = (mode == MODE_COMPAT) ? max(0, vis - max(0, len - K + 1)) : 0;
 }
 
+// Bytes an EMPTY read may walk over in compat mode: up to the end of ITS reference chunk's buffer.  The
+// reference runs one kmer_main per chunk on a buffer that holds that chunk's reads only
+// (src/main.cu:110-206,222), so the walk of an empty read stops where the next chunk begins; one
+// launch here covers many chunks (chunk_size / index_base), and the next chunk's reads follow in the
+// same buffer.  Only evaluated for len == 0 (rare).
+struct ChunkScope {
+    const int64_t* start;
+    int64_t nS, nN, chunk_size, index_base;
+};
+__device__ __forceinline__ int64_t compat_avail(const ChunkScope& c, int64_t r, int64_t s, int len, int mode)
+{
+    if (mode != MODE_COMPAT || len != 0 || c.chunk_size <= 0) return c.nN - s;
+    const int64_t e = r + (c.chunk_size - (c.index_base + r) % c.chunk_size);   // first read of the next chunk
+    return (e < c.nS ? c.start[e] : c.nN) - s;
+}
+
 // Fill the table for reads [r0, r0+n) (n <= kMaxGroupReads+1).  Call with all threads, then
 // __syncthreads(), then scan_read_table() from warp 0, then __syncthreads().
 template <int K>
 __device__ __forceinline__ void fill_read_table(const ReadTable& tb, const int64_t* __restrict__ start,
                                                 const int32_t* __restrict__ length, int64_t r0, int n,
-                                                int mode, int64_t nN)
+                                                int mode, int64_t nN, int64_t nS = 0, int64_t chunk_size = 0,
+                                                int64_t index_base = 0)
 {
+    const ChunkScope cs{start, nS, nN, chunk_size, index_base};
     for (int q = threadIdx.x; q < n; q += blockDim.x) {
         int64_t s = start[r0 + q];
         int len = length[r0 + q];
         int tend, extra;
-        read_extent<K>(mode, len, nN - s, tend, extra);
+        read_extent<K>(mode, len, compat_avail(cs, r0 + q, s, len, mode), tend, extra);
         tb.start[q] = s;
         tb.tend[q] = tend;
         tb.extra[q] = extra;
@@ -325,12 +343,12 @@ struct LaneRead {      // read q = lane q of the warp
 
 // have: the lane describes a read (tend / extra are computed); items: its blocks are enumerated
 template <int K>
-__device__ __forceinline__ LaneRead make_lane_read(bool have, bool items, int64_t s, int len, int mode, int64_t nN)
+__device__ __forceinline__ LaneRead make_lane_read(bool have, bool items, int64_t s, int len, int mode, int64_t avail)
 {
     LaneRead lr;
     lr.start = s; lr.tend = 0; lr.extra = 0; lr.nblk = 0; lr.cum = 0;
     if (have) {
-        read_extent<K>(mode, len, nN - s, lr.tend, lr.extra);
+        read_extent<K>(mode, len, avail, lr.tend, lr.extra);
         lr.nblk = (items && lr.tend > 0) ? (uint32_t)(((s + lr.tend - 1) >> 4) - (s >> 4) + 1) : 0u;
     }
     uint32_t inc = lr.nblk;

@@ -78,10 +78,33 @@ constexpr int kSparseWarps = 8;
 
 // ------------------------------------------------------------------------------------------
 // window counts -> row_begin (exclusive scan done by cub::DeviceScan: plumbing)
-__global__ void nwin_kernel(const int32_t* __restrict__ length, int64_t nS, int k, int64_t* __restrict__ out)
+// also counts the reads per size class, so that only the kernels that have work are launched:
+// cls[0] reads of 1..144 windows, cls[1] 145..256, cls[2] 257..512, cls[3] longer
+__global__ void nwin_kernel(const int32_t* __restrict__ length, int64_t nS, int k, int64_t* __restrict__ out,
+                            unsigned long long* __restrict__ cls)
 {
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= nS; r += (int64_t)gridDim.x * blockDim.x)
-        out[r] = r < nS ? max(0, length[r] - k + 1) : 0;
+    unsigned long long c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r <= nS; r += (int64_t)gridDim.x * blockDim.x) {
+        const int n = r < nS ? max(0, length[r] - k + 1) : 0;
+        out[r] = n;
+        c0 += n >= 1 && n <= 144;
+        c1 += n > 144 && n <= 256;
+        c2 += n > 256 && n <= 512;
+        c3 += n > 512;
+    }
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        c0 += __shfl_xor_sync(0xffffffffu, c0, d);
+        c1 += __shfl_xor_sync(0xffffffffu, c1, d);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, d);
+        c3 += __shfl_xor_sync(0xffffffffu, c3, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (c0) atomicAdd(cls + 0, c0);
+        if (c1) atomicAdd(cls + 1, c1);
+        if (c2) atomicAdd(cls + 2, c2);
+        if (c3) atomicAdd(cls + 3, c3);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1383,8 +1406,12 @@ static cudaError_t sparse_impl(const void* bases, const int64_t* start, const in
 
     SparseTrace tr(st);
     keep_pool_memory(dev);
-    // 1. row_begin = exclusive scan of window counts
-    nwin_kernel<<<num_sms * 4, 256, 0, st>>>(length, nS, k, row_begin);
+    // 1. row_begin = exclusive scan of window counts (+ how many reads each size class has)
+    PoolScratch lists(st);   // released on every return path
+    unsigned long long* d_cls = nullptr;
+    if ((e = lists.get(&d_cls, 4)) != cudaSuccess) return e;
+    cudaMemsetAsync(d_cls, 0, 32, st);
+    nwin_kernel<<<num_sms * 4, 256, 0, st>>>(length, nS, k, row_begin, d_cls);
     count_launch();
     size_t tmp_bytes = 0;
     if ((e = cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, row_begin, row_begin, nS + 1, st)) != cudaSuccess) return e;
@@ -1394,7 +1421,9 @@ static cudaError_t sparse_impl(const void* bases, const int64_t* start, const in
     cudaFreeAsync(tmp, st);
     if (e != cudaSuccess) return e;
     int64_t total = 0;
+    unsigned long long cls[4] = {0, 0, 0, 0};
     if ((e = cudaMemcpyAsync(&total, row_begin + nS, 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(cls, d_cls, 32, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
     if (total_windows) *total_windows = total;
     if (total > capacity) return cudaErrorInvalidValue;   // caller maps to CFRK_EINVAL "capacity"
@@ -1412,18 +1441,26 @@ static cudaError_t sparse_impl(const void* bases, const int64_t* start, const in
         const char* hev = getenv("CFRK_SPARSE_HALF");            // 0: round-1 classes (one warp per read for every length)
         const bool use_half = !(hev && atoi(hev) == 0);
         if (use_half) {
-            // reads of <= 144 windows: two per warp (sparse_half_kernel); 145..256 and 257..512: one warp each
+            // reads of <= 144 windows: two per warp (sparse_half_kernel; it also writes row_count = 0 for reads
+            // without a window); 145..256 and 257..512: one warp each, launched only if such reads exist
             const int64_t hctas = ((nS + 1) / 2 + kSparseWarps - 1) / kSparseWarps;
             const unsigned hgrid = (unsigned)(hctas < (int64_t)num_sms * 8 ? hctas : (int64_t)num_sms * 8);
             sparse_half_kernel<KeyT, FMT><<<hgrid, kSparseWarps * 32, 0, st>>>(b8, nullptr, start, length, nS, k, row_begin, row_count, keys, counts);
-            sparse_short_kernel<KeyT, FMT, 8><<<grid, SparseCta<8>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts, group_split, kHalfSlots + 1);
-            sparse_short_kernel<KeyT, FMT, 16><<<grid, SparseCta<16>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts, group_split, 257);
+            count_launch();
+            if (cls[1]) {
+                sparse_short_kernel<KeyT, FMT, 8><<<grid, SparseCta<8>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts, group_split, kHalfSlots + 1);
+                count_launch();
+            }
+            if (cls[2]) {
+                sparse_short_kernel<KeyT, FMT, 16><<<grid, SparseCta<16>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts, group_split, 257);
+                count_launch();
+            }
         } else {
             sparse_short_kernel<KeyT, FMT, 4><<<grid, SparseCta<4>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts, group_split, 1);
             sparse_short_kernel<KeyT, FMT, 8><<<grid, SparseCta<8>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts, group_split, 129);
             sparse_short_kernel<KeyT, FMT, 16><<<grid, SparseCta<16>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts, group_split, 257);
+            count_launch(); count_launch(); count_launch();
         }
-        count_launch(); count_launch(); count_launch();
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
     }
 
@@ -1436,7 +1473,7 @@ static cudaError_t sparse_impl(const void* bases, const int64_t* start, const in
     const int64_t cap_long = total / kShortMaxWindows + 1;   // such a row has > 512 windows
     const char* mev = getenv("CFRK_SPARSE_MEDIUM");          // 0: medium rows take the long-row path (A/B measurements)
     const bool use_medium = !(mev && atoi(mev) == 0);
-    PoolScratch lists(st);   // released on every return path
+    if (cls[3] == 0) return cudaGetLastError();               // no read above 512 windows: done
     if ((e = lists.get(&long_rows, (size_t)cap_long)) != cudaSuccess) return e;
     if ((e = lists.get(&medium_rows, (size_t)cap_long)) != cudaSuccess) return e;
     if ((e = lists.get(&d_n, 3)) != cudaSuccess) return e;

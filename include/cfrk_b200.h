@@ -97,6 +97,17 @@ int cfrk_count_dense_host(const void *bases, int fmt, const int64_t *start, cons
                           int32_t *freq_out);
 
 /*
+ * Host threads of cfrk_count_dense_host / kmer_main (the reference's `nt`, src/main.cu:235, is parsed
+ * and unused: its OpenMP pragmas are compiled without -fopenmp).  For rows of >= 4 KiB the operator
+ * splits a batch: one share of the rows is written into the caller's buffer by the GPU's DMA engine,
+ * for the rest only the k-mer index of each window crosses PCIe and n host threads write the rows
+ * (zeros + counts, streaming stores).  The k-mers are computed on the GPU either way.  n = 0: DMA only;
+ * n < 0: back to the default.
+ * Default: min(hardware threads, 16), or the environment variable CFRK_HOST_THREADS.
+ */
+void cfrk_set_host_threads(int n);
+
+/*
  * Device-resident variant: every pointer is device memory on `device`, `stream` is a
  * cudaStream_t (NULL = the legacy default stream).  Asynchronous.  d_bases must honour
  * CFRK_PAD; d_freq must be 16-byte aligned.  Reads [read_begin, read_end) of the batch

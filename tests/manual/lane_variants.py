@@ -30,7 +30,8 @@ def run_dense(bases_t, start, length, nN, k, mode, fmt, lo=0, hi=None, chunk=0, 
     nS = len(start)
     hi = nS if hi is None else hi
     out = torch.full(((hi - lo) * 4 ** k + 64,), -1, dtype=torch.int32, device="cuda")
-    cf.count_dense_device(bases_t.data_ptr(), dev(start).data_ptr(), dev(length).data_ptr(), nN, nS, k, out.data_ptr(),
+    d_start, d_length = dev(start), dev(length)     # named: a temporary would be freed (and reused) before the launch
+    cf.count_dense_device(bases_t.data_ptr(), d_start.data_ptr(), d_length.data_ptr(), nN, nS, k, out.data_ptr(),
                           mode=mode, fmt=fmt, read_begin=lo, read_end=hi, chunk_size=chunk, first_read_index=first)
     torch.cuda.synchronize()
     assert bool((out[(hi - lo) * 4 ** k:] == -1).all()), "wrote past the rows"
@@ -75,7 +76,8 @@ def parity(k):
         b3 = pad(d3, 0xFF)
         cf.encode_2bit_device(b3.data_ptr(), len(d3), codes.data_ptr(), valid.data_ptr(), fmt=cf.FMT_CODES)
         out = torch.empty((20011, 4 ** k), dtype=torch.int32, device="cuda")
-        cf.count_dense_packed_device(codes.data_ptr(), valid.data_ptr(), dev(s3).data_ptr(), dev(l3).data_ptr(), len(d3), 20011, k,
+        d_s3, d_l3 = dev(s3), dev(l3)
+        cf.count_dense_packed_device(codes.data_ptr(), valid.data_ptr(), d_s3.data_ptr(), d_l3.data_ptr(), len(d3), 20011, k,
                                      out.data_ptr(), mode=mode, chunk_size=100)
         torch.cuda.synchronize()
         ok &= bool(np.array_equal(out.cpu().numpy(), w3))

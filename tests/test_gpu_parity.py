@@ -121,3 +121,34 @@ def test_dense_rows_up_to_k12(k):
         got = cf.count_dense_host(data, start, length, k, mode)
         want = ob.count_dense_fast(data, start, length, k, mode)
         np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("k,nS", [(5, 9000), (6, 8192), (7, 3000), (8, 700)])
+@pytest.mark.parametrize("mode", [cf.MODE_COMPAT, cf.MODE_EXACT], ids=["compat", "exact"])
+def test_host_operator_split_between_dma_and_host_threads(k, nS, mode):
+    """cfrk_count_dense_host on batches large enough for the split: part of the rows arrive as dense rows by DMA, the
+    rest as index lists expanded by host threads (streaming stores); same rows as the oracle, whatever the share and
+    the thread count, with N bases (spill across the DMA / host boundary), reads up to the 1024-window cap, a read
+    without windows, and an output buffer that is not 64-byte aligned"""
+    rng = np.random.default_rng(100 + k)
+    lens = rng.choice([150, 151, 100, 1, 2, 37, 1030, 1500], size=nS, p=[0.6, 0.2, 0.1, 0.02, 0.02, 0.02, 0.02, 0.02]).astype(np.int32)
+    start = np.concatenate([[0], np.cumsum(lens[:-1].astype(np.int64) + 1)])
+    nN = int(start[-1] + lens[-1] + 1)
+    data = rng.integers(0, 4, size=nN, dtype=np.int8)
+    data[rng.random(nN) < 0.003] = -1
+    data[start + lens] = -1
+    omode = ob.MODE_COMPAT if mode == cf.MODE_COMPAT else ob.MODE_EXACT
+    want = ob.count_dense_fast(data, start, lens, k, omode)
+    try:
+        for nt in (0, 1, 5, 16):
+            cf.lib().cfrk_set_host_threads(nt)
+            for rep in range(3):        # the share adapts between calls
+                got = cf.count_dense_host(data, start, lens, k, mode, cf.FMT_CODES)
+                np.testing.assert_array_equal(got, want, err_msg=f"nt={nt} rep={rep}")
+        # unaligned rows (offset by 4 bytes): the in-cache path of the expansion
+        raw = np.empty(nS * 4 ** k + 1, dtype=np.int32)
+        out = raw[1:].reshape(nS, 4 ** k)
+        got = cf.count_dense_host(data, start, lens, k, mode, cf.FMT_CODES, out=out)
+        np.testing.assert_array_equal(got, want)
+    finally:
+        cf.lib().cfrk_set_host_threads(-1)
