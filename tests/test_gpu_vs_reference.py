@@ -53,3 +53,51 @@ def test_same_inputs_same_rows(k):
     got = call_kmer_main(ours, data, start, length, k)
     np.testing.assert_array_equal(got, want)
     np.testing.assert_array_equal(got, ob.count_dense_fast(data, start, length, k, ob.MODE_COMPAT))
+
+
+# ---- the reference's own DRIVER on this hot path -----------------------------
+# oracle/_ref/cfrk_ref_linked = the reference's unmodified main.cu + fastaIO.h + kmer.cuh + tipos.h, linked against
+# libcfrk_b200.so instead of kmer_main.cu + kmer_kernel.cu (oracle/Makefile ref-link).  Its reader strcat()s into
+# uninitialised malloc memory (src/fastaIO.h:51-52); MALLOC_PERTURB_=255 makes glibc hand out zero-filled blocks, which
+# is what the reader silently assumes, so the run is deterministic.  One visible GPU: with devCount > 1 the driver
+# skips chunks.
+LINKED = os.path.join(ob.ORACLE_DIR, "_ref", "cfrk_ref_linked")
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _run_linked(fasta, out, k, chunk):
+    import subprocess
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="0", MALLOC_PERTURB_="255")
+    r = subprocess.run([LINKED, str(fasta), str(out), str(k), "12", str(chunk)], env=env, capture_output=True, timeout=300)
+    assert r.returncode == 0, r.stdout.decode()[-400:] + r.stderr.decode()[-400:]
+    assert r.stdout == b"", r.stdout[:300]      # the reference prints its CUDA errors on stdout: none
+
+
+@pytest.mark.skipif(not os.path.exists(LINKED), reason="oracle/_ref/cfrk_ref_linked not built")
+@pytest.mark.parametrize("name", ["seq1", "seq2"])
+def test_reference_driver_on_this_hot_path_reproduces_test_sh(tmp_path, name):
+    """test/test.sh:13-19 with the reference's own main(): k=2, nt=12, chunk 8192, diff against the committed goldens"""
+    import subprocess, sys
+    subprocess.check_call([sys.executable, os.path.join(GOLD, "make_standins.py"), str(tmp_path)], stdout=subprocess.DEVNULL)
+    out = tmp_path / "out.cfrk"
+    _run_linked(tmp_path / f"{name}.standin.fasta", out, 2, 8192)
+    assert out.read_bytes() == open(os.path.join(GOLD, f"out-{name}.cfrk"), "rb").read()
+
+
+@pytest.mark.skipif(not os.path.exists(LINKED), reason="oracle/_ref/cfrk_ref_linked not built")
+@pytest.mark.parametrize("key", ["A_basic.k1.c8192", "A_basic.k3.c8192", "A_basic.k6.c8192", "B_withN.k2.c8192", "B_withN.k5.c8192",
+                                 "D_long.k4.c8192", "E_chunk20.k3.c7", "E_chunk20.k2.c8", "E_chunk16.k2.c8", "G_short.k3.c8192",
+                                 "I_gtheader.k3.c8192", "H_like_seq2.k5.c8192"])
+def test_reference_driver_on_this_hot_path_matches_reference_code(tmp_path, key):
+    """single-line fixtures of the manifest (the reference's reader overflows its heap on wrapped records,
+    src/fastaIO.h:59-60): same bytes as the reference's own kernels produce (tests/golden/ref_shim/manifest.json)"""
+    import hashlib, json
+    import fixtures as fx
+    m = json.load(open(os.path.join(GOLD, "ref_shim", "manifest.json")))[key]
+    name = key.split(".")[0]
+    text = next((t for n, t, *_ in list(fx.EDGE_SET) + list(fx.CHUNK_SET) if n == name), None) or fx.fx_like_seq(710, 151)
+    fa, out = tmp_path / "in.fa", tmp_path / "out.cfrk"
+    fa.write_text(text)
+    _run_linked(fa, out, m["k"], m["chunk"])
+    data = out.read_bytes()
+    assert len(data) == m["out_bytes"] and hashlib.sha256(data).hexdigest() == m["out_sha256"]
