@@ -24,9 +24,9 @@
 //
 // Compat spill (src/kmer_kernel.cu:84-87: an invalid visited window of read i adds 1 to the LAST bin of
 // read i-1): inside a tile it moves one lane group to the left; across tiles the same hand-off protocol
-// as the warp kernels of kernels.cu -- the length-only part is added from length[] by the tile that owns
-// the row, the data-dependent part is recorded by the tile that owns the read and added by
-// spill_fixup_kernel; the last tile of a launch scans the first read of the next range itself.
+// as the warp kernels of kernels.cu -- the tile that owns the read records its invalid windows in a word
+// per tile boundary, spill_fixup_kernel adds them to the previous tile's last row after the kernel; the
+// last tile of a launch scans the first read of the next range itself.
 #include "kernels.h"
 #include "kmer_device.cuh"
 #include "dense_args.h"
@@ -286,16 +286,12 @@ __global__ void __launch_bounds__(WARPS * 32) dense_lane_kernel(const DenseArgs 
     // packed input: blocks per staging buffer (4-byte codes + 2-byte validity each), multiple of 8
     constexpr int kPackedBlocks = (G::SPAN / 6) / 8 * 8;
 
-    // (start, length) of the tile's reads -- lane group q <-> read r0 + q -- and, in lane 0's second pair,
-    // of the read after the tile; always one tile ahead
-    int64_t s = 0, s_next = 0; int len = 0, len_next = 0;
+    // (start, length) of the tile's reads -- lane group q <-> read r0 + q; always one tile ahead
+    int64_t s = 0; int len = 0;
     auto load_meta = [&](int64_t t) {
-        const int64_t r0 = a.read_begin + t * R;
-        const int64_t r = r0 + q;
-        s = 0; len = 0; s_next = 0; len_next = 0;
+        const int64_t r = a.read_begin + t * R + q;
+        s = 0; len = 0;
         if (r < a.read_end) { s = a.start[r]; len = a.length[r]; }
-        const int64_t rn = min(r0 + R, a.read_end);
-        if (lane == 0 && rn < a.nS) { s_next = a.start[rn]; len_next = a.length[rn]; }
     };
     load_meta(tile);
 
@@ -322,14 +318,17 @@ __global__ void __launch_bounds__(WARPS * 32) dense_lane_kernel(const DenseArgs 
         // (one opener per tile unless the chunks are shorter than a tile: no division in the common case)
         const bool many = period <= R;
         auto opens = [&](int qq) { return qq == first || (many && first >= 0 && qq > first && (qq - first) % period == 0); };
-        // the read after the tile: its spill lands in the tile's last row
-        const bool has_next = compat && (r0 + nrows < a.nS) && !opens(nrows);
-        const bool scan_next = has_next && (a.handoff == nullptr || tile == a.num_tiles - 1);
+        // The spill of the read after the tile lands in the tile's last row.  Inside a launch the tile that
+        // OWNS that read records it (hand-off word, added by spill_fixup_kernel); the last tile of a launch
+        // scans that read itself (the owner is another launch).
+        const bool scan_next = compat && (a.handoff == nullptr || tile == a.num_tiles - 1) && (r0 + nrows < a.nS) && !opens(nrows);
+        int64_t sn = 0;
         int ex_next = 0, tend_next = 0;
-        if (lane == 0 && has_next) read_extent<K>(a.mode, len_next, compat_avail(cs, r0 + nrows, s_next, len_next, a.mode), tend_next, ex_next);
-        const int64_t sn = __shfl_sync(kFull, s_next, 0);
-        tend_next = __shfl_sync(kFull, tend_next, 0);
-        ex_next = __shfl_sync(kFull, ex_next, 0);
+        if (scan_next) {
+            sn = a.start[r0 + nrows];
+            const int ln = a.length[r0 + nrows];
+            read_extent<K>(a.mode, ln, compat_avail(cs, r0 + nrows, sn, ln, a.mode), tend_next, ex_next);
+        }
 
         // span of the tile in 16-byte blocks, relative to the first read with blocks
         const uint32_t with_blocks = __ballot_sync(kFull, nblk > 0);
@@ -415,7 +414,7 @@ __global__ void __launch_bounds__(WARPS * 32) dense_lane_kernel(const DenseArgs 
                 for (int d = 1; d < SPLIT; d <<= 1) nbad += __shfl_xor_sync(kFull, nbad, d);
                 const bool drop = !have || opens(q);
                 const int inv = drop ? 0 : nbad + extra;      // to the last bin of read q - 1
-                if (q == 0) carry0 = drop ? 0 : nbad;
+                if (q == 0) carry0 = inv;                     // ... of the previous tile: through the hand-off word
                 if constexpr (PLANES) {
                     const int from_right = __shfl_down_sync(kFull, inv, 1);
                     if (lane + 1 < nrows) cnt[BINS - 1] += (uint32_t)from_right;
@@ -426,12 +425,8 @@ __global__ void __launch_bounds__(WARPS * 32) dense_lane_kernel(const DenseArgs 
             }
             if constexpr (PLANES) {
                 uint4* o4 = reinterpret_cast<uint4*>(out_s + lane * BINS);
-                if (has_next && lane == nrows - 1) cnt[BINS - 1] += (uint32_t)ex_next;
 #pragma unroll
                 for (int i = 0; i < BINS / 4; i++) o4[i] = make_uint4(cnt[4 * i], cnt[4 * i + 1], cnt[4 * i + 2], cnt[4 * i + 3]);
-            } else {
-                if (has_next && lane == 0 && ex_next > 0)
-                    asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(out_saddr + (uint32_t)(nrows * BINS - 1) * 4u), "r"((uint32_t)ex_next) : "memory");
             }
         } else {
             // ---- warp-wide: read after read, lanes take consecutive blocks, coalesced global loads
@@ -464,13 +459,11 @@ __global__ void __launch_bounds__(WARPS * 32) dense_lane_kernel(const DenseArgs 
 #pragma unroll
                     for (int d = 16; d >= 1; d >>= 1) nbad += __shfl_xor_sync(kFull, nbad, d);
                     const bool drop = opens(qq);
-                    if (qq == 0) carry0 = drop ? 0 : nbad;
+                    if (qq == 0) carry0 = drop ? 0 : nbad + extraq;
                     else if (!drop && lane == 0 && nbad + extraq > 0)
                         asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(rowq - 4u), "r"((uint32_t)(nbad + extraq)) : "memory");
                 }
             }
-            if (has_next && lane == 0 && ex_next > 0)
-                asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(out_saddr + (uint32_t)(nrows * BINS - 1) * 4u), "r"((uint32_t)ex_next) : "memory");
         }
 
         if (scan_next && tend_next > 0) {
@@ -492,8 +485,8 @@ __global__ void __launch_bounds__(WARPS * 32) dense_lane_kernel(const DenseArgs 
 #pragma unroll
             for (int d = 16; d >= 1; d >>= 1) nbad += __shfl_xor_sync(kFull, nbad, d);
             __syncwarp();
-            if (lane == 0 && nbad > 0)
-                asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(out_saddr + (uint32_t)(nrows * BINS - 1) * 4u), "r"((uint32_t)nbad) : "memory");
+            if (lane == 0 && nbad + ex_next > 0)
+                asm volatile("red.shared.add.u32 [%0], %1;" :: "r"(out_saddr + (uint32_t)(nrows * BINS - 1) * 4u), "r"((uint32_t)(nbad + ex_next)) : "memory");
         }
 
         // rows -> HBM: one TMA bulk store per tile
@@ -501,8 +494,7 @@ __global__ void __launch_bounds__(WARPS * 32) dense_lane_kernel(const DenseArgs 
         __syncwarp();
         if (lane == 0) {
             bulk_store_tile(a.out + (r0 - a.read_begin) * BINS, out_s, (uint32_t)nrows * BINS * 4u);
-            const bool q0_opens = opens(0);
-            if (compat && a.handoff != nullptr && carry0 > 0 && tile != 0 && !q0_opens) a.handoff[tile - 1] = (uint32_t)carry0;
+            if (compat && a.handoff != nullptr && carry0 > 0 && tile != 0) a.handoff[tile - 1] = (uint32_t)carry0;   // (0 for a chunk opener)
         }
         tile = next_tile;
     }

@@ -59,15 +59,16 @@ def test_same_inputs_same_rows(k):
 # oracle/_ref/cfrk_ref_linked = the reference's unmodified main.cu + fastaIO.h + kmer.cuh + tipos.h, linked against
 # libcfrk_b200.so instead of kmer_main.cu + kmer_kernel.cu (oracle/Makefile ref-link).  Its reader strcat()s into
 # uninitialised malloc memory (src/fastaIO.h:51-52); MALLOC_PERTURB_=255 makes glibc hand out zero-filled blocks, which
-# is what the reader silently assumes, so the run is deterministic.  One visible GPU: with devCount > 1 the driver
-# skips chunks.
+# is what the reader silently assumes -- but only on the allocator's slow path: blocks recycled through the per-thread
+# cache (tcache) keep their stale bytes (popen/pclose in GetNs and the CUDA runtime free plenty), so the cache is
+# switched off as well.  One visible GPU: with devCount > 1 the driver skips chunks.
 LINKED = os.path.join(ob.ORACLE_DIR, "_ref", "cfrk_ref_linked")
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def _run_linked(fasta, out, k, chunk):
     import subprocess
-    env = dict(os.environ, CUDA_VISIBLE_DEVICES="0", MALLOC_PERTURB_="255")
+    env = dict(os.environ, CUDA_VISIBLE_DEVICES="0", MALLOC_PERTURB_="255", GLIBC_TUNABLES="glibc.malloc.tcache_count=0")
     r = subprocess.run([LINKED, str(fasta), str(out), str(k), "12", str(chunk)], env=env, capture_output=True, timeout=300)
     assert r.returncode == 0, r.stdout.decode()[-400:] + r.stderr.decode()[-400:]
     assert r.stdout == b"", r.stdout[:300]      # the reference prints its CUDA errors on stdout: none
