@@ -190,6 +190,160 @@ cudaError_t launch_unwrap(const uint8_t* d_buf, int64_t n, const int64_t* d_head
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------
+// FASTQ (4 lines per record: '@' header, sequence, '+' line, qualities; the reference cannot read it --
+// it looks for '>' -- but the SRR datasets of swift/roda.sh are distributed in this form).  Record i =
+// lines 4i .. 4i+3 of the span; the read is line 4i+1 without its line terminator, so (start, length)
+// into the raw bytes again, and the '\n' behind it is the separator the kernels expect.
+//   pass 1  newlines per 4 KiB chunk;  scan;  pass 2  one thread per 16 bytes: for every newline, its
+//           line number decides what begins behind it (4i: header '@', 4i+1: read, 4i+2: '+').
+__global__ void __launch_bounds__(kScanThreads) fastq_count_kernel(const uint8_t* __restrict__ buf, int64_t n,
+                                                                  int64_t* __restrict__ chunk_count)
+{
+    const int64_t p0 = ((int64_t)blockIdx.x * kScanThreads + threadIdx.x) * 16;
+    int c = 0;
+    if (p0 < n) {
+        const uint4 v = *reinterpret_cast<const uint4*>(buf + p0);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const int cnt = (int)min((int64_t)16, n - p0);
+#pragma unroll
+        for (int j = 0; j < 16; j++) c += (j < cnt && (uint8_t)(w[j >> 2] >> (8 * (j & 3))) == '\n');
+    }
+    __shared__ int s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    const int wsum = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(&s_sum, wsum);
+    __syncthreads();
+    if (threadIdx.x == 0) chunk_count[blockIdx.x] = s_sum;
+}
+
+// line L (0-based) begins at byte 0 (L = 0) or behind the L-th newline.  header[i] = begin of line 4i,
+// start[i] = begin of line 4i+1, length[i] = (begin of line 4i+2) - 1 - start[i]; err: line 4i does not
+// begin with '@' (1), line 4i+2 does not begin with '+' (2).
+__global__ void __launch_bounds__(kScanThreads) fastq_write_kernel(const uint8_t* __restrict__ buf, int64_t n,
+                                                                  const int64_t* __restrict__ chunk_off,
+                                                                  int64_t* __restrict__ header, int64_t* __restrict__ start,
+                                                                  int32_t* __restrict__ length, int64_t cap, int* __restrict__ err)
+{
+    const int64_t p0 = ((int64_t)blockIdx.x * kScanThreads + threadIdx.x) * 16;
+    uint32_t m = 0;
+    if (p0 < n) {
+        const uint4 v = *reinterpret_cast<const uint4*>(buf + p0);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        const int cnt = (int)min((int64_t)16, n - p0);
+#pragma unroll
+        for (int j = 0; j < 16; j++)
+            if (j < cnt && (uint8_t)(w[j >> 2] >> (8 * (j & 3))) == '\n') m |= 1u << j;
+    }
+    const int c = __popc(m);
+    __shared__ int s_warp[kScanThreads / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    int before = 0;
+#pragma unroll
+    for (int w = 0; w < kScanThreads / 32; w++) before += w < warp ? s_warp[w] : 0;
+    int64_t nl = chunk_off[blockIdx.x] + before + inc - c;   // newlines before this thread's bytes
+    if (p0 == 0 && n > 0) {                                  // line 0 begins the span
+        if (buf[0] != '@') *err = 1;
+        if (cap > 0) header[0] = 0;
+    }
+    uint32_t mm = m;
+    while (mm) {
+        const int j = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const int64_t line = nl + 1;                         // the line that begins behind this newline
+        const int64_t q = p0 + j + 1, rec = line >> 2;
+        nl++;
+        if (rec >= cap) continue;
+        switch ((int)(line & 3)) {
+        case 0: if (q < n) { header[rec] = q; if (buf[q] != '@') *err = 1; } break;
+        case 1: start[rec] = q; break;
+        case 2: {
+            // the read ended one byte before q: its '\n' (a '\r' before it stays a base, like CRLF FASTA)
+            // start[rec] is written by another thread: store the END here, the length is fixed up below
+            length[rec] = (int32_t)0;
+            header[cap + rec] = q - 1;                       // scratch: end of the read (second half of header[])
+            if (q < n && buf[q] != '+') *err = 2;
+            break;
+        }
+        default: break;
+        }
+    }
+}
+
+__global__ void fastq_length_kernel(const int64_t* __restrict__ header, const int64_t* __restrict__ start, int64_t nrec,
+                                    int64_t cap, int32_t* __restrict__ length, int* __restrict__ err)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrec) return;
+    const int64_t len = header[cap + i] - start[i];
+    if (len > 2147483647ll) { *err = 3; return; }
+    length[i] = (int32_t)(len > 0 ? len : 0);
+}
+
+// FASTQ span (begins with a '@' header line, ends behind a whole record or at the end of the input) ->
+// header / start / length of its records.  d_header must hold 2 * cap entries (the second half is scratch).
+// h_out[0] = records, h_out[1] = error (0 ok, 1 a record does not begin with '@', 2 no '+' line, 3 read too
+// long, 4 more records than cap, 5 the span does not end with a whole record).  Synchronises the stream.
+cudaError_t launch_fastq_scan(const uint8_t* d_buf, int64_t n, int64_t* d_header, int64_t* d_start, int32_t* d_length,
+                              int64_t cap, int64_t* h_out, cudaStream_t st)
+{
+    h_out[0] = 0; h_out[1] = 0;
+    if (n <= 0) return cudaSuccess;
+    cudaError_t e;
+    const int64_t nchunks = (n + kScanChunk - 1) / kScanChunk;
+    int64_t* chunk = nullptr;
+    int* d_err = nullptr;
+    if ((e = cudaMallocAsync(reinterpret_cast<void**>(&chunk), (size_t)(nchunks + 1) * 8, st)) != cudaSuccess) return e;
+    if ((e = cudaMallocAsync(reinterpret_cast<void**>(&d_err), 4, st)) != cudaSuccess) return e;
+    cudaMemsetAsync(d_err, 0, 4, st);
+    cudaMemsetAsync(chunk + nchunks, 0, 8, st);
+    fastq_count_kernel<<<(unsigned)nchunks, kScanThreads, 0, st>>>(d_buf, n, chunk);
+    count_launch();
+    size_t tmp_bytes = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, chunk, chunk, nchunks + 1, st);
+    void* tmp = nullptr;
+    if ((e = cudaMallocAsync(&tmp, tmp_bytes ? tmp_bytes : 16, st)) != cudaSuccess) return e;
+    if ((e = cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, chunk, chunk, nchunks + 1, st)) != cudaSuccess) return e;
+    int64_t newlines = 0;
+    uint8_t last = 0;
+    cudaMemcpyAsync(&newlines, chunk + nchunks, 8, cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&last, d_buf + n - 1, 1, cudaMemcpyDeviceToHost, st);
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    const int64_t lines = newlines + (last == '\n' ? 0 : 1);      // a last line without '\n' still counts
+    int err = 0;
+    const int64_t nrec = lines / 4;
+    if (lines % 4 != 0) {
+        err = 5;
+    } else if (nrec > cap) {
+        err = 4;
+    } else if (nrec > 0) {
+        fastq_write_kernel<<<(unsigned)nchunks, kScanThreads, 0, st>>>(d_buf, n, chunk, d_header, d_start, d_length, cap, d_err);
+        count_launch();
+        if (last != '\n') {
+            // the quality line of the last record has no terminator: nothing begins behind it; fine
+        }
+        fastq_length_kernel<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(d_header, d_start, nrec, cap, d_length, d_err);
+        count_launch();
+        cudaMemcpyAsync(&err, d_err, 4, cudaMemcpyDeviceToHost, st);
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    }
+    cudaFreeAsync(tmp, st);
+    cudaFreeAsync(chunk, st);
+    cudaFreeAsync(d_err, st);
+    h_out[0] = err == 4 ? nrec : (err ? 0 : nrec);
+    h_out[1] = err;
+    return cudaGetLastError();
+}
+
 // d_header: cap entries; d_start/d_length: cap entries; h_out[0] = number of headers in the span,
 // h_out[1] = error (0 ok, 1 '>' inside a sequence line, 2 text before the first header, 3 record too long,
 // 4 more headers than cap).  Synchronises the stream.

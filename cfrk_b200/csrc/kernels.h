@@ -40,6 +40,11 @@ cudaError_t launch_sparse(const void* bases, int fmt, const int64_t* start, cons
 cudaError_t launch_fasta_scan(const uint8_t* d_buf, int64_t n, int final_span, int64_t* d_header, int64_t* d_start,
                               int32_t* d_length, int64_t cap, int64_t* h_out, cudaStream_t st);
 
+// The same for a 4-line FASTQ span; d_header holds 2 * cap entries.  h_out[1]: 0 ok, 1 no '@', 2 no '+',
+// 3 read too long, 4 cap too small, 5 the span does not end with a whole record.
+cudaError_t launch_fastq_scan(const uint8_t* d_buf, int64_t n, int64_t* d_header, int64_t* d_start, int32_t* d_length,
+                              int64_t cap, int64_t* h_out, cudaStream_t st);
+
 // Exact mode at file level: record text without line terminators, last base kept (fasta_scan.cu).
 cudaError_t launch_unwrap(const uint8_t* d_buf, int64_t n, const int64_t* d_header, int64_t n_headers,
                           const int64_t* d_start, int64_t nrec, uint8_t* d_out, int64_t* d_new_start,

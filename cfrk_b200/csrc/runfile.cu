@@ -1,7 +1,7 @@
 // runfile.cu -- cfrk_run_file(): FASTA file -> GPU count -> .cfrk text, the whole of the
 // reference's main() (src/main.cu:232-305) re-designed around one or several GPUs.
 //
-//   reader   SpanReader: ONE thread reads the file (plain or gzip) into a pool of PINNED buffers and
+//   reader   SpanReader: ONE thread reads the file (FASTA or 4-line FASTQ, plain or gzip) into a pool of PINNED buffers and
 //            cuts it into SPANS at header lines, on the host, by looking at a few hundred bytes at the
 //            end of each window (the bases are never touched).  A span = complete records; its
 //            last >= 1088 text bytes of records are LOOKAHEAD: they get no rows in this span (they
@@ -115,6 +115,15 @@ public:
         return true;
     }
     bool is_gzip() const { return gz_ != nullptr; }
+    // '@' as the first byte of the (uncompressed) input: 4-line FASTQ records instead of FASTA
+    bool detect_fastq(Err& err)
+    {
+        char c = 0; size_t got = 0; bool eof = false;
+        if (!restart(0, err) || !read(&c, 1, &got, &eof, err)) return false;
+        fastq_ = got == 1 && c == '@';
+        return restart(0, err);
+    }
+    bool is_fastq() const { return fastq_; }
     size_t size_hint() const { return gz_ ? size_ * 4 : size_; }   // a guess for gzip; only sizes the buffers
     bool restart(size_t off, Err& err)
     {
@@ -156,6 +165,7 @@ private:
     int fd_ = -1;
     gzFile gz_ = nullptr;
     size_t size_ = 0, pos_ = 0;
+    bool fastq_ = false;
 };
 
 // ------------------------------------------------------------------------------------------
@@ -178,6 +188,31 @@ inline size_t prev_header(const char* buf, size_t lo, size_t p)
         const size_t q = (size_t)(static_cast<const char*>(m) - buf);
         if (q == 0 || buf[q - 1] == '\n') return q;
         p = q;
+    }
+    return SIZE_MAX;
+}
+
+// FASTQ: last q in [lo, p) that begins a record: '@' at a line start whose line after next begins with '+'
+// (a quality line may begin with '@' too, but is never followed two lines later by a '+' line).  *text =
+// bytes of its sequence line, '\n' included.  Candidates whose next two lines are not in [0, fill) yet are
+// skipped.
+inline size_t prev_fastq_record(const char* buf, size_t lo, size_t p, size_t fill, size_t* text)
+{
+    while (p > lo) {
+        const void* m = memrchr(buf + lo, '@', p - lo);
+        if (!m) return SIZE_MAX;
+        const size_t q = (size_t)(static_cast<const char*>(m) - buf);
+        p = q;
+        if (q != 0 && buf[q - 1] != '\n') continue;
+        const void* n1 = memchr(buf + q, '\n', fill - q);
+        if (!n1) continue;
+        const size_t l1 = (size_t)(static_cast<const char*>(n1) - buf) + 1;      // sequence line
+        const void* n2 = l1 < fill ? memchr(buf + l1, '\n', fill - l1) : nullptr;
+        if (!n2) continue;
+        const size_t l2 = (size_t)(static_cast<const char*>(n2) - buf) + 1;      // '+' line
+        if (l2 >= fill || buf[l2] != '+') continue;
+        if (text) *text = l2 - l1;
+        return q;
     }
     return SIZE_MAX;
 }
@@ -273,17 +308,27 @@ private:
                 size_t got = 0;
                 if (!src_->read(s.buf + fill, s.cap - fill, &got, &eof, err_)) return finish();
                 fill += got;
-                if (eof) { s.n = fill; s.rows_end = fill; s.final = true; break; }
+                if (eof) {
+                    // FASTQ: blank lines at the end of the file are not a fifth line of the last record
+                    if (src_->is_fastq()) while (fill > 1 && s.buf[fill - 1] == '\n' && (s.buf[fill - 2] == '\n' || s.buf[fill - 2] == '\r')) fill--;
+                    s.n = fill; s.rows_end = fill; s.final = true;
+                    break;
+                }
                 // cut at the last header line; hold back >= kLookText text bytes of complete records
-                const size_t h_last = prev_header(s.buf, 1, fill);
+                const bool fq = src_->is_fastq();
+                const size_t h_last = fq ? prev_fastq_record(s.buf, 1, fill, fill, nullptr) : prev_header(s.buf, 1, fill);
                 size_t cut = SIZE_MAX;
                 if (h_last != SIZE_MAX) {
                     size_t held = 0, next = h_last, h = h_last;
                     while (h > 0) {
-                        h = prev_header(s.buf, 0, h);
+                        size_t text = 0;
+                        h = fq ? prev_fastq_record(s.buf, 0, h, fill, &text) : prev_header(s.buf, 0, h);
                         if (h == SIZE_MAX) break;
-                        const void* eol = memchr(s.buf + h, '\n', next - h);
-                        held += eol ? next - ((size_t)(static_cast<const char*>(eol) - s.buf) + 1) : 0;
+                        if (!fq) {
+                            const void* eol = memchr(s.buf + h, '\n', next - h);
+                            text = eol ? next - ((size_t)(static_cast<const char*>(eol) - s.buf) + 1) : 0;
+                        }
+                        held += text;
                         next = h;
                         if (held >= kLookText) { cut = h; break; }
                     }
@@ -686,6 +731,7 @@ struct Pipeline {
     void* h_pool[4] = {}; size_t cap_hpool[4] = {};
     char* h_hdr = nullptr; size_t cap_hhdr = 0;     // pinned staging of the record table
     Sequencer* seq = nullptr;
+    bool fastq = false;                              // 4-line FASTQ records (fasta_scan.cu launch_fastq_scan)
 
     bool init(int dev, Sequencer* s, Err& err)
     {
@@ -732,7 +778,7 @@ struct Pipeline {
             cap_reads = nreads + nreads / 4 + 64;
             RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_start), cap_reads * 8));
             RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_length), cap_reads * 4));
-            RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_header), cap_reads * 8));
+            RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_header), cap_reads * 16));   // FASTQ scan: second half is scratch
         }
         const size_t need = row_bytes;
         if (row_bytes && need > cap_rows) {
@@ -762,11 +808,20 @@ struct Pipeline {
         RF_CU(cudaMemsetAsync(d_in + in_bytes, 0, CFRK_PAD, compute));
         int64_t out[2];
         for (;;) {
-            cudaError_t e = cfrk::launch_fasta_scan(reinterpret_cast<const uint8_t*>(d_in), (int64_t)in_bytes, 1,
-                                                    d_header, d_start, d_length, (int64_t)cap_reads, out, compute);
-            if (e != cudaSuccess) { err.code = CFRK_ECUDA; err.msg = std::string("fasta scan: ") + cudaGetErrorString(e); return false; }
+            cudaError_t e = fastq ? cfrk::launch_fastq_scan(reinterpret_cast<const uint8_t*>(d_in), (int64_t)in_bytes, d_header, d_start,
+                                                            d_length, (int64_t)cap_reads, out, compute)
+                                  : cfrk::launch_fasta_scan(reinterpret_cast<const uint8_t*>(d_in), (int64_t)in_bytes, 1,
+                                                            d_header, d_start, d_length, (int64_t)cap_reads, out, compute);
+            if (e != cudaSuccess) { err.code = CFRK_ECUDA; err.msg = std::string("record scan: ") + cudaGetErrorString(e); return false; }
             if (out[1] != 4) break;
             if (!reserve(in_bytes, (size_t)out[0], 0, err)) return false;   // more records than guessed: grow, rescan
+        }
+        if (fastq && out[1] != 0) {
+            err.code = CFRK_EFORMAT;
+            err.msg = out[1] == 1 ? "FASTQ: a record does not begin with '@' (4 lines per record expected)"
+                    : out[1] == 2 ? "FASTQ: the third line of a record does not begin with '+' (wrapped FASTQ is not supported)"
+                    : out[1] == 3 ? "FASTQ: read longer than 2^31-1 bytes" : "FASTQ: the input does not end with a whole 4-line record";
+            return false;
         }
         if (out[1] == 1) { err.code = CFRK_EFORMAT; err.msg = "'>' inside a sequence line (grep -c over-counts nS in the reference, src/fastaIO.h:16)"; return false; }
         if (out[1] == 2) { err.code = CFRK_EFORMAT; err.msg = "sequence text before the first '>' header (undefined in the reference, src/fastaIO.h:49-52)"; return false; }
@@ -799,6 +854,7 @@ struct Pipeline {
     bool unwrap_scanned(size_t in_bytes, size_t nreads, Err& err)
     {
         if (nreads == 0) return true;
+        if (fastq) return true;     // a FASTQ read is one line: (start, length) already is the unwrapped read
         if (in_bytes + CFRK_PAD > cap_packed) {
             cudaFree(d_packed); d_packed = nullptr;
             cap_packed = in_bytes + CFRK_PAD + in_bytes / 8;
@@ -1063,6 +1119,7 @@ bool run_pass(Source& src, size_t file_off, int64_t first_read, bool rows, const
             Err e;
             Pipeline gpu;
             if (!gpu.init(cfg.devices[(size_t)t % cfg.devices.size()], &seq, e)) { fail(e); return; }
+            gpu.fastq = src.is_fastq();
             RecordIndex ri;
             for (;;) {
                 if (failed.load()) return;
@@ -1113,7 +1170,7 @@ bool run_file(const char* fasta, const char* out_path, const RunCfg& cfg, Err& e
 {
     Trace tr;
     Source src;
-    if (!src.open(fasta, err)) return false;
+    if (!src.open(fasta, err) || !src.detect_fastq(err)) return false;
     CfrkWriter w;
     if (!w.open(out_path, cfg.k, cfg.nt, cfg.flags & CFRK_RUN_SPARSE, err)) return false;
     tr.mark("opened");

@@ -333,3 +333,48 @@ def test_two_gpus_same_bytes_as_one(tmp_path):
     assert ob.run_cli(str(big), str(one), 3, 8192, ob.MODE_COMPAT, all_rows=True) == 0
     run_cfrk_env({"CFRK_WINDOW_BYTES": str(8 << 20)}, big, two, 3, 8, 8192, "--all-rows", "--devices=0,1")
     assert hashlib.sha256(one.read_bytes()).hexdigest() == hashlib.sha256(two.read_bytes()).hexdigest()
+
+
+def _fasta_to_fastq(text, seed=5):
+    """single-line FASTA records -> 4-line FASTQ with quality strings that like to begin with '@' and '+'"""
+    import random
+    rng = random.Random(seed)
+    out = []
+    lines = text.split("\n")
+    i = 0
+    while i + 1 < len(lines):
+        if lines[i].startswith(">"):
+            seq = lines[i + 1]
+            q = "".join(rng.choice("@+IIIIFF#:,") for _ in range(len(seq)))
+            out.append(f"@{lines[i][1:]}\n{seq}\n+{lines[i][1:] if rng.random() < 0.5 else ''}\n{q}\n")
+            i += 2
+        else:
+            i += 1
+    return "".join(out)
+
+
+@pytest.mark.parametrize("window", [0, 8192])
+def test_fastq_input(tmp_path, window):
+    """4-line FASTQ (the form SRR datasets come in, swift/roda.sh:3): the same rows as the FASTA file of the same
+    reads, in every mode, across span cuts (quality lines that begin with '@' must not be taken for headers), with
+    blank lines at the end of the file, and gzip-compressed"""
+    import gzip
+    text = fx.fx_with_n() + fx.fx_chunk(20) + fx.fx_long() + fx.fx_short() + fx.fx_basic()
+    fa, fq, fqz = tmp_path / "in.fa", tmp_path / "in.fq", tmp_path / "in.fq.gz"
+    fa.write_text(text)
+    fq.write_text(_fasta_to_fastq(text) + "\n\n")
+    with gzip.open(fqz, "wb") as f:
+        f.write(_fasta_to_fastq(text).encode())
+    env = {"CFRK_WINDOW_BYTES": str(window)} if window else {}
+    a, b = tmp_path / "a", tmp_path / "b"
+    for args in ((2, 4, 8192, "--all-rows"), (3, 4, 7, "--all-rows"), (3, 4, 7), (5, 4, 8192, "--all-rows", "--exact"),
+                 (6, 4, 16, "--all-rows", "--sparse"), (12, 4, 8192, "--all-rows", "--sparse", "--exact")):
+        run_cfrk(fa, a, *args)
+        run_cfrk_env(env, fq, b, *args)
+        assert a.read_bytes() == b.read_bytes(), args
+        run_cfrk_env(env, fqz, b, *args)
+        assert a.read_bytes() == b.read_bytes(), ("gz", args)
+    bad = tmp_path / "bad.fq"
+    bad.write_text("@r1\nACGT\nACGT\nIIII\n")
+    r = subprocess.run([CFRK, str(bad), str(b), "2"], capture_output=True, timeout=120)
+    assert r.returncode == 1 and b"FASTQ" in r.stderr
