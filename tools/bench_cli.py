@@ -10,6 +10,8 @@ ap.add_argument("--read-len", type=int, default=150)
 ap.add_argument("--k", type=int, default=4)
 ap.add_argument("--nt", type=int, default=os.cpu_count() or 8)
 ap.add_argument("--dir", default="/dev/shm")
+ap.add_argument("--devices", default="", help="e.g. 0,1 or all: several GPUs (cfrk --devices=...)")
+ap.add_argument("--runs", default="all_rows_dense,all_rows_sparse,tail_only")
 a = ap.parse_args()
 d = tempfile.mkdtemp(dir=a.dir if os.path.isdir(a.dir) else None)
 fa, out = os.path.join(d, "in.fa"), os.path.join(d, "out.cfrk")
@@ -21,7 +23,11 @@ with open(fa, "wb") as f:
         hdr = np.frombuffer("".join(f">{i:09d}\n" for i in range(s, s + n)).encode(), dtype=np.uint8).reshape(n, 11)
         f.write(np.concatenate([hdr, blk, np.full((n, 1), 10, np.uint8)], axis=1).tobytes())
 res = {}
+dev = [f"--devices={a.devices}"] if a.devices else []
 for label, extra in (("all_rows_dense", ["--all-rows"]), ("all_rows_sparse", ["--all-rows", "--sparse"]), ("tail_only", [])):
+    if label not in a.runs.split(","):
+        continue
+    extra = extra + dev
     t0 = time.perf_counter()
     r = subprocess.run([os.path.join(ROOT, "bin", "cfrk"), fa, out, str(a.k), str(a.nt), "8192", *extra],
                        capture_output=True, env=dict(os.environ, CFRK_TRACE="1"))
@@ -32,7 +38,7 @@ for label, extra in (("all_rows_dense", ["--all-rows"]), ("all_rows_sparse", ["-
                   "out_gb_s": round(os.path.getsize(out) / dt / 1e9, 3)}
     last = [l for l in r.stderr.decode().splitlines() if "trace" in l][-1:]
     res[label]["pipeline_ms"] = float(last[0].split()[2]) if last else None
-print(json.dumps({"reads": a.reads, "read_len": a.read_len, "k": a.k, "nt": a.nt, "fasta_bytes": os.path.getsize(fa), **res}))
+print(json.dumps({"reads": a.reads, "read_len": a.read_len, "k": a.k, "nt": a.nt, "devices": a.devices or "0", "fasta_bytes": os.path.getsize(fa), **res}))
 for p in (fa, out):
     os.remove(p)
 os.rmdir(d)
