@@ -588,7 +588,8 @@ def run_ours(args):
     achieved = dom_bytes_per_launch / dom_s_per_launch / 1e9
     roofline = {"bound": "hbm", "achieved": round(achieved, 1), "peak": peak, "unit": "GB/s",
                 "frac": round(achieved / peak, 4), "traffic": None, "peak_source": peak_src,
-                "kernel": f"dense_count_kernel<K={dom},{args.fmt}>", "share_of_step": round(per_k_ms[dom] / sum(per_k_ms.values()), 3),
+                "kernel": {8: "dense_bigrow_kernel<8,ascii,65536>", 7: "dense_bigrow_kernel<7,FMT,32768>", 6: "dense_warp_kernel<6,FMT,1,6>",
+                           5: "dense_warp_kernel<5,FMT,3,3>"}.get(dom, f"dense_lane_kernel<{dom},FMT>").replace("FMT", args.fmt), "share_of_step": round(per_k_ms[dom] / sum(per_k_ms.values()), 3),
                 "bytes_per_launch": int(dom_bytes_per_launch), "us_per_launch": round(dom_s_per_launch * 1e6, 1),
                 "write_only_fill_gbs": round(write_only_gbs, 1),
                 "note": "peak = measured COPY bandwidth (read+write); the dominant kernel only writes, and a plain "

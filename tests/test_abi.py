@@ -60,6 +60,20 @@ def test_argument_validation_needs_no_gpu():
     assert L.cfrk_run_file(b"/nonexistent", b"/tmp/x", 2, 1, 0, 0, 0) == -1
 
 
+def test_housekeeping_entry_points_need_no_gpu():
+    """cfrk_release / cfrk_free_host / cfrk_set_host_threads are safe to call at any time, GPU or not"""
+    L = cf.lib()
+    L.cfrk_free_host(None)
+    L.cfrk_set_host_threads(3)
+    L.cfrk_set_host_threads(-1)
+    assert L.cfrk_release() == 0
+    assert L.cfrk_release() == 0
+    devs = (ctypes.c_int * 2)(0, 1)
+    assert L.cfrk_run_file_multi(b"/nonexistent", b"/tmp/x", 2, 1, 8192, 0, devs, 0) == -1       # no devices
+    assert L.cfrk_run_file_multi(b"/nonexistent", b"/tmp/x", 2, 1, 8192, 0, None, 1) == -1
+    assert L.cfrk_run_file_multi(b"/nonexistent", b"/tmp/x", 40, 1, 8192, 0, devs, 2) == -1      # k out of range
+
+
 @pytest.mark.skipif(cf.device_count() > 0, reason="a GPU is present")
 def test_fails_loudly_without_gpu(tmp_path):
     with pytest.raises(cf.CfrkError) as e:

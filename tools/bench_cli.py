@@ -36,6 +36,8 @@ for label, extra in (("all_rows_dense", ["--all-rows"]), ("all_rows_sparse", ["-
     res[label] = {"seconds": round(dt, 3), "out_bytes": os.path.getsize(out),
                   "gbases_s": round(a.reads * a.read_len / dt / 1e9, 4),
                   "out_gb_s": round(os.path.getsize(out) / dt / 1e9, 3)}
+    if os.environ.get("CFRK_BENCH_CLI_TRACE"):
+        sys.stderr.write(f"== {label} k={a.k}\n" + r.stderr.decode())
     last = [l for l in r.stderr.decode().splitlines() if "trace" in l][-1:]
     res[label]["pipeline_ms"] = float(last[0].split()[2]) if last else None
 print(json.dumps({"reads": a.reads, "read_len": a.read_len, "k": a.k, "nt": a.nt, "devices": a.devices or "0", "fasta_bytes": os.path.getsize(fa), **res}))
