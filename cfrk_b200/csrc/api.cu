@@ -469,6 +469,7 @@ int cfrk_count_dense_host(const void* bases, int fmt, const int64_t* start, cons
     if (!bases || !start || !length || !freq_out) return fail(CFRK_EINVAL, "null pointer");
     if (cfrk_device_count() <= device || device < 0)
         return fail(CFRK_ECUDA, "no such CUDA device (this library has no CPU fallback)");
+    const auto wall0 = std::chrono::steady_clock::now();
     HostCtx* cp = nullptr;
     rc = ensure_ctx(device, &cp);
     if (rc) return rc;
@@ -601,8 +602,9 @@ int cfrk_count_dense_host(const void* bases, int fmt, const int64_t* start, cons
     if (trace) {
         float ms = 0.f;
         if (nD > 0) cudaEventElapsedTime(&ms, c.t0, c.t1);
-        fprintf(stderr, "[cfrk host op] k=%d nS=%lld dma rows=%lld (%.2f ms) host rows=%lld (%.2f ms, %d threads)\n", k, (long long)nS,
-                (long long)nD, ms, (long long)nH, host_ms, nt);
+        fprintf(stderr, "[cfrk host op] k=%d nS=%lld dma rows=%lld (%.2f ms) host rows=%lld (%.2f ms, %d threads) call %.2f ms\n", k,
+                (long long)nS, (long long)nD, ms, (long long)nH, host_ms, nt,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - wall0).count());
         cudaGetLastError();
     }
     if (nH > 0 && nD > 0) {
