@@ -7,7 +7,7 @@
 //   * rows leave the device through a two-slot ring so that the device->host copy of slice i
 //     overlaps the kernel of slice i+1 (the reference does one synchronous cudaMemcpy of the
 //     whole Freq, src/kmer_main.cu:116),
-//   * part of the rows is written by host threads from index lists (HostExpand below), so that the
+//   * part of the rows is written by host threads from GPU-compacted (bin, count) pairs (below), so that the
 //     PCIe link is not the only path into the caller's buffer,
 //   * errors are returned, not printed.
 #include "../../include/cfrk_b200.h"
@@ -69,11 +69,16 @@ struct HostCtx {
     void* d_bases = nullptr;  size_t cap_bases = 0;
     int64_t* d_start = nullptr; int32_t* d_length = nullptr; size_t cap_reads = 0;
     int32_t* d_ring[2] = {nullptr, nullptr}; size_t cap_ring = 0;
-    // host-expanded part of a call: index lists (device + pinned mirror), their offsets, timing events
-    uint32_t* d_idx = nullptr; size_t cap_idx = 0;
-    int64_t* d_ibeg = nullptr; size_t cap_ibeg = 0;
-    uint32_t* h_idx = nullptr; size_t cap_hidx = 0;
-    cudaEvent_t idx_ready = nullptr, t0 = nullptr, t1 = nullptr;
+    // host-expanded part of a call: a device slot for its dense rows, their (bin, count) pairs (device +
+    // pinned mirror), per-row offsets and counts, a stream for the small copies, events per slice
+    cudaStream_t aux = nullptr;
+    int32_t* d_hslot = nullptr; size_t cap_hslot = 0;
+    uint32_t* d_pk = nullptr; uint32_t* d_pc = nullptr; size_t cap_pairs = 0;
+    int64_t* d_poff = nullptr; int32_t* d_prc = nullptr; size_t cap_prows = 0;
+    uint32_t* h_pk = nullptr; uint32_t* h_pc = nullptr; size_t cap_hpairs = 0;
+    int32_t* h_prc = nullptr; size_t cap_hprc = 0;
+    std::vector<cudaEvent_t> packed, ready;     // per host slice: pairs built / pairs in host memory
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
     double dma_frac[CFRK_DENSE_MAX_K + 1] = {0};   // share of the rows that goes through the DMA engine, per k (adaptive)
 
     void release()
@@ -82,9 +87,13 @@ struct HostCtx {
         cudaSetDevice(device);
         cudaFree(d_bases); cudaFree(d_start); cudaFree(d_length);
         cudaFree(d_ring[0]); cudaFree(d_ring[1]);
-        cudaFree(d_idx); cudaFree(d_ibeg);
-        if (h_idx) cudaFreeHost(h_idx);
-        if (idx_ready) cudaEventDestroy(idx_ready);
+        cudaFree(d_hslot); cudaFree(d_pk); cudaFree(d_pc); cudaFree(d_poff); cudaFree(d_prc);
+        if (h_pk) cudaFreeHost(h_pk);
+        if (h_pc) cudaFreeHost(h_pc);
+        if (h_prc) cudaFreeHost(h_prc);
+        for (cudaEvent_t e : packed) cudaEventDestroy(e);
+        for (cudaEvent_t e : ready) cudaEventDestroy(e);
+        if (aux) cudaStreamDestroy(aux);
         if (t0) cudaEventDestroy(t0);
         if (t1) cudaEventDestroy(t1);
         for (int i = 0; i < 2; i++) {
@@ -136,7 +145,7 @@ int ensure_ctx(int device, HostCtx** out)
             CU(cudaEventCreateWithFlags(&c->done[i], cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&c->drained[i], cudaEventDisableTiming));
         }
-        CU(cudaEventCreateWithFlags(&c->idx_ready, cudaEventDisableTiming));
+        CU(cudaStreamCreateWithFlags(&c->aux, cudaStreamNonBlocking));
         CU(cudaEventCreate(&c->t0));
         CU(cudaEventCreate(&c->t1));
         c->device = device;
@@ -162,10 +171,11 @@ int grow(T*& p, size_t& cap, size_t need)
 // HOST memory (256 KiB per 150-bp read at k = 8, of which <= 150 words are not zero) and a PCIe Gen5
 // link moves 55 GB/s: with every row crossing the bus the operator ran at 0.12 Gbases/s on a k = 4..8
 // sweep, below a 16-thread CPU counter.  So the rows are split: one share is written by
-// the GPU's DMA engine as before, for the other share only the k-mer index of every visited window
-// crosses the bus (dense_index.cu: 4 bytes per window) and `nt` host threads write those rows -- zeros
-// and counts in one pass of streaming stores, no read-for-ownership.  The split adapts per k to
-// whichever side finishes first.  The k-mers are still computed on the GPU only.
+// the GPU's DMA engine as before; the rows of the other share are counted on the GPU like all the others
+// (compat spill included), compacted there to the (bin, count) pairs of their non-zero bins
+// (row_pairs.cu: <= 1.2 KB per 150-bp read), and `nt` host threads EXPAND the pairs into the caller's
+// rows -- zeros and counts in one pass of streaming stores, no read-for-ownership.  The split adapts per
+// k to whichever side finishes first.  Nothing is counted on the host.
 std::atomic<int> g_host_threads{-2};    // -2: not configured yet
 
 int host_threads()
@@ -246,36 +256,26 @@ inline void stream_zero_line(int32_t* p)      // 64 bytes, 64-byte aligned
 #endif
 }
 
-// one row from its index list: bins[v]++ for every valid entry; returns the number of invalid entries
-// (compat: they are owed to the previous row's last bin).  Rows of >= 16 KiB are written in one
-// streaming pass (sorted indices, zero lines with non-temporal stores, the few lines that hold counts
-// built in a register buffer); smaller rows are cleared and counted in cache.
-int expand_one(const uint32_t* idx, int64_t n, size_t fourk, int32_t* row, uint32_t* tmp)
+// One row from the (bin, count) pairs of its non-zero bins (ascending bins, as row_pairs.cu emits them).
+// Rows of >= 16 KiB that are 64-byte aligned are written in ONE streaming pass: zero lines with
+// non-temporal stores, the few lines that hold counts built in a register buffer -- no read for
+// ownership, nothing is read back; smaller rows are cleared and patched in cache.
+void expand_one(const uint32_t* keys, const uint32_t* counts, int n, size_t fourk, int32_t* row)
 {
-    int invalid = 0;
     const bool aligned = (reinterpret_cast<uintptr_t>(row) & 63) == 0;
     if (fourk < 4096 || !aligned) {
         memset(row, 0, fourk * 4);
-        for (int64_t t = 0; t < n; t++) {
-            const uint32_t v = idx[t];
-            if (v < fourk) row[v]++; else invalid++;
-        }
-        return invalid;
+        for (int i = 0; i < n; i++) row[keys[i]] = (int32_t)counts[i];
+        return;
     }
-    int64_t m = 0;
-    for (int64_t t = 0; t < n; t++) {
-        const uint32_t v = idx[t];
-        if (v < fourk) tmp[m++] = v; else invalid++;
-    }
-    std::sort(tmp, tmp + m);
     size_t line = 0;                        // next 16-word line to write
     const size_t nlines = fourk / 16;
-    int64_t i = 0;
-    while (i < m) {
-        const size_t l = tmp[i] >> 4;
+    int i = 0;
+    while (i < n) {
+        const size_t l = keys[i] >> 4;
         for (; line < l; line++) stream_zero_line(row + line * 16);
         alignas(64) int32_t buf[16] = {0};
-        while (i < m && (tmp[i] >> 4) == l) buf[tmp[i++] & 15]++;
+        while (i < n && (keys[i] >> 4) == l) { buf[keys[i] & 15] = (int32_t)counts[i]; i++; }
 #if defined(__SSE2__)
         for (int q = 0; q < 4; q++)
             _mm_stream_si128(reinterpret_cast<__m128i*>(row + l * 16) + q, _mm_load_si128(reinterpret_cast<const __m128i*>(buf) + q));
@@ -285,37 +285,22 @@ int expand_one(const uint32_t* idx, int64_t n, size_t fourk, int32_t* row, uint3
         line = l + 1;
     }
     for (; line < nlines; line++) stream_zero_line(row + line * 16);
-    return invalid;
 }
 
-// rows [nD, nS) of freq_out from the index lists (h_idx, ibeg relative to read nD)
-void expand_rows(const uint32_t* h_idx, const int64_t* ibeg, int64_t nD, int64_t nS, size_t fourk, int mode,
-                 int32_t* freq_out, int nt)
+// rows [r0, r1) of the host share (indices relative to its first row): pairs at poff[], counts in prc[]
+void expand_rows(const uint32_t* h_pk, const uint32_t* h_pc, const int64_t* poff, const int32_t* h_prc, int64_t r0, int64_t r1,
+                 size_t fourk, int32_t* rows_out /* row 0 of the host share */, int nt)
 {
     std::call_once(g_pool_once, [] { g_pool = new HostPool(); });
-    const int64_t nH = nS - nD;
-    const int parts = (int)std::max<int64_t>(1, std::min<int64_t>(nt, nH / 4));
+    const int64_t n = r1 - r0;
+    const int parts = (int)std::max<int64_t>(1, std::min<int64_t>(nt, n / 4));
     const std::function<void(int)> fn = [&](int p) {
-        const int64_t a = nH * p / parts, b = nH * (p + 1) / parts;
-        std::vector<uint32_t> tmp((size_t)cfrk::kRefBlockThreads + 64);
-        for (int64_t i = a; i < b; i++) {
-            const int64_t n = ibeg[i + 1] - ibeg[i];
-            if ((size_t)n > tmp.size()) tmp.resize((size_t)n);
-            expand_one(h_idx + ibeg[i], n, fourk, freq_out + (size_t)(nD + i) * fourk, tmp.data());
-        }
+        const int64_t a = r0 + n * p / parts, b = r0 + n * (p + 1) / parts;
+        for (int64_t i = a; i < b; i++)
+            expand_one(h_pk + poff[i], h_pc + poff[i], h_prc[i], fourk, rows_out + (size_t)i * fourk);
 #if defined(__SSE2__)
         _mm_sfence();
 #endif
-        if (mode == CFRK_MODE_COMPAT) {
-            // spill: the invalid windows of read i+1 land in the last bin of row i (src/kmer_kernel.cu:84-87).
-            // Row nD-1 is the GPU's (it scans read nD itself); the thread that owns row i looks at list i+1.
-            for (int64_t i = a; i < b; i++) {
-                if (i + 1 >= nH) break;
-                int inv = 0;
-                for (int64_t t = ibeg[i + 1]; t < ibeg[i + 2]; t++) inv += h_idx[t] >= fourk;
-                if (inv) freq_out[(size_t)(nD + i) * fourk + fourk - 1] += inv;
-            }
-        }
     };
     g_pool->run(parts, fn);
 }
@@ -479,12 +464,11 @@ int cfrk_count_dense_host(const void* bases, int fmt, const int64_t* start, cons
     const size_t row_bytes = fourk * 4;
     const int rpt = cfrk::dense_reads_per_tile(k);
 
-    // ---- split: rows [0, nD) leave as dense rows through the DMA engine, rows [nD, nS) as index lists
-    // that host threads expand (see HostExpand above).  Not for tiny rows / batches (nothing to win) and
+    // ---- split: rows [0, nD) leave as dense rows through the DMA engine, rows [nD, nS) as (bin, count) pairs
+    // that host threads expand (see above).  Not for tiny rows / batches (nothing to win) and
     // not when a compat batch holds an empty read (its walk over the following reads stays on the GPU).
     const int nt = host_threads();
     int64_t nD = nS;
-    std::vector<int64_t> ibeg;
     if (nt > 0 && row_bytes >= 4096 && (size_t)nS * row_bytes >= ((size_t)32 << 20)) {
         bool ok = true;
         if (mode == CFRK_MODE_COMPAT)
@@ -498,20 +482,24 @@ int cfrk_count_dense_host(const void* bases, int fmt, const int64_t* start, cons
         }
     }
     const int64_t nH = nS - nD;                     // rows expanded on the host
-    int64_t idx_total = 0;
+    // pairs of host row i (relative to nD) at poff[i]: capacity = min(4^k, visited windows + 1)
+    std::vector<int64_t> poff;
+    int64_t pairs_total = 0;
     if (nH > 0) {
-        ibeg.resize((size_t)nH + 1);
+        poff.resize((size_t)nH + 1);
         for (int64_t i = 0; i < nH; i++) {
-            ibeg[(size_t)i] = idx_total;
-            idx_total += visited_windows(length[nD + i], k, mode);
+            poff[(size_t)i] = pairs_total;
+            pairs_total += std::min<int64_t>((int64_t)fourk, visited_windows(length[nD + i], k, mode) + 1);
         }
-        ibeg[(size_t)nH] = idx_total;
+        poff[(size_t)nH] = pairs_total;
     }
 
     int64_t slice = (int64_t)std::max<size_t>(1, kRingSlotBytes / row_bytes);
     slice = std::max<int64_t>(rpt, slice / rpt * rpt);
-    if (slice > nD) slice = std::max<int64_t>(rpt, (nD + rpt - 1) / rpt * rpt);
-    const int64_t nslices = nD > 0 ? (nD + slice - 1) / slice : 0;
+    const int64_t dslice = std::min(slice, std::max<int64_t>(rpt, (nD + rpt - 1) / rpt * rpt));
+    const int64_t hslice = std::min(slice, std::max<int64_t>(rpt, (nH + rpt - 1) / rpt * rpt));
+    const int64_t nslices = nD > 0 ? (nD + dslice - 1) / dslice : 0;
+    const int64_t nhslices = nH > 0 ? (nH + hslice - 1) / hslice : 0;
 
     if ((rc = grow(c.d_bases, c.cap_bases, (size_t)nN + CFRK_PAD))) return rc;
     {
@@ -528,7 +516,7 @@ int cfrk_count_dense_host(const void* bases, int fmt, const int64_t* start, cons
         }
     }
     if (nD > 0) {
-        size_t need = (size_t)std::min<int64_t>(slice, nD) * row_bytes;
+        size_t need = (size_t)std::min<int64_t>(dslice, nD) * row_bytes;
         if (need > c.cap_ring) {
             cudaFree(c.d_ring[0]); cudaFree(c.d_ring[1]); c.d_ring[0] = c.d_ring[1] = nullptr; c.cap_ring = 0;
             const int slots = nslices > 1 ? 2 : 1;
@@ -546,17 +534,49 @@ int cfrk_count_dense_host(const void* bases, int fmt, const int64_t* start, cons
         }
     }
     if (nH > 0) {
-        if ((rc = grow(c.d_idx, c.cap_idx, (size_t)std::max<int64_t>(idx_total, 1) * 4))) return rc;
-        if ((rc = grow(c.d_ibeg, c.cap_ibeg, ((size_t)nH + 1) * 8))) return rc;
-        const size_t need = (size_t)std::max<int64_t>(idx_total, 1) * 4;
-        if (need > c.cap_hidx) {
-            if (c.h_idx) cudaFreeHost(c.h_idx);
-            c.h_idx = nullptr; c.cap_hidx = 0;
-            if (cudaMallocHost(reinterpret_cast<void**>(&c.h_idx), need + need / 4) != cudaSuccess) {
+        if ((rc = grow(c.d_hslot, c.cap_hslot, (size_t)std::min(hslice, nH) * row_bytes))) return rc;
+        const size_t np = (size_t)std::max<int64_t>(pairs_total, 1);
+        if (np * 4 > c.cap_pairs) {
+            cudaFree(c.d_pk); cudaFree(c.d_pc); c.d_pk = c.d_pc = nullptr; c.cap_pairs = 0;
+            const size_t want = np * 4 + np + 256;
+            if (cudaMalloc(reinterpret_cast<void**>(&c.d_pk), want) != cudaSuccess || cudaMalloc(reinterpret_cast<void**>(&c.d_pc), want) != cudaSuccess) {
                 cudaGetLastError();
-                return fail(CFRK_ENOMEM, "cudaMallocHost(index lists)");
+                return fail(CFRK_ENOMEM, "cudaMalloc(pairs)");
             }
-            c.cap_hidx = need + need / 4;
+            c.cap_pairs = want;
+        }
+        if ((size_t)nH + 1 > c.cap_prows) {
+            cudaFree(c.d_poff); cudaFree(c.d_prc); c.d_poff = nullptr; c.d_prc = nullptr; c.cap_prows = 0;
+            const size_t want = (size_t)nH + (size_t)nH / 4 + 64;
+            if (cudaMalloc(reinterpret_cast<void**>(&c.d_poff), want * 8) != cudaSuccess || cudaMalloc(reinterpret_cast<void**>(&c.d_prc), want * 4) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(CFRK_ENOMEM, "cudaMalloc(pair offsets)");
+            }
+            c.cap_prows = want;
+        }
+        if (np * 4 > c.cap_hpairs) {
+            if (c.h_pk) cudaFreeHost(c.h_pk);
+            if (c.h_pc) cudaFreeHost(c.h_pc);
+            c.h_pk = c.h_pc = nullptr; c.cap_hpairs = 0;
+            const size_t want = np * 4 + np + 256;
+            if (cudaMallocHost(reinterpret_cast<void**>(&c.h_pk), want) != cudaSuccess || cudaMallocHost(reinterpret_cast<void**>(&c.h_pc), want) != cudaSuccess) {
+                cudaGetLastError();
+                return fail(CFRK_ENOMEM, "cudaMallocHost(pairs)");
+            }
+            c.cap_hpairs = want;
+        }
+        if ((size_t)nH * 4 > c.cap_hprc) {
+            if (c.h_prc) cudaFreeHost(c.h_prc);
+            c.h_prc = nullptr; c.cap_hprc = 0;
+            const size_t want = (size_t)nH * 5 + 256;
+            if (cudaMallocHost(reinterpret_cast<void**>(&c.h_prc), want) != cudaSuccess) { cudaGetLastError(); return fail(CFRK_ENOMEM, "cudaMallocHost(pair counts)"); }
+            c.cap_hprc = want;
+        }
+        while ((int64_t)c.ready.size() < nhslices) {
+            cudaEvent_t e1 = nullptr, e2 = nullptr;
+            CU(cudaEventCreateWithFlags(&e1, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&e2, cudaEventDisableTiming));
+            c.packed.push_back(e1); c.ready.push_back(e2);
         }
     }
 
@@ -565,38 +585,54 @@ int cfrk_count_dense_host(const void* bases, int fmt, const int64_t* start, cons
     CU(cudaMemsetAsync(static_cast<char*>(c.d_bases) + nN, 0xFF, CFRK_PAD, c.compute));
     CU(cudaMemcpyAsync(c.d_start, start, (size_t)nS * 8, cudaMemcpyHostToDevice, c.compute));
     CU(cudaMemcpyAsync(c.d_length, length, (size_t)nS * 4, cudaMemcpyHostToDevice, c.compute));
+    if (nH > 0) CU(cudaMemcpyAsync(c.d_poff, poff.data(), ((size_t)nH + 1) * 8, cudaMemcpyHostToDevice, c.compute));
 
-    if (nH > 0) {
-        // index lists first: they are small, and the host threads can start while the dense rows move
-        CU(cudaMemcpyAsync(c.d_ibeg, ibeg.data(), ((size_t)nH + 1) * 8, cudaMemcpyHostToDevice, c.compute));
-        cudaError_t e = cfrk::launch_dense_index(c.d_bases, fmt, c.d_start, c.d_length, c.d_ibeg, nD, nS, k, mode, c.d_idx, c.compute);
-        if (e != cudaSuccess) return fail_cuda(e, "dense_index_kernel launch");
-        CU(cudaMemcpyAsync(c.h_idx, c.d_idx, (size_t)idx_total * 4, cudaMemcpyDeviceToHost, c.compute));
-        CU(cudaEventRecord(c.idx_ready, c.compute));
-    }
+    // host slices and DMA slices alternate on the compute stream, so both ways into the caller's buffer are
+    // fed from the start; every row -- compat spill included -- is counted by the same kernels
     CU(cudaEventRecord(c.t0, c.compute));
-    for (int64_t s = 0; s < nslices; s++) {
-        const int slot = (int)(s & 1);
-        const int64_t r0 = s * slice, r1 = std::min(nD, r0 + slice);
-        if (s >= 2) CU(cudaStreamWaitEvent(c.compute, c.drained[slot], 0));
-        cudaError_t e = cfrk::launch_dense(c.d_bases, fmt, c.d_start, c.d_length, nN, nS, r0, r1, k, mode,
-                                           0, 0, c.d_ring[slot], c.compute);
-        if (e != cudaSuccess) return fail_cuda(e, "dense_count_kernel launch");
-        CU(cudaEventRecord(c.done[slot], c.compute));
-        CU(cudaStreamWaitEvent(c.copy, c.done[slot], 0));
-        CU(cudaMemcpyAsync(freq_out + (size_t)r0 * fourk, c.d_ring[slot], (size_t)(r1 - r0) * row_bytes,
-                           cudaMemcpyDeviceToHost, c.copy));
-        CU(cudaEventRecord(c.drained[slot], c.copy));
+    for (int64_t s = 0; s < std::max(nslices, nhslices); s++) {
+        if (s < nhslices) {
+            const int64_t h0 = s * hslice, h1 = std::min(nH, h0 + hslice);        // relative to nD
+            cudaError_t e = cfrk::launch_dense(c.d_bases, fmt, c.d_start, c.d_length, nN, nS, nD + h0, nD + h1, k, mode,
+                                               0, 0, c.d_hslot, c.compute);
+            if (e != cudaSuccess) return fail_cuda(e, "dense_count_kernel launch");
+            e = cfrk::launch_rows_to_pairs(c.d_hslot, h1 - h0, (int)fourk, c.d_poff + h0, c.d_pk, c.d_pc, c.d_prc + h0, c.compute);
+            if (e != cudaSuccess) return fail_cuda(e, "rows_to_pairs_kernel launch");
+            CU(cudaEventRecord(c.packed[(size_t)s], c.compute));
+            CU(cudaStreamWaitEvent(c.aux, c.packed[(size_t)s], 0));
+            const size_t p0 = (size_t)poff[(size_t)h0], p1 = (size_t)poff[(size_t)h1];
+            CU(cudaMemcpyAsync(c.h_prc + h0, c.d_prc + h0, (size_t)(h1 - h0) * 4, cudaMemcpyDeviceToHost, c.aux));
+            if (p1 > p0) {
+                CU(cudaMemcpyAsync(c.h_pk + p0, c.d_pk + p0, (p1 - p0) * 4, cudaMemcpyDeviceToHost, c.aux));
+                CU(cudaMemcpyAsync(c.h_pc + p0, c.d_pc + p0, (p1 - p0) * 4, cudaMemcpyDeviceToHost, c.aux));
+            }
+            CU(cudaEventRecord(c.ready[(size_t)s], c.aux));
+        }
+        if (s < nslices) {
+            const int slot = (int)(s & 1);
+            const int64_t r0 = s * dslice, r1 = std::min(nD, r0 + dslice);
+            if (s >= 2) CU(cudaStreamWaitEvent(c.compute, c.drained[slot], 0));
+            cudaError_t e = cfrk::launch_dense(c.d_bases, fmt, c.d_start, c.d_length, nN, nS, r0, r1, k, mode,
+                                               0, 0, c.d_ring[slot], c.compute);
+            if (e != cudaSuccess) return fail_cuda(e, "dense_count_kernel launch");
+            CU(cudaEventRecord(c.done[slot], c.compute));
+            CU(cudaStreamWaitEvent(c.copy, c.done[slot], 0));
+            CU(cudaMemcpyAsync(freq_out + (size_t)r0 * fourk, c.d_ring[slot], (size_t)(r1 - r0) * row_bytes,
+                               cudaMemcpyDeviceToHost, c.copy));
+            CU(cudaEventRecord(c.drained[slot], c.copy));
+        }
     }
     CU(cudaEventRecord(c.t1, c.copy));
     double host_ms = 0.0;
-    if (nH > 0) {
-        CU(cudaEventSynchronize(c.idx_ready));
-        const auto h0 = std::chrono::steady_clock::now();
-        expand_rows(c.h_idx, ibeg.data(), nD, nS, fourk, mode, freq_out, nt);
-        host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+    for (int64_t s = 0; s < nhslices; s++) {
+        CU(cudaEventSynchronize(c.ready[(size_t)s]));
+        const int64_t h0 = s * hslice, h1 = std::min(nH, h0 + hslice);
+        const auto t_a = std::chrono::steady_clock::now();
+        expand_rows(c.h_pk, c.h_pc, poff.data(), c.h_prc, h0, h1, fourk, freq_out + (size_t)nD * fourk, nt);
+        host_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_a).count();
     }
     CU(cudaStreamSynchronize(c.copy));
+    CU(cudaStreamSynchronize(c.aux));
     CU(cudaStreamSynchronize(c.compute));
     static const bool trace = getenv("CFRK_TRACE") != nullptr;
     if (trace) {

@@ -50,10 +50,10 @@ cudaError_t launch_unwrap(const uint8_t* d_buf, int64_t n, const int64_t* d_head
                           const int64_t* d_start, int64_t nrec, uint8_t* d_out, int64_t* d_new_start,
                           int32_t* d_new_length, cudaStream_t st);
 
-// Index list of the visited windows of reads [r_begin, r_end) (dense_index.cu): what the host-buffer
-// operator ships over PCIe for the rows that host threads expand.  k <= 12.
-cudaError_t launch_dense_index(const void* bases, int fmt, const int64_t* start, const int32_t* length, const int64_t* ibeg,
-                               int64_t r_begin, int64_t r_end, int k, int mode, uint32_t* idx_out, cudaStream_t st);
+// Dense rows in HBM -> (bin, count) pairs of their non-zero bins, row r at keys/counts[off[r] ..] (row_pairs.cu):
+// what the host-buffer operator ships over PCIe for the rows that host threads expand.
+cudaError_t launch_rows_to_pairs(const int32_t* rows, int64_t nrows, int bins, const int64_t* off, uint32_t* keys,
+                                 uint32_t* counts, int32_t* row_count, cudaStream_t st);
 
 uint64_t launch_count();
 

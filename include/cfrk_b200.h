@@ -100,8 +100,8 @@ int cfrk_count_dense_host(const void *bases, int fmt, const int64_t *start, cons
  * Host threads of cfrk_count_dense_host / kmer_main (the reference's `nt`, src/main.cu:235, is parsed
  * and unused: its OpenMP pragmas are compiled without -fopenmp).  For rows of >= 4 KiB the operator
  * splits a batch: one share of the rows is written into the caller's buffer by the GPU's DMA engine,
- * for the rest only the k-mer index of each window crosses PCIe and n host threads write the rows
- * (zeros + counts, streaming stores).  The k-mers are computed on the GPU either way.  n = 0: DMA only;
+ * the rest is counted on the GPU as well, compacted there to (bin, count) pairs, and n host threads expand
+ * the pairs into the rows (zeros + counts, streaming stores).  Nothing is counted on the host.  n = 0: DMA only;
  * n < 0: back to the default.
  * Default: min(hardware threads, 16), or the environment variable CFRK_HOST_THREADS.
  */

@@ -127,7 +127,7 @@ def test_dense_rows_up_to_k12(k):
 @pytest.mark.parametrize("mode", [cf.MODE_COMPAT, cf.MODE_EXACT], ids=["compat", "exact"])
 def test_host_operator_split_between_dma_and_host_threads(k, nS, mode):
     """cfrk_count_dense_host on batches large enough for the split: part of the rows arrive as dense rows by DMA, the
-    rest as index lists expanded by host threads (streaming stores); same rows as the oracle, whatever the share and
+    rest as GPU-compacted (bin, count) pairs expanded by host threads (streaming stores); same rows as the oracle, whatever the share and
     the thread count, with N bases (spill across the DMA / host boundary), reads up to the 1024-window cap, a read
     without windows, and an output buffer that is not 64-byte aligned"""
     rng = np.random.default_rng(100 + k)
