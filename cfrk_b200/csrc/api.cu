@@ -77,7 +77,7 @@ struct HostCtx {
     int64_t* d_poff = nullptr; int32_t* d_prc = nullptr; size_t cap_prows = 0;
     uint32_t* h_pk = nullptr; uint32_t* h_pc = nullptr; size_t cap_hpairs = 0;
     int32_t* h_prc = nullptr; size_t cap_hprc = 0;
-    std::vector<cudaEvent_t> packed, ready;     // per host slice: pairs built / pairs in host memory
+    std::vector<cudaEvent_t> packed, ready;     // packed[0]: inputs uploaded; ready[s]: pairs of host slice s in host memory
     cudaEvent_t t0 = nullptr, t1 = nullptr;
     double dma_frac[CFRK_DENSE_MAX_K + 1] = {0};   // share of the rows that goes through the DMA engine, per k (adaptive)
 
@@ -587,28 +587,31 @@ int cfrk_count_dense_host(const void* bases, int fmt, const int64_t* start, cons
     CU(cudaMemcpyAsync(c.d_length, length, (size_t)nS * 4, cudaMemcpyHostToDevice, c.compute));
     if (nH > 0) CU(cudaMemcpyAsync(c.d_poff, poff.data(), ((size_t)nH + 1) * 8, cudaMemcpyHostToDevice, c.compute));
 
-    // host slices and DMA slices alternate on the compute stream, so both ways into the caller's buffer are
-    // fed from the start; every row -- compat spill included -- is counted by the same kernels
+    // The host share runs on its own stream (dense rows into a private slot -> pairs -> small D2H copies), so it
+    // is not held back by the DMA slices, whose kernels wait for their ring slot to drain at PCIe pace; every
+    // row -- compat spill included -- is counted by the same kernels.
     CU(cudaEventRecord(c.t0, c.compute));
-    for (int64_t s = 0; s < std::max(nslices, nhslices); s++) {
-        if (s < nhslices) {
-            const int64_t h0 = s * hslice, h1 = std::min(nH, h0 + hslice);        // relative to nD
-            cudaError_t e = cfrk::launch_dense(c.d_bases, fmt, c.d_start, c.d_length, nN, nS, nD + h0, nD + h1, k, mode,
-                                               0, 0, c.d_hslot, c.compute);
-            if (e != cudaSuccess) return fail_cuda(e, "dense_count_kernel launch");
-            e = cfrk::launch_rows_to_pairs(c.d_hslot, h1 - h0, (int)fourk, c.d_poff + h0, c.d_pk, c.d_pc, c.d_prc + h0, c.compute);
-            if (e != cudaSuccess) return fail_cuda(e, "rows_to_pairs_kernel launch");
-            CU(cudaEventRecord(c.packed[(size_t)s], c.compute));
-            CU(cudaStreamWaitEvent(c.aux, c.packed[(size_t)s], 0));
-            const size_t p0 = (size_t)poff[(size_t)h0], p1 = (size_t)poff[(size_t)h1];
-            CU(cudaMemcpyAsync(c.h_prc + h0, c.d_prc + h0, (size_t)(h1 - h0) * 4, cudaMemcpyDeviceToHost, c.aux));
-            if (p1 > p0) {
-                CU(cudaMemcpyAsync(c.h_pk + p0, c.d_pk + p0, (p1 - p0) * 4, cudaMemcpyDeviceToHost, c.aux));
-                CU(cudaMemcpyAsync(c.h_pc + p0, c.d_pc + p0, (p1 - p0) * 4, cudaMemcpyDeviceToHost, c.aux));
-            }
-            CU(cudaEventRecord(c.ready[(size_t)s], c.aux));
-        }
-        if (s < nslices) {
+    if (nhslices > 0) {
+        CU(cudaEventRecord(c.packed[0], c.compute));            // inputs are in HBM
+        CU(cudaStreamWaitEvent(c.aux, c.packed[0], 0));
+    }
+    for (int64_t s = 0; s < nhslices; s++) {
+        const int64_t h0 = s * hslice, h1 = std::min(nH, h0 + hslice);        // relative to nD
+        cudaError_t e = cfrk::launch_dense(c.d_bases, fmt, c.d_start, c.d_length, nN, nS, nD + h0, nD + h1, k, mode,
+                                           0, 0, c.d_hslot, c.aux);
+        if (e != cudaSuccess) return fail_cuda(e, "dense_count_kernel launch");
+        e = cfrk::launch_rows_to_pairs(c.d_hslot, h1 - h0, (int)fourk, c.d_poff + h0, c.d_pk, c.d_pc, c.d_prc + h0, c.aux);
+        if (e != cudaSuccess) return fail_cuda(e, "rows_to_pairs_kernel launch");
+        const size_t p0 = (size_t)poff[(size_t)h0], p1 = (size_t)poff[(size_t)h1];
+        // pinned host memory is mapped into the device's address space (unified addressing): SM stores, not the
+        // copy engine, which is busy with the dense rows of the DMA share for milliseconds at a time
+        e = cfrk::launch_pairs_to_host(reinterpret_cast<const uint32_t*>(c.d_prc + h0), reinterpret_cast<uint32_t*>(c.h_prc + h0), h1 - h0,
+                                       c.d_pk + p0, c.h_pk + p0, (int64_t)(p1 - p0), c.d_pc + p0, c.h_pc + p0, (int64_t)(p1 - p0), c.aux);
+        if (e != cudaSuccess) return fail_cuda(e, "pairs_to_host_kernel launch");
+        CU(cudaEventRecord(c.ready[(size_t)s], c.aux));
+    }
+    for (int64_t s = 0; s < nslices; s++) {
+        {
             const int slot = (int)(s & 1);
             const int64_t r0 = s * dslice, r1 = std::min(nD, r0 + dslice);
             if (s >= 2) CU(cudaStreamWaitEvent(c.compute, c.drained[slot], 0));

@@ -55,6 +55,10 @@ cudaError_t launch_unwrap(const uint8_t* d_buf, int64_t n, const int64_t* d_head
 cudaError_t launch_rows_to_pairs(const int32_t* rows, int64_t nrows, int bins, const int64_t* off, uint32_t* keys,
                                  uint32_t* counts, int32_t* row_count, cudaStream_t st);
 
+// three word-wise copies into mapped pinned host memory, done by SMs (the copy engine is busy with dense rows)
+cudaError_t launch_pairs_to_host(const uint32_t* s0, uint32_t* d0, int64_t n0, const uint32_t* s1, uint32_t* d1, int64_t n1,
+                                 const uint32_t* s2, uint32_t* d2, int64_t n2, cudaStream_t st);
+
 uint64_t launch_count();
 
 }  // namespace cfrk

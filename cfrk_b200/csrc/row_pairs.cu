@@ -46,6 +46,30 @@ __global__ void __launch_bounds__(256) rows_to_pairs_kernel(const int32_t* __res
     }
 }
 
+// Three small device -> pinned-host copies done by SMs (stores to mapped host memory) instead of the copy
+// engine: the engine is busy for milliseconds at a time with the dense rows of the DMA share, and the
+// pairs of the host share would queue behind them.
+__global__ void __launch_bounds__(256) pairs_to_host_kernel(const uint32_t* __restrict__ s0, uint32_t* __restrict__ d0, int64_t n0,
+                                                            const uint32_t* __restrict__ s1, uint32_t* __restrict__ d1, int64_t n1,
+                                                            const uint32_t* __restrict__ s2, uint32_t* __restrict__ d2, int64_t n2)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t i = t; i < n0; i += stride) d0[i] = s0[i];
+    for (int64_t i = t; i < n1; i += stride) d1[i] = s1[i];
+    for (int64_t i = t; i < n2; i += stride) d2[i] = s2[i];
+}
+
+cudaError_t launch_pairs_to_host(const uint32_t* s0, uint32_t* d0, int64_t n0, const uint32_t* s1, uint32_t* d1, int64_t n1,
+                                 const uint32_t* s2, uint32_t* d2, int64_t n2, cudaStream_t st)
+{
+    const int64_t n = n0 > n1 ? (n0 > n2 ? n0 : n2) : (n1 > n2 ? n1 : n2);
+    if (n <= 0) return cudaSuccess;
+    const int64_t ctas = (n + 255) / 256;
+    pairs_to_host_kernel<<<(unsigned)(ctas < 148 * 4 ? ctas : 148 * 4), 256, 0, st>>>(s0, d0, n0, s1, d1, n1, s2, d2, n2);
+    count_launch();
+    return cudaGetLastError();
+}
+
 cudaError_t launch_rows_to_pairs(const int32_t* rows, int64_t nrows, int bins, const int64_t* off, uint32_t* keys,
                                  uint32_t* counts, int32_t* row_count, cudaStream_t st)
 {
