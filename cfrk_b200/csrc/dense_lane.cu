@@ -136,15 +136,16 @@ __device__ __forceinline__ void bulk_load(uint32_t sdst, const void* gsrc, uint3
 }
 
 // ---- geometry per (K, SPLIT)
-template <int K, int SPLIT>
+template <int K, int SPLIT, int FMT>
 struct LaneGeo {
     static constexpr int BINS = 1 << (2 * K);
     static constexpr int R = 32 / SPLIT;                       // reads (rows) per warp tile
     static constexpr int OUT_BYTES = R * BINS * 4;             // the tile's rows, contiguous = one bulk store
     static constexpr int ROW_ALIGN = BINS * 4 < 128 ? 128 : BINS * 4;
     // staging: bytes of the bases buffer one tile may span (reads + separators + header lines of a FASTA
-    // span): 272 per read on average covers 250-bp reads with short headers; longer -> warp-wide path
-    static constexpr int SPAN = R * 272;
+    // span): 272 per read on average covers 250-bp reads with short headers; longer -> warp-wide path.
+    // Packed reads need 6 bytes per 16 bases: the same span in 104 bytes per read -- more warps per SM.
+    static constexpr int SPAN = FMT == FMT_PACKED ? R * 104 : R * 272;
     static constexpr int WARP_BYTES = OUT_BYTES + SPAN;
 };
 
@@ -250,10 +251,10 @@ __device__ __forceinline__ uint4 fetch_block(const BasesRef& bases, const Stage&
 }  // namespace
 
 // ------------------------------------------------------------------------------------------
-template <int K, int FMT, int SPLIT, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) dense_lane_kernel(const DenseArgs a)
+template <int K, int FMT, int SPLIT, int WARPS, int MINB = 1>
+__global__ void __launch_bounds__(WARPS * 32, MINB) dense_lane_kernel(const DenseArgs a)
 {
-    using G = LaneGeo<K, SPLIT>;
+    using G = LaneGeo<K, SPLIT, FMT>;
     constexpr int BINS = G::BINS, R = G::R;
     constexpr bool PLANES = K <= 2;
     static_assert(!PLANES || SPLIT == 1, "register rows belong to one lane");
@@ -502,11 +503,11 @@ __global__ void __launch_bounds__(WARPS * 32) dense_lane_kernel(const DenseArgs 
 }
 
 // ------------------------------------------------------------------------------------------
-template <int K, int FMT, int SPLIT, int WARPS>
+template <int K, int FMT, int SPLIT, int WARPS, int MINB = 1>
 static cudaError_t launch_lane_t(const DenseArgs& a0, cudaStream_t st)
 {
-    using G = LaneGeo<K, SPLIT>;
-    auto kern = dense_lane_kernel<K, FMT, SPLIT, WARPS>;
+    using G = LaneGeo<K, SPLIT, FMT>;
+    auto kern = dense_lane_kernel<K, FMT, SPLIT, WARPS, MINB>;
     constexpr int smem = WARPS * G::WARP_BYTES + WARPS * 8 + G::ROW_ALIGN;
     static thread_local int configured_dev = -1;
     static thread_local int ctas_per_sm = 0, num_sms = 0;
@@ -554,21 +555,27 @@ static int lane_env(const char* name, int dflt)
 }
 
 // lane groups per k: measured choices (profiles/r2_notes.md); the environment switches re-run the A/B
-static int lane_split(int k)
+static int lane_split(int k, int fmt)
 {
-    static const int s3 = lane_env("CFRK_LANE_SPLIT_K3", 2), s4 = lane_env("CFRK_LANE_SPLIT_K4", 4);
-    return k <= 2 ? 1 : (k == 3 ? s3 : s4);
+    // k = 3 from packed reads: the small staging buffer leaves room for a lane per read (32-read tiles: the
+    // tile set-up is paid once per 32 reads instead of 16) at 20 warps per SM
+    static const int s3 = lane_env("CFRK_LANE_SPLIT_K3", 0), s4 = lane_env("CFRK_LANE_SPLIT_K4", 4);
+    return k <= 2 ? 1 : (k == 3 ? (s3 ? s3 : (fmt == FMT_PACKED ? 1 : 2)) : s4);
 }
 
-int dense_lane_reads_per_tile(int k) { return 32 / lane_split(k); }
+// granularity for callers that cut a batch into ranges: a multiple of the tile of every layout
+int dense_lane_reads_per_tile(int k) { return k <= 3 ? 32 : 32 / lane_split(k, FMT_ASCII); }
 
 template <int FMT>
 static cudaError_t launch_lane_fmt(int k, const DenseArgs& a, cudaStream_t st)
 {
-    const int sp = lane_split(k);
+    const int sp = lane_split(k, FMT);
     switch (k) {
     case 1: return launch_lane_t<1, FMT, 1, 4>(a, st);
-    case 2: return launch_lane_t<2, FMT, 1, 4>(a, st);
+    case 2: {
+        static const int minb = lane_env("CFRK_LANE_MINB_K2", 1);      // 8: cap at 64 registers (A/B)
+        return minb == 8 ? launch_lane_t<2, FMT, 1, 4, 8>(a, st) : launch_lane_t<2, FMT, 1, 4>(a, st);
+    }
     case 3:
         if (sp == 1) return launch_lane_t<3, FMT, 1, 4>(a, st);
         if (sp == 4) return launch_lane_t<3, FMT, 4, 4>(a, st);

@@ -42,7 +42,7 @@ def test_no_torch_types_in_header():
 
 def test_version_and_tile_geometry():
     assert "sm_100a" in cf.version()
-    assert [cf.dense_reads_per_tile(k) for k in range(1, 9)] == [32, 32, 16, 8, 4, 1, 1, 1]
+    assert [cf.dense_reads_per_tile(k) for k in range(1, 9)] == [32, 32, 32, 8, 4, 1, 1, 1]
 
 
 def test_argument_validation_needs_no_gpu():
