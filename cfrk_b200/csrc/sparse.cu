@@ -432,58 +432,70 @@ constexpr int kHalfE = 9;
 constexpr int kHalfSlots = 16 * kHalfE;              // 144
 constexpr int kHalfBlocks = 16;                      // 16-base blocks per half-warp stream
 
-template <typename KeyT>
-__device__ __forceinline__ void sort9(KeyT (&k)[kHalfE])
+// optimal comparator networks for 9 inputs (25 comparators) and 11 inputs (35), checked with the 0-1 principle
+template <typename KeyT, int E>
+__device__ __forceinline__ void sort_lane(KeyT (&k)[E])
 {
+    static_assert(E == 9 || E == 11, "networks for 9 and 11 keys per lane");
 #define CFRK_CE(i, j) { const KeyT a_ = k[i], b_ = k[j]; k[i] = a_ < b_ ? a_ : b_; k[j] = a_ < b_ ? b_ : a_; }
-    CFRK_CE(0, 3) CFRK_CE(1, 7) CFRK_CE(2, 5) CFRK_CE(4, 8)
-    CFRK_CE(0, 7) CFRK_CE(2, 4) CFRK_CE(3, 8) CFRK_CE(5, 6)
-    CFRK_CE(0, 2) CFRK_CE(1, 3) CFRK_CE(4, 5) CFRK_CE(7, 8)
-    CFRK_CE(1, 4) CFRK_CE(3, 6) CFRK_CE(5, 7)
-    CFRK_CE(0, 1) CFRK_CE(2, 4) CFRK_CE(3, 5) CFRK_CE(6, 8)
-    CFRK_CE(2, 3) CFRK_CE(4, 5) CFRK_CE(6, 7)
-    CFRK_CE(1, 2) CFRK_CE(3, 4) CFRK_CE(5, 6)
+    if constexpr (E == 9) {
+        CFRK_CE(0, 3) CFRK_CE(1, 7) CFRK_CE(2, 5) CFRK_CE(4, 8)
+        CFRK_CE(0, 7) CFRK_CE(2, 4) CFRK_CE(3, 8) CFRK_CE(5, 6)
+        CFRK_CE(0, 2) CFRK_CE(1, 3) CFRK_CE(4, 5) CFRK_CE(7, 8)
+        CFRK_CE(1, 4) CFRK_CE(3, 6) CFRK_CE(5, 7)
+        CFRK_CE(0, 1) CFRK_CE(2, 4) CFRK_CE(3, 5) CFRK_CE(6, 8)
+        CFRK_CE(2, 3) CFRK_CE(4, 5) CFRK_CE(6, 7)
+        CFRK_CE(1, 2) CFRK_CE(3, 4) CFRK_CE(5, 6)
+    } else {
+        CFRK_CE(0, 9) CFRK_CE(1, 6) CFRK_CE(2, 4) CFRK_CE(3, 7) CFRK_CE(5, 8)
+        CFRK_CE(0, 1) CFRK_CE(3, 5) CFRK_CE(4, 10) CFRK_CE(6, 9) CFRK_CE(7, 8)
+        CFRK_CE(1, 3) CFRK_CE(2, 5) CFRK_CE(4, 7) CFRK_CE(8, 10)
+        CFRK_CE(0, 4) CFRK_CE(1, 2) CFRK_CE(3, 7) CFRK_CE(5, 9) CFRK_CE(6, 8)
+        CFRK_CE(0, 1) CFRK_CE(2, 6) CFRK_CE(4, 5) CFRK_CE(7, 8) CFRK_CE(9, 10)
+        CFRK_CE(2, 4) CFRK_CE(3, 6) CFRK_CE(5, 7) CFRK_CE(8, 9)
+        CFRK_CE(1, 2) CFRK_CE(3, 4) CFRK_CE(5, 6) CFRK_CE(7, 8)
+        CFRK_CE(2, 3) CFRK_CE(4, 5) CFRK_CE(6, 7)
+    }
 #undef CFRK_CE
 }
 
-// 16 lanes x 9 keys, blocked layout (lane hl holds elements 9*hl .. 9*hl+8), ascending; both halves of
+// 16 lanes x E keys, blocked layout (lane hl holds elements E*hl .. E*hl+E-1), ascending; both halves of
 // the warp at once (lane masks < 16 never cross the halves)
-template <typename KeyT>
-__device__ __forceinline__ void half_sort(KeyT (&key)[kHalfE])
+template <typename KeyT, int E = kHalfE>
+__device__ __forceinline__ void half_sort(KeyT (&key)[E])
 {
     const int hl = threadIdx.x & 15;
-    sort9<KeyT>(key);
+    sort_lane<KeyT, E>(key);
 #pragma unroll
     for (int m = 2; m <= 16; m <<= 1) {
-        {   // mirrored compare: element e with element 8-e of lane hl ^ (m-1)
+        {   // mirrored compare: element e with element E-1-e of lane hl ^ (m-1)
             const bool upper = (hl & (m >> 1)) != 0;
-            KeyT other[kHalfE];
+            KeyT other[E];
 #pragma unroll
-            for (int e = 0; e < kHalfE; e++) other[e] = __shfl_xor_sync(0xffffffffu, key[kHalfE - 1 - e], m - 1);
+            for (int e = 0; e < E; e++) other[e] = __shfl_xor_sync(0xffffffffu, key[E - 1 - e], m - 1);
 #pragma unroll
-            for (int e = 0; e < kHalfE; e++) key[e] = keep_minmax<KeyT>(key[e], other[e], upper);
+            for (int e = 0; e < E; e++) key[e] = keep_minmax<KeyT>(key[e], other[e], upper);
         }
 #pragma unroll
         for (int st = m >> 2; st >= 1; st >>= 1) {
             const bool upper = (hl & st) != 0;
 #pragma unroll
-            for (int e = 0; e < kHalfE; e++) {
+            for (int e = 0; e < E; e++) {
                 const KeyT other = __shfl_xor_sync(0xffffffffu, key[e], st);
                 key[e] = keep_minmax<KeyT>(key[e], other, upper);
             }
         }
-        sort9<KeyT>(key);
+        sort_lane<KeyT, E>(key);
     }
 }
 
 // sorted keys of one half (first nvalid slots real) -> (key, count) pairs; both halves run in lockstep
 // (every shuffle is a full-mask shuffle of width 16).  Returns the number of pairs of this half.
-template <typename KeyT>
-__device__ __forceinline__ int half_rle_store(const KeyT (&key)[kHalfE], int nvalid, KeyT* __restrict__ keys_out,
+template <typename KeyT, int E = kHalfE>
+__device__ __forceinline__ int half_rle_store(const KeyT (&key)[E], int nvalid, KeyT* __restrict__ keys_out,
                                               uint32_t* __restrict__ counts_out, KeyT* __restrict__ stage_k,
                                               uint32_t* __restrict__ stage_c)
 {
-    constexpr int E = kHalfE;
     const int hl = threadIdx.x & 15;
     const int vpos0 = hl * E;
     const int nlive = min(E, max(0, nvalid - vpos0));
@@ -499,7 +511,7 @@ __device__ __forceinline__ int half_rle_store(const KeyT (&key)[kHalfE], int nva
     // common case: every key of BOTH reads is distinct -> element v goes to slot v with count 1
     if (__all_sync(0xffffffffu, heads == live)) {
 #pragma unroll
-        for (int e = 0; e < E; e++) stage_k[vpos0 + e] = key[e];      // stride 9 words: conflict-free
+        for (int e = 0; e < E; e++) stage_k[vpos0 + e] = key[e];      // odd stride in words: conflict-free
         __syncwarp();
         for (int i = hl; i < nvalid; i += 16) {
             keys_out[i] = stage_k[i];
@@ -602,9 +614,9 @@ __global__ void __launch_bounds__(kSparseWarps * 32) sparse_half_kernel(
         int nvalid = __popc(valid);
 #pragma unroll
         for (int d = 8; d >= 1; d >>= 1) nvalid += __shfl_xor_sync(0xffffffffu, nvalid, d);
-        half_sort<KeyT>(key);
+        half_sort<KeyT, kHalfE>(key);
         const int64_t rb = mine ? row_begin[r] : 0;
-        const int nd = half_rle_store<KeyT>(key, nvalid, keys + rb, counts + rb, s_stage_k[warp][h], s_stage_c[warp][h]);
+        const int nd = half_rle_store<KeyT, kHalfE>(key, nvalid, keys + rb, counts + rb, s_stage_k[warp][h], s_stage_c[warp][h]);
         if (mine && hl == 0) row_count[r] = nd;
     }
 }
@@ -976,7 +988,7 @@ __global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) bucket_sort_kernel(
     const unsigned long long* __restrict__ bend, int64_t nb, KeyT* __restrict__ scratch, uint32_t* __restrict__ pc,
     unsigned long long* __restrict__ distinct, int64_t* __restrict__ fb_list, unsigned long long* __restrict__ n_fb,
     const int64_t* __restrict__ boff, int64_t j0, int64_t j1, const int64_t* __restrict__ long_rows,
-    const int32_t* __restrict__ length, int k)
+    const int32_t* __restrict__ length, int k, int min_keys, bool list_oversized)
 {
     constexpr int WARPS = SparseCta<E>::WARPS;
     __shared__ __align__(16) KeyT s_stage_k[WARPS][32 * E];
@@ -985,8 +997,8 @@ __global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) bucket_sort_kernel(
     for (int64_t b = (int64_t)blockIdx.x * WARPS + warp; b < nb; b += (int64_t)gridDim.x * WARPS) {
         const int64_t beg = b ? (int64_t)bend[b - 1] : 0;
         const int64_t n64 = (int64_t)bend[b] - beg;
-        if (E == 4 && n64 > kBucketCap && lane == 0) fb_list[atomicAdd(n_fb, 1ull)] = b;
-        if (n64 == 0 || n64 > 32 * E || (E > 4 && n64 <= 16 * E)) continue;
+        if (list_oversized && n64 > kBucketCap && lane == 0) fb_list[atomicAdd(n_fb, 1ull)] = b;
+        if (n64 == 0 || n64 > 32 * E || n64 < min_keys) continue;
         const int n = (int)n64;
         KeyT key[E];
         uint32_t valid = 0;
@@ -1007,6 +1019,47 @@ __global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) bucket_sort_kernel(
         __syncwarp();   // every lane has its keys: the bucket's place is rewritten below
         const int nd = warp_sort_rle<KeyT, E>(key, valid, gshift, scratch + beg, pc + beg, s_stage_k[warp], s_stage_c[warp]);
         if (lane == 0) distinct[b] = (unsigned long long)nd;
+    }
+}
+
+// Buckets of <= 176 keys (97 % of them on uniform keys: the mean is ~150): TWO buckets per warp, 16 lanes x 11
+// keys each, the network of the short reads with an 11-input lane network (35 comparators).  Also lists the
+// buckets that are too large for a warp.
+constexpr int kHalfBucketE = 11;
+constexpr int kHalfBucketSlots = 16 * kHalfBucketE;   // 176
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kSparseWarps * 32) bucket_sort_half_kernel(
+    const unsigned long long* __restrict__ bend, int64_t nb, KeyT* __restrict__ scratch, uint32_t* __restrict__ pc,
+    unsigned long long* __restrict__ distinct, int64_t* __restrict__ fb_list, unsigned long long* __restrict__ n_fb)
+{
+    constexpr int WARPS = kSparseWarps, E = kHalfBucketE;
+    __shared__ __align__(16) KeyT s_stage_k[WARPS][2][kHalfBucketSlots];
+    __shared__ uint32_t s_stage_c[WARPS][2][kHalfBucketSlots];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int h = lane >> 4, hl = lane & 15;
+    const int64_t npairs = (nb + 1) >> 1;
+    for (int64_t pair = (int64_t)blockIdx.x * WARPS + warp; pair < npairs; pair += (int64_t)gridDim.x * WARPS) {
+        const int64_t b = 2 * pair + h;
+        int64_t beg = 0, n64 = 0;
+        if (b < nb) {
+            beg = b ? (int64_t)bend[b - 1] : 0;
+            n64 = (int64_t)bend[b] - beg;
+            if (n64 > kBucketCap && hl == 0) fb_list[atomicAdd(n_fb, 1ull)] = b;
+        }
+        const bool mine = n64 > 0 && n64 <= kHalfBucketSlots;
+        if (!__any_sync(0xffffffffu, mine)) continue;
+        const int n = mine ? (int)n64 : 0;
+        KeyT key[E];
+#pragma unroll
+        for (int e = 0; e < E; e++) {      // any placement will do: the network sorts it
+            const int g = e * 16 + hl;
+            key[e] = g < n ? scratch[beg + g] : KeyMax<KeyT>::value;
+        }
+        __syncwarp();   // every lane has its keys: the bucket's place is rewritten below
+        half_sort<KeyT, E>(key);
+        const int nd = half_rle_store<KeyT, E>(key, n, scratch + beg, pc + beg, s_stage_k[warp][h], s_stage_c[warp][h]);
+        if (mine && hl == 0) distinct[b] = (unsigned long long)nd;
     }
 }
 
@@ -1329,9 +1382,18 @@ static cudaError_t sparse_long_rows(const uint8_t* bases, const int64_t* start, 
         {
             const unsigned g4 = (unsigned)std::min<int64_t>((nb + SparseCta<4>::WARPS - 1) / SparseCta<4>::WARPS, (int64_t)num_sms * 8);
             const unsigned g16 = (unsigned)std::min<int64_t>((nb + SparseCta<16>::WARPS - 1) / SparseCta<16>::WARPS, (int64_t)num_sms * 8);
-            bucket_sort_kernel<SortT, 4><<<g4, SparseCta<4>::WARPS * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb, boff, j0, j1, long_rows, length, k);
-            bucket_sort_kernel<SortT, 8><<<g4, SparseCta<8>::WARPS * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb, boff, j0, j1, long_rows, length, k);
-            bucket_sort_kernel<SortT, 16><<<g16, SparseCta<16>::WARPS * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb, boff, j0, j1, long_rows, length, k);
+            static const bool half_buckets = !(getenv("CFRK_SPARSE_HALF") && atoi(getenv("CFRK_SPARSE_HALF")) == 0);
+            if (half_buckets) {
+                // <= 176 keys: two buckets per warp; 177..256 and 257..512: one warp each
+                const unsigned gh = (unsigned)std::min<int64_t>(((nb + 1) / 2 + kSparseWarps - 1) / kSparseWarps, (int64_t)num_sms * 8);
+                bucket_sort_half_kernel<SortT><<<gh, kSparseWarps * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb);
+                bucket_sort_kernel<SortT, 8><<<g4, SparseCta<8>::WARPS * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb, boff, j0, j1, long_rows, length, k, kHalfBucketSlots + 1, false);
+                bucket_sort_kernel<SortT, 16><<<g16, SparseCta<16>::WARPS * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb, boff, j0, j1, long_rows, length, k, 257, false);
+            } else {
+                bucket_sort_kernel<SortT, 4><<<g4, SparseCta<4>::WARPS * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb, boff, j0, j1, long_rows, length, k, 1, true);
+                bucket_sort_kernel<SortT, 8><<<g4, SparseCta<8>::WARPS * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb, boff, j0, j1, long_rows, length, k, 129, false);
+                bucket_sort_kernel<SortT, 16><<<g16, SparseCta<16>::WARPS * 32, 0, st>>>(bucket, nb, scratch, pc, distinct, fb_list, n_fb, boff, j0, j1, long_rows, length, k, 257, false);
+            }
             count_launch(); count_launch(); count_launch();
         }
         unsigned long long nfb = 0;
