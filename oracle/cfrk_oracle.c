@@ -3,7 +3,8 @@
  *
  * TEST INFRASTRUCTURE ONLY (see cfrk_oracle.h).  Parity status: PINNED against
  * the reference's goldens and against the reference's own code run on the CPU
- * (tests/test_oracle_golden.py, tests/test_oracle_ref_shim.py).
+ * (tests/test_oracle_golden.py: goldens through the stand-in inputs, the sha256 manifest of the reference's own
+ * sources compiled for the CPU, and a live comparison with oracle/_ref/cfrk_ref_cpu).
  *
  * Written from the behavioural spec in SURVEY.md 8(c); each function cites the
  * reference lines it restates.  Deliberately the *slow obvious* algorithm
