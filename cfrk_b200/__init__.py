@@ -7,6 +7,6 @@ anywhere, calling a compute entry point without a CUDA device raises CfrkError.
 """
 from .api import (  # noqa: F401
     CfrkError, FMT_ASCII, FMT_CODES, MODE_COMPAT, MODE_EXACT, RUN_ALL_ROWS, RUN_EXACT, RUN_SPARSE,
-    count_dense_device, count_dense_host, count_dense_packed_device, count_sparse_device, dense_reads_per_tile, device_count, encode_2bit_device,
+    count_dense_device, count_dense_host, count_dense_packed_device, count_sparse_device, count_sparse_packed_device, dense_reads_per_tile, device_count, encode_2bit_device,
     global_hist_device, kmer_main, launch_count, lib, run_file, scan_fasta_device, version,
 )

@@ -10,7 +10,7 @@ SYMBOLS = [
     "cfrk_version", "cfrk_last_error", "cfrk_device_count", "cfrk_launch_count", "cfrk_release", "cfrk_free_host",
     "cfrk_count_dense_host", "cfrk_set_host_threads", "cfrk_count_dense_device", "cfrk_count_dense_packed_device",
     "cfrk_dense_reads_per_tile",
-    "cfrk_encode_2bit_device", "cfrk_global_hist_device", "cfrk_count_sparse_device", "cfrk_scan_fasta_device",
+    "cfrk_encode_2bit_device", "cfrk_global_hist_device", "cfrk_count_sparse_device", "cfrk_count_sparse_packed_device", "cfrk_scan_fasta_device",
     "cfrk_run_file", "cfrk_run_file_multi",
 ]
 
@@ -44,6 +44,8 @@ def load():
     L.cfrk_global_hist_device.argtypes = [vp, i32, vp, vp, i64, i64, i32, vp, vp]
     L.cfrk_count_sparse_device.argtypes = [vp, i32, vp, vp, i64, i64, i32, i32, vp, vp, vp, vp, i64,
                                            C.POINTER(C.c_int64), vp]
+    L.cfrk_count_sparse_packed_device.argtypes = [vp, vp, vp, vp, i64, i64, i32, i32, vp, vp, vp, vp, i64,
+                                                  C.POINTER(C.c_int64), vp]
     L.cfrk_scan_fasta_device.argtypes = [vp, i64, i32, vp, vp, vp, i64, C.POINTER(C.c_int64), vp]
     L.cfrk_run_file.argtypes = [C.c_char_p, C.c_char_p, i32, i32, i64, i32, i32]
     L.cfrk_run_file_multi.argtypes = [C.c_char_p, C.c_char_p, i32, i32, i64, i32, C.POINTER(C.c_int), i32]

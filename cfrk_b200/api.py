@@ -113,6 +113,16 @@ def count_sparse_device(d_bases, d_start, d_length, nN, nS, k, d_row_begin, d_ro
     return total.value
 
 
+def count_sparse_packed_device(d_codes, d_valid, d_start, d_length, nN, nS, k, d_row_begin, d_row_count, d_keys, d_counts,
+                               capacity, key_bytes=8, stream=0):
+    """Sparse per-read rows from packed 2-bit reads (the output of encode_2bit_device)."""
+    total = C.c_int64(0)
+    _check(lib().cfrk_count_sparse_packed_device(d_codes, d_valid, d_start, d_length, nN, nS, k, key_bytes, d_row_begin,
+                                                 d_row_count, d_keys, d_counts, capacity, C.byref(total), stream),
+           "cfrk_count_sparse_packed_device")
+    return total.value
+
+
 def scan_fasta_device(d_bytes, n, is_final, d_header, d_start, d_length, capacity, stream=0):
     """Record table of raw FASTA bytes on the GPU; returns the number of headers in the span."""
     nh = C.c_int64(0)

@@ -704,6 +704,30 @@ int cfrk_count_sparse_device(const void* d_bases, int fmt, const int64_t* d_star
     return CFRK_OK;
 }
 
+int cfrk_count_sparse_packed_device(const uint32_t* d_codes, const uint16_t* d_valid, const int64_t* d_start,
+                                    const int32_t* d_length, int64_t nN, int64_t nS, int k, int key_bytes,
+                                    int64_t* d_row_begin, int32_t* d_row_count, void* d_keys, uint32_t* d_counts,
+                                    int64_t capacity, int64_t* total_windows, void* stream)
+{
+    int rc = check_common(CFRK_FMT_CODES, k, CFRK_SPARSE_MAX_K, CFRK_MODE_EXACT);
+    if (rc) return rc;
+    if (key_bytes != 4 && key_bytes != 8) return fail(CFRK_EINVAL, "key_bytes must be 4 or 8");
+    if (key_bytes == 4 && k > 16) return fail(CFRK_EINVAL, "uint32 keys hold k <= 16");
+    if (nS < 0 || nN < 0 || capacity < 0) return fail(CFRK_EINVAL, "negative size");
+    if (!d_row_begin) return fail(CFRK_EINVAL, "null device pointer");
+    if (total_windows) *total_windows = 0;
+    if (nS == 0) return CFRK_OK;
+    if (!d_codes || !d_valid || !d_start || !d_length || !d_row_count || !d_keys || !d_counts)
+        return fail(CFRK_EINVAL, "null device pointer");
+    int64_t total = -1;
+    cudaError_t e = cfrk::launch_sparse(d_codes, cfrk::FMT_PACKED, d_start, d_length, nS, k, d_row_begin, d_row_count, d_keys,
+                                        key_bytes, d_counts, capacity, &total, static_cast<cudaStream_t>(stream), d_valid);
+    if (total_windows) *total_windows = total < 0 ? 0 : total;
+    if (total > capacity) { cudaGetLastError(); return fail(CFRK_EINVAL, "capacity smaller than the number of windows"); }
+    if (e != cudaSuccess) return fail_cuda(e, "sparse path (packed reads)");
+    return CFRK_OK;
+}
+
 int cfrk_scan_fasta_device(const void* d_bytes, int64_t n, int is_final, int64_t* d_header, int64_t* d_start,
                            int32_t* d_length, int64_t capacity, int64_t* n_headers, void* stream)
 {

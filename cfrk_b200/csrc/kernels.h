@@ -32,7 +32,8 @@ cudaError_t launch_encode_2bit(const void* bases, int fmt, int64_t n, uint32_t* 
 // `st` internally (needs the total window count on the host).  cudaErrorInvalidValue = capacity.
 cudaError_t launch_sparse(const void* bases, int fmt, const int64_t* start, const int32_t* length, int64_t nS, int k,
                           int64_t* row_begin, int32_t* row_count, void* keys, int key_bytes, uint32_t* counts,
-                          int64_t capacity, int64_t* total_windows, cudaStream_t st);
+                          int64_t capacity, int64_t* total_windows, cudaStream_t st,
+                          const uint16_t* packed_valid = nullptr);   // fmt 2 (packed): bases = uint32 codes
 
 // FASTA record table of a span of raw file bytes (16-byte aligned, padded): header positions,
 // and (start, length) of every record whose end is known (all when final_span, else all but the

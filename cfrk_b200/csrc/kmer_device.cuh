@@ -100,6 +100,14 @@ __device__ __forceinline__ void encode16(const uint4 v, uint32_t& codes, uint32_
     valid = (m0 << 12) | (m1 << 8) | (m2 << 4) | m3;
 }
 
+// what load_block() returned -> codes + validity, whatever the layout
+template <int FMT>
+__device__ __forceinline__ void decode_block(const uint4 raw, uint32_t& codes, uint32_t& valid)
+{
+    if (FMT == FMT_PACKED) { codes = raw.x; valid = raw.y; }
+    else encode16<FMT == FMT_PACKED ? FMT_CODES : FMT>(raw, codes, valid);
+}
+
 // mask with the bits of positions [p, 16) set (position j <-> bit 15-j); p in [0, 16]
 __device__ __forceinline__ uint32_t from_pos(int p) { return (0x10000u >> p) - 1u; }
 

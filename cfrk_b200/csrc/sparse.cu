@@ -379,7 +379,7 @@ template <int E> struct SparseCta { static constexpr int WARPS = E == 16 ? 4 : k
 
 template <typename KeyT, int FMT, int E>
 __global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) sparse_short_kernel(
-    const uint8_t* __restrict__ bases, const int64_t* __restrict__ start, const int32_t* __restrict__ length,
+    const BasesRef src, const int64_t* __restrict__ start, const int32_t* __restrict__ length,
     int64_t nS, int k, const int64_t* __restrict__ row_begin, int32_t* __restrict__ row_count,
     KeyT* __restrict__ keys, uint32_t* __restrict__ counts, bool group_split, int min_windows)
 {
@@ -403,7 +403,7 @@ __global__ void __launch_bounds__(SparseCta<E>::WARPS * 32) sparse_short_kernel(
         for (int b = lane; b < kStreamBlocks; b += 32) {
             uint32_t c = 0, v = 0;
             if (b < nblocks) {
-                encode16<FMT>(ld_block(bases + ((s >> 4) + b) * 16), c, v);
+                decode_block<FMT>(load_block<FMT>(src, (s >> 4) + b), c, v);
                 v &= from_pos(max(0, a - 16 * b)) & ~from_pos(min(16, max(0, a + len - 16 * b)));
             }
             st.cw[b] = c;
@@ -564,7 +564,7 @@ __device__ __forceinline__ int half_rle_store(const KeyT (&key)[E], int nvalid, 
 
 template <typename KeyT, int FMT>
 __global__ void __launch_bounds__(kSparseWarps * 32) sparse_half_kernel(
-    const uint8_t* __restrict__ bases, const uint16_t* __restrict__ packed_valid, const int64_t* __restrict__ start,
+    const BasesRef src, const int64_t* __restrict__ start,
     const int32_t* __restrict__ length, int64_t nS, int k, const int64_t* __restrict__ row_begin,
     int32_t* __restrict__ row_count, KeyT* __restrict__ keys, uint32_t* __restrict__ counts)
 {
@@ -576,7 +576,6 @@ __global__ void __launch_bounds__(kSparseWarps * 32) sparse_half_kernel(
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int h = lane >> 4, hl = lane & 15;
     WarpStream st{s_cw[warp][h], s_vh[warp][h]};
-    const BasesRef src{bases, packed_valid};
     const int64_t nwarps = (int64_t)gridDim.x * WARPS;
     const int64_t npairs = (nS + 1) >> 1;
     for (int64_t pair = (int64_t)blockIdx.x * WARPS + warp; pair < npairs; pair += nwarps) {
@@ -595,8 +594,7 @@ __global__ void __launch_bounds__(kSparseWarps * 32) sparse_half_kernel(
             uint32_t c = 0, v = 0;
             if (hl < nblocks) {
                 const uint4 raw = load_block<FMT>(src, (s >> 4) + hl);
-                if (FMT == FMT_PACKED) { c = raw.x; v = raw.y; }
-                else encode16<FMT == FMT_PACKED ? FMT_CODES : FMT>(raw, c, v);
+                decode_block<FMT>(raw, c, v);
                 v &= from_pos(max(0, a - 16 * hl)) & ~from_pos(min(16, max(0, a + len - 16 * hl)));
             }
             st.cw[hl] = c;
@@ -706,7 +704,7 @@ __global__ void collect_long_kernel(const int32_t* __restrict__ length, int64_t 
 
 template <typename KeyT, int FMT>
 __global__ void __launch_bounds__(kMedThreads, sizeof(KeyT) == 8 ? 3 : 4) sparse_medium_kernel(
-    const uint8_t* __restrict__ bases, const int64_t* __restrict__ start, const int32_t* __restrict__ length, int k,
+    const BasesRef src, const int64_t* __restrict__ start, const int32_t* __restrict__ length, int k,
     const int64_t* __restrict__ medium_rows, int64_t n_medium, const int64_t* __restrict__ row_begin,
     int32_t* __restrict__ row_count, KeyT* __restrict__ keys, uint32_t* __restrict__ counts, bool split,
     int64_t* __restrict__ long_rows, unsigned long long* __restrict__ n_long, int64_t cap)
@@ -735,7 +733,7 @@ __global__ void __launch_bounds__(kMedThreads, sizeof(KeyT) == 8 ? 3 : 4) sparse
         for (int b = threadIdx.x; b < kMedBlocks; b += T) {
             uint32_t c = 0, v = 0;
             if (b < nblocks) {
-                encode16<FMT>(ld_block(bases + ((s >> 4) + b) * 16), c, v);
+                decode_block<FMT>(load_block<FMT>(src, (s >> 4) + b), c, v);
                 v &= from_pos(max(0, a - 16 * b)) & ~from_pos(min(16, max(0, a + len - 16 * b)));
             }
             st.cw[b] = c;
@@ -873,7 +871,7 @@ __device__ __forceinline__ int64_t locate(const int64_t* __restrict__ scan, int6
 //                    (afterwards bucket[b] = end of bucket b in the scratch).
 template <typename KeyT, typename SortT, int FMT, bool SCATTER, int T, int ILP = 1>
 __global__ void __launch_bounds__(T, SCATTER ? (ILP > 1 ? 4 : 5) : 1) partition_kernel(
-    const uint8_t* __restrict__ bases, const int64_t* __restrict__ start, const int32_t* __restrict__ length, int k,
+    const BasesRef src, const int64_t* __restrict__ start, const int32_t* __restrict__ length, int k,
     const int64_t* __restrict__ long_rows, const int64_t* __restrict__ boff, const int64_t* __restrict__ ptile,
     const int64_t* __restrict__ uoff, int64_t j0, int64_t j1, unsigned long long* __restrict__ bucket,
     SortT* __restrict__ scratch)
@@ -914,7 +912,7 @@ __global__ void __launch_bounds__(T, SCATTER ? (ILP > 1 ? 4 : 5) : 1) partition_
 #pragma unroll
         for (int q = 0; q < NB; q++) {
             const int64_t b = blk0 + threadIdx.x + q * T;
-            raw[q] = threadIdx.x + q * T < kPartBlocks && b < blk_end ? ld_block(bases + b * 16) : make_uint4(0, 0, 0, 0);
+            raw[q] = threadIdx.x + q * T < kPartBlocks && b < blk_end ? load_block<FMT>(src, b) : make_uint4(0, 0, 0, 0);
         }
         for (int64_t w0 = wbeg; w0 < wend; w0 += STEP) {
             const int64_t rs = s - blk0 * 16, re = s + len - blk0 * 16;   // the read in stream coordinates
@@ -924,7 +922,7 @@ __global__ void __launch_bounds__(T, SCATTER ? (ILP > 1 ? 4 : 5) : 1) partition_
                 const int b = threadIdx.x + q * T;
                 if (b < kPartBlocks) {
                     uint32_t cc, v;
-                    encode16<FMT>(raw[q], cc, v);
+                    decode_block<FMT>(raw[q], cc, v);
                     const int lo = (int)max((int64_t)0, min((int64_t)16, rs - 16 * b));
                     const int hi = (int)max((int64_t)0, min((int64_t)16, re - 16 * b));
                     v &= from_pos(lo) & ~from_pos(hi);
@@ -938,7 +936,7 @@ __global__ void __launch_bounds__(T, SCATTER ? (ILP > 1 ? 4 : 5) : 1) partition_
 #pragma unroll
                 for (int q = 0; q < NB; q++) {
                     const int64_t b = blk0 + threadIdx.x + q * T;
-                    raw[q] = threadIdx.x + q * T < kPartBlocks && b < blk_end ? ld_block(bases + b * 16) : make_uint4(0, 0, 0, 0);
+                    raw[q] = threadIdx.x + q * T < kPartBlocks && b < blk_end ? load_block<FMT>(src, b) : make_uint4(0, 0, 0, 0);
                 }
             }
             KeyT key[W];
@@ -1283,7 +1281,7 @@ static cudaError_t scan_in_place(T* data, int64_t n, void* tmp, size_t tmp_bytes
 #define CFRK_TRY(x) do { if ((e = (x)) != cudaSuccess) return e; } while (0)
 
 template <typename KeyT, typename SortT, int FMT>
-static cudaError_t sparse_long_rows(const uint8_t* bases, const int64_t* start, const int32_t* length, int k,
+static cudaError_t sparse_long_rows(const BasesRef bases, const int64_t* start, const int32_t* length, int k,
                                     const int64_t* row_begin, int32_t* row_count, KeyT* keys, uint32_t* counts,
                                     const int64_t* long_rows, int64_t nl, int num_sms, SparseTrace& tr, cudaStream_t st)
 {
@@ -1457,7 +1455,7 @@ static cudaError_t sparse_long_rows(const uint8_t* bases, const int64_t* start, 
 
 // ------------------------------------------------------------------------------------------
 template <typename KeyT, int FMT>
-static cudaError_t sparse_impl(const void* bases, const int64_t* start, const int32_t* length, int64_t nS, int k,
+static cudaError_t sparse_impl(const BasesRef bases, const int64_t* start, const int32_t* length, int64_t nS, int k,
                                int64_t* row_begin, int32_t* row_count, KeyT* keys, uint32_t* counts,
                                int64_t capacity, int64_t* total_windows, cudaStream_t st)
 {
@@ -1497,7 +1495,7 @@ static cudaError_t sparse_impl(const void* bases, const int64_t* start, const in
         const unsigned grid = (unsigned)(ctas < (int64_t)num_sms * 8 ? ctas : (int64_t)num_sms * 8);
         // which classes occur is not known on the host without a pass over the lengths: launch all
         // three; a class without reads costs one pass over length[] (4 B/read)
-        const uint8_t* b8 = static_cast<const uint8_t*>(bases);
+        const BasesRef b8 = bases;
         const char* gev = getenv("CFRK_SPARSE_GROUPS");          // 0: always the full network (A/B measurements)
         const bool group_split = !(gev && atoi(gev) == 0);
         const char* hev = getenv("CFRK_SPARSE_HALF");            // 0: round-1 classes (one warp per read for every length)
@@ -1507,7 +1505,7 @@ static cudaError_t sparse_impl(const void* bases, const int64_t* start, const in
             // without a window); 145..256 and 257..512: one warp each, launched only if such reads exist
             const int64_t hctas = ((nS + 1) / 2 + kSparseWarps - 1) / kSparseWarps;
             const unsigned hgrid = (unsigned)(hctas < (int64_t)num_sms * 8 ? hctas : (int64_t)num_sms * 8);
-            sparse_half_kernel<KeyT, FMT><<<hgrid, kSparseWarps * 32, 0, st>>>(b8, nullptr, start, length, nS, k, row_begin, row_count, keys, counts);
+            sparse_half_kernel<KeyT, FMT><<<hgrid, kSparseWarps * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts);
             count_launch();
             if (cls[1]) {
                 sparse_short_kernel<KeyT, FMT, 8><<<grid, SparseCta<8>::WARPS * 32, 0, st>>>(b8, start, length, nS, k, row_begin, row_count, keys, counts, group_split, kHalfSlots + 1);
@@ -1545,7 +1543,7 @@ static cudaError_t sparse_impl(const void* bases, const int64_t* start, const in
     unsigned long long n_rows[3] = {0, 0, 0};
     cudaMemcpyAsync(n_rows, d_n, 24, cudaMemcpyDeviceToHost, st);
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
-    const uint8_t* b8 = static_cast<const uint8_t*>(bases);
+    const BasesRef b8 = bases;
     if (n_rows[2] > 0) {
         const size_t dyn = (size_t)(kMedMaxWindows + (kMedThreads / 32) * 256) * (sizeof(KeyT) + 4);
         auto kern = sparse_medium_kernel<KeyT, FMT>;
@@ -1567,20 +1565,29 @@ static cudaError_t sparse_impl(const void* bases, const int64_t* start, const in
     return e != cudaSuccess ? e : cudaGetLastError();
 }
 
+template <typename KeyT>
+static cudaError_t sparse_fmt(const BasesRef src, int fmt, const int64_t* start, const int32_t* length, int64_t nS, int k,
+                              int64_t* row_begin, int32_t* row_count, KeyT* keys, uint32_t* counts, int64_t capacity,
+                              int64_t* total_windows, cudaStream_t st)
+{
+    if (fmt == FMT_PACKED)
+        return sparse_impl<KeyT, FMT_PACKED>(src, start, length, nS, k, row_begin, row_count, keys, counts, capacity, total_windows, st);
+    return fmt == FMT_ASCII
+               ? sparse_impl<KeyT, FMT_ASCII>(src, start, length, nS, k, row_begin, row_count, keys, counts, capacity, total_windows, st)
+               : sparse_impl<KeyT, FMT_CODES>(src, start, length, nS, k, row_begin, row_count, keys, counts, capacity, total_windows, st);
+}
+
+// fmt 2 (packed): bases = the uint32 codes, packed_valid = the uint16 validity masks of cfrk_encode_2bit_device
 cudaError_t launch_sparse(const void* bases, int fmt, const int64_t* start, const int32_t* length, int64_t nS, int k,
                           int64_t* row_begin, int32_t* row_count, void* keys, int key_bytes, uint32_t* counts,
-                          int64_t capacity, int64_t* total_windows, cudaStream_t st)
+                          int64_t capacity, int64_t* total_windows, cudaStream_t st, const uint16_t* packed_valid)
 {
-    if (key_bytes == 4) {
-        auto* kk = static_cast<uint32_t*>(keys);
-        return fmt == FMT_ASCII
-                   ? sparse_impl<uint32_t, FMT_ASCII>(bases, start, length, nS, k, row_begin, row_count, kk, counts, capacity, total_windows, st)
-                   : sparse_impl<uint32_t, FMT_CODES>(bases, start, length, nS, k, row_begin, row_count, kk, counts, capacity, total_windows, st);
-    }
-    auto* kk = static_cast<uint64_t*>(keys);
-    return fmt == FMT_ASCII
-               ? sparse_impl<uint64_t, FMT_ASCII>(bases, start, length, nS, k, row_begin, row_count, kk, counts, capacity, total_windows, st)
-               : sparse_impl<uint64_t, FMT_CODES>(bases, start, length, nS, k, row_begin, row_count, kk, counts, capacity, total_windows, st);
+    const BasesRef src{static_cast<const uint8_t*>(bases), packed_valid};
+    if (key_bytes == 4)
+        return sparse_fmt<uint32_t>(src, fmt, start, length, nS, k, row_begin, row_count, static_cast<uint32_t*>(keys), counts, capacity,
+                                    total_windows, st);
+    return sparse_fmt<uint64_t>(src, fmt, start, length, nS, k, row_begin, row_count, static_cast<uint64_t*>(keys), counts, capacity,
+                                total_windows, st);
 }
 
 }  // namespace cfrk

@@ -177,6 +177,13 @@ int cfrk_count_sparse_device(const void *d_bases, int fmt, const int64_t *d_star
                              uint32_t *d_counts, int64_t capacity, int64_t *total_windows,
                              void *stream);
 
+/* The same on PACKED reads (the output of cfrk_encode_2bit_device: encode once, count for any number of k). */
+int cfrk_count_sparse_packed_device(const uint32_t *d_codes, const uint16_t *d_valid, const int64_t *d_start,
+                                    const int32_t *d_length, int64_t nN, int64_t nS, int k, int key_bytes,
+                                    int64_t *d_row_begin, int32_t *d_row_count, void *d_keys,
+                                    uint32_t *d_counts, int64_t capacity, int64_t *total_windows,
+                                    void *stream);
+
 /*
  * FASTA record table on the GPU (replaces popen("grep -c") + the getline loop of
  * src/fastaIO.h:12-69 for bytes that are already in HBM).  d_bytes: n raw file bytes, 16-byte

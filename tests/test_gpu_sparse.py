@@ -233,3 +233,44 @@ def test_scale_properties(nS, L, k, key_bytes):
         assert n == orp[1]
         np.testing.assert_array_equal(K[r, :n].cpu().numpy().view(np.uint32 if key_bytes == 4 else np.uint64).astype(np.uint64), okeys)
         np.testing.assert_array_equal(Cn[r, :n].cpu().numpy().view(np.uint32), ocnt)
+
+
+@pytest.mark.parametrize("k,key_bytes", [(12, 4), (21, 8), (31, 8)])
+def test_packed_reads_input(k, key_bytes):
+    """cfrk_count_sparse_packed_device: every size class (two reads per warp, one warp, one CTA, bucket path) reads the
+    packed 2-bit words + validity masks of cfrk_encode_2bit_device instead of bytes; same rows as the oracle"""
+    import random
+    rng = random.Random(900 + k)
+    reads = []
+    for L in [150] * 300 + [k - 1, k, 100, 144 + k - 1, 145 + k - 1, 200, 300, 500, 512 + k, 700, 2000, 4000, 4500, 30000, 70000]:
+        s_ = [rng.choice("ACGT") for _ in range(L)]
+        if L > 20 and rng.random() < 0.5:
+            s_[rng.randrange(L)] = "N"
+        reads.append("".join(s_))
+    rng.shuffle(reads)
+    text = "".join(f">r{i}\n{r}\n" for i, r in enumerate(reads))
+    data, start, length = ob.parse_fasta(text=text)
+    nS, nN = len(start), len(data)
+    b = torch.from_numpy(np.concatenate([data.view(np.uint8), np.full(16, 255, np.uint8)])).cuda()
+    nb = (nN + 15) // 16 + 8
+    codes = torch.zeros(nb, dtype=torch.int32, device="cuda")
+    valid = torch.zeros(nb, dtype=torch.int16, device="cuda")
+    cf.encode_2bit_device(b.data_ptr(), nN, codes.data_ptr(), valid.data_ptr(), fmt=cf.FMT_CODES)
+    d_s, d_l = torch.from_numpy(start).cuda(), torch.from_numpy(length).cuda()
+    cap = int(np.maximum(length.astype(np.int64) - k + 1, 0).sum()) + 1
+    rb = torch.zeros(nS + 1, dtype=torch.int64, device="cuda")
+    rc = torch.zeros(nS, dtype=torch.int32, device="cuda")
+    keys = torch.zeros(cap, dtype=torch.int32 if key_bytes == 4 else torch.int64, device="cuda")
+    cnt = torch.zeros(cap, dtype=torch.int32, device="cuda")
+    cf.count_sparse_packed_device(codes.data_ptr(), valid.data_ptr(), d_s.data_ptr(), d_l.data_ptr(), nN, nS, k, rb.data_ptr(),
+                                  rc.data_ptr(), keys.data_ptr(), cnt.data_ptr(), cap, key_bytes=key_bytes)
+    torch.cuda.synchronize()
+    orp, okeys, ocnt = ob.count_sparse(data, start, length, k)
+    hrb, hrc = rb.cpu().numpy(), rc.cpu().numpy()
+    hk = keys.cpu().numpy().view(np.uint32 if key_bytes == 4 else np.uint64).astype(np.uint64)
+    hc = cnt.cpu().numpy().view(np.uint32)
+    for i in range(nS):
+        a, n = int(hrb[i]), int(hrc[i])
+        assert n == orp[i + 1] - orp[i], f"row {i} len {length[i]}"
+        np.testing.assert_array_equal(hk[a:a + n], okeys[orp[i]:orp[i + 1]], err_msg=f"row {i}")
+        np.testing.assert_array_equal(hc[a:a + n], ocnt[orp[i]:orp[i + 1]], err_msg=f"row {i}")
