@@ -250,13 +250,14 @@ public:
         free_.push_back((int)(s - slots_.data()));
         cv_.notify_all();
     }
-    void stop()
+    void stop()     // may be called by several failing workers and by the owner: only one joins
     {
         {
             std::lock_guard<std::mutex> lk(mu_);
             stop_ = true;
             cv_.notify_all();
         }
+        std::lock_guard<std::mutex> jk(join_mu_);
         if (th_.joinable()) th_.join();
     }
     const Err& error() const { return err_; }
@@ -358,7 +359,7 @@ private:
     std::vector<int> free_;
     std::deque<Span*> ready_;
     std::thread th_;
-    std::mutex mu_;
+    std::mutex mu_, join_mu_;
     std::condition_variable cv_;
     bool stop_ = false, done_ = false;
     Err err_;

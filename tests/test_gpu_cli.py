@@ -378,3 +378,15 @@ def test_fastq_input(tmp_path, window):
     bad.write_text("@r1\nACGT\nACGT\nIIII\n")
     r = subprocess.run([CFRK, str(bad), str(b), "2"], capture_output=True, timeout=120)
     assert r.returncode == 1 and b"FASTQ" in r.stderr
+
+
+def test_error_in_a_later_span_stops_the_run(tmp_path):
+    """a '>' inside a sequence line (undefined in the reference, src/fastaIO.h:16) far into the file: the worker that
+    scans that span fails, the other workers and the reader stop, the command exits 1 with the message -- no hang"""
+    text = fx.fx_basic(n=400) + ">bad\nACGT>ACGT\n" + fx.fx_basic(n=400, seed=3)
+    fa = tmp_path / "in.fa"
+    fa.write_text(text)
+    e = dict(os.environ, CFRK_WINDOW_BYTES="8192")
+    for extra in (["--all-rows"], []):
+        r = subprocess.run([CFRK, str(fa), str(tmp_path / "o"), "3", "4", "50", *extra], capture_output=True, timeout=120, env=e)
+        assert r.returncode == 1 and b"inside a sequence line" in r.stderr, r.stderr
