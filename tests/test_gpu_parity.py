@@ -152,3 +152,30 @@ def test_host_operator_split_between_dma_and_host_threads(k, nS, mode):
         np.testing.assert_array_equal(got, want)
     finally:
         cf.lib().cfrk_set_host_threads(-1)
+
+
+def test_release_and_reuse():
+    """cfrk_release() frees the calling thread's context, the launch scratch and the cached pinned buffers; the next
+    call builds them again (no unbounded growth, an explicit release); contexts of exited threads are
+    taken over by new threads"""
+    import threading
+    data, start, length = fx.synthetic_codes(5000, 150, seed=9, n_frac=0.002)
+    want = ob.count_dense_fast(data, start, length, 6, ob.MODE_COMPAT)
+    L = cf.lib()
+    for _ in range(3):
+        np.testing.assert_array_equal(cf.kmer_main(data, start, length, 6), want)
+        assert L.cfrk_release() == 0
+    errs = []
+
+    def work():
+        try:
+            if not np.array_equal(cf.kmer_main(data, start, length, 6), want):
+                errs.append("mismatch")
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+    for _ in range(6):          # thread churn: each new thread adopts the context the previous one left behind
+        t = threading.Thread(target=work)
+        t.start(); t.join()
+    assert not errs, errs
+    assert L.cfrk_release() == 0
+    np.testing.assert_array_equal(cf.kmer_main(data, start, length, 6), want)
