@@ -273,3 +273,43 @@ def test_no_write_outside_the_rows(k, mode):
     torch.cuda.synchronize()
     assert bool((buf[: guard * bins] == 0x5A5A5A5A).all()) and bool((buf[(guard + nS) * bins:] == 0x5A5A5A5A).all())
     np.testing.assert_array_equal(out.view(nS, bins).cpu().numpy(), ob.count_dense_fast(data, start, length, k, mode))
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("k", [2, 4, 6])
+def test_read_range_shards_on_two_gpus(k):
+    """SURVEY 8e with the kernels (the gloo test does it with the oracle): the batch is resident on both GPUs, GPU g
+    counts its read range [b_g, b_g+1) of the FULL batch (so the compat halo -- the first read of the next shard --
+    is there), the rows gathered in order equal the one-GPU rows and the oracle's; the per-GPU histograms add up"""
+    import threading
+    from cfrk_b200.sharding import shard_bounds
+    data, start, length = ob.parse_fasta(text=fx.fx_with_n() + fx.fx_ragged() + fx.fx_basic(n=300) + fx.fx_long())
+    nS, nN = len(start), len(data)
+    want = ob.count_dense_fast(data, start, length, k, ob.MODE_COMPAT)
+    b = shard_bounds(length, 2, align=cf.dense_reads_per_tile(k))
+    rows, hists, errs = [None, None], [None, None], []
+
+    def work(g):
+        try:
+            with torch.cuda.device(g):
+                dev_ = torch.device("cuda", g)
+                bases = torch.full((nN + 16,), 0xFF, dtype=torch.uint8, device=dev_)
+                bases[:nN] = torch.from_numpy(data.view(np.uint8).copy()).to(dev_)
+                d_s, d_l = torch.from_numpy(start).to(dev_), torch.from_numpy(length).to(dev_)
+                r0, r1 = b[g], b[g + 1]
+                out = torch.empty(((r1 - r0), 4 ** k), dtype=torch.int32, device=dev_)
+                cf.count_dense_device(bases.data_ptr(), d_s.data_ptr(), d_l.data_ptr(), nN, nS, k, out.data_ptr(),
+                                      read_begin=r0, read_end=r1, stream=torch.cuda.current_stream().cuda_stream)
+                h = torch.zeros(4 ** k, dtype=torch.int32, device=dev_)
+                cf.global_hist_device(bases.data_ptr(), d_s[r0:r1].data_ptr(), d_l[r0:r1].data_ptr(), nN, r1 - r0, k, h.data_ptr(),
+                                      stream=torch.cuda.current_stream().cuda_stream)
+                torch.cuda.synchronize()
+                rows[g], hists[g] = out.cpu().numpy(), h.cpu().numpy().astype(np.int64)
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+    th = [threading.Thread(target=work, args=(g,)) for g in range(2)]
+    [t.start() for t in th]
+    [t.join() for t in th]
+    assert not errs, errs
+    np.testing.assert_array_equal(np.concatenate(rows), want)
+    np.testing.assert_array_equal(hists[0] + hists[1], ob.global_hist(data, start, length, k).astype(np.int64))
