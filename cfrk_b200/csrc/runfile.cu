@@ -50,7 +50,9 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/statvfs.h>
 #include <thread>
 #include <unistd.h>
 #include <vector>
@@ -433,17 +435,23 @@ private:
 
 // ------------------------------------------------------------------------------------------
 // .cfrk text writer
-// "bin:" labels as fixed 8-byte records (bins < 65536 -> at most "65535:"): one 64-bit store per token
+// "bin:" labels as fixed 8-byte records (bins < 65536 -> at most "65535:"): one 64-bit store per token;
+// and the text of a row whose counts are all one digit ("0:0 1:0 2:0 ... "), with the place of every digit
 struct BinLabels {
     std::vector<uint64_t> rec;
     std::vector<uint8_t> len;
-    explicit BinLabels(size_t bins) : rec(bins), len(bins)
+    std::string tmpl;
+    std::vector<uint32_t> pos;
+    explicit BinLabels(size_t bins) : rec(bins), len(bins), pos(bins)
     {
         char tmp[16];
         for (size_t b = 0; b < bins; b++) {
             memset(tmp, 0, sizeof tmp);
             len[b] = (uint8_t)snprintf(tmp, sizeof tmp, "%zu:", b);
             memcpy(&rec[b], tmp, 8);
+            tmpl.append(tmp, len[b]);
+            pos[b] = (uint32_t)tmpl.size();
+            tmpl.append("0 ");
         }
     }
 };
@@ -481,36 +489,91 @@ inline char* put_int(char* p, int32_t v)
     while (l) *p++ = tmp[--l];
     return p;
 }
-
-bool format_rows(const int32_t* rows, size_t nrows, size_t bins, const BinLabels& lab, bool sparse,
-                 bool first_row_of_file, RawBuf& out)
+inline int ndigits(uint64_t u)
 {
-    // worst case per token: 8-byte label store + 11 digits + space
-    if (!out.reserve(nrows * (bins * 20 + 1) + 16)) return false;
-    char* p = out.data;
-    for (size_t r = 0; r < nrows; r++) {
-        if (!(first_row_of_file && r == 0)) *p++ = '\n';
-        const int32_t* row = rows + r * bins;
-        for (size_t b = 0; b < bins; b++) {
-            const int32_t v = row[b];
-            if (sparse && v == 0) continue;
-            memcpy(p, &lab.rec[b], 8);
-            p += lab.len[b];
-            p = put_int(p, v);
-            *p++ = ' ';
+    int n = 1;
+    while (u >= 10) { u /= 10; n++; }
+    return n;
+}
+
+// One row -> text at p.  EXACT = false may store up to 6 bytes past the end of the row's text (the 8-byte label
+// records); EXACT = true never does (rows at the end of a thread's piece of the mapped file).
+template <bool EXACT>
+inline char* put_token(char* p, const BinLabels& lab, size_t b, int32_t v)
+{
+    if (EXACT) memcpy(p, &lab.rec[b], lab.len[b]); else memcpy(p, &lab.rec[b], 8);
+    p = put_int(p + lab.len[b], v);
+    *p++ = ' ';
+    return p;
+}
+char* format_row(const int32_t* row, size_t bins, const BinLabels& lab, bool sparse, bool exact, char* p)
+{
+    if (!sparse) {
+        // every count in 0..9 (the usual row): the row's text is the template with the digits patched in
+        uint32_t over = 0;
+        for (size_t b = 0; b < bins; b++) over |= (uint32_t)row[b] | (uint32_t)(9 - row[b]);
+        if (!(over >> 31)) {
+            memcpy(p, lab.tmpl.data(), lab.tmpl.size());
+            const uint32_t* pos = lab.pos.data();
+            for (size_t b = 0; b < bins; b++) p[pos[b]] = (char)('0' + row[b]);
+            return p + lab.tmpl.size();
         }
+        if (exact) for (size_t b = 0; b < bins; b++) p = put_token<true>(p, lab, b, row[b]);
+        else for (size_t b = 0; b < bins; b++) p = put_token<false>(p, lab, b, row[b]);
+        return p;
     }
-    out.size = (size_t)(p - out.data);
-    return true;
+    // non-zero bins: index list without a data-dependent branch (43 % of the bins of a 150-bp read at k = 4 are
+    // zero: the branchy loop mispredicts on every other bin), then the tokens
+    static thread_local std::vector<uint16_t> idx_buf;
+    if (idx_buf.size() < bins + 1) idx_buf.resize(bins + 1);
+    uint16_t* idx = idx_buf.data();
+    size_t m = 0;
+    for (size_t b = 0; b < bins; b++) { idx[m] = (uint16_t)b; m += row[b] != 0; }
+    if (exact) for (size_t i = 0; i < m; i++) p = put_token<true>(p, lab, idx[i], row[idx[i]]);
+    else for (size_t i = 0; i < m; i++) p = put_token<false>(p, lab, idx[i], row[idx[i]]);
+    return p;
+}
+// bytes of format_row()'s text (the host twin of row_text_bytes_kernel)
+int32_t row_text_bytes(const int32_t* row, size_t bins, const BinLabels& lab, bool sparse)
+{
+    int64_t n = 0;
+    for (size_t b = 0; b < bins; b++) {
+        const int32_t v = row[b];
+        if (sparse && v == 0) continue;
+        n += lab.len[b] + 1 + (v < 0 ? 1 + ndigits((uint64_t)(-(int64_t)v)) : ndigits((uint64_t)v));
+    }
+    return (int32_t)n;
+}
+template <typename KeyT>
+inline char* format_pairs(const KeyT* kk, const uint32_t* cc, int32_t n, char* p)
+{
+    for (int32_t i = 0; i < n; i++) {
+        char tmp[24];
+        int l = 0;
+        uint64_t u = (uint64_t)kk[i];
+        do { tmp[l++] = (char)('0' + u % 10); u /= 10; } while (u);
+        while (l) *p++ = tmp[--l];
+        *p++ = ':';
+        p = put_int(p, (int32_t)cc[i]);
+        *p++ = ' ';
+    }
+    return p;
 }
 
 class CfrkWriter {
 public:
     bool open(const char* path, int k, int nt, bool sparse, Err& err)
     {
-        fd_ = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);   // fopen(path, "w"), src/main.cu:34
+        // fopen(path, "w"), src/main.cu:34.  Read-write so that the file can be mapped; a target that cannot be
+        // opened that way (a write-only pipe) is written sequentially.
+        fd_ = ::open(path, O_RDWR | O_CREAT | O_TRUNC, 0644);
+        const bool rdwr = fd_ >= 0;
+        if (fd_ < 0) fd_ = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
         if (fd_ < 0) { err.code = CFRK_EIO; err.msg = std::string("cannot open output ") + path; return false; }
+        struct stat st;
         seekable_ = lseek(fd_, 0, SEEK_CUR) != (off_t)-1;
+        const char* ev = getenv("CFRK_WRITER");          // "pwrite": private buffers + pwrite (round 1) for A/B runs
+        mapped_ = rdwr && seekable_ && fstat(fd_, &st) == 0 && S_ISREG(st.st_mode) && !(ev && strcmp(ev, "pwrite") == 0);
         bins_ = k <= CFRK_CLI_DENSE_MAX_K ? (size_t)1 << (2 * k) : 0;
         if (bins_) labels_.reset(new BinLabels(bins_));
         nt_ = std::max(1, std::min(nt, 64));
@@ -519,15 +582,33 @@ public:
         sparse_ = sparse;
         return true;
     }
-    bool write_rows(const int32_t* rows, size_t nrows, Err& err)
+    bool sized() const { return mapped_; }   // text sizes of the rows wanted (they are computed on the GPU)
+    size_t bins() const { return bins_; }
+    const BinLabels& labels() const { return *labels_; }
+    ThreadPool& pool() { return *pool_; }
+    int threads() const { return nt_; }
+
+    // text_bytes[r] = bytes of row r's tokens (row_text_bytes_kernel), or null
+    bool write_rows(const int32_t* rows, size_t nrows, const int32_t* text_bytes, Err& err)
     {
         if (!nrows) return true;
+        if (mapped_ && text_bytes)
+            return write_mapped(nrows, text_bytes, [&](size_t r, char* p, bool exact) {
+                return format_row(rows + r * bins_, bins_, *labels_, sparse_, exact, p); }, err);
         const int nt = (int)std::min<size_t>((size_t)nt_, nrows);
         std::vector<char> good(nt, 1);
         const bool first_file = first_;
         pool_->run(nt, [&](int t) {
             const size_t a = nrows * t / nt, b = nrows * (t + 1) / nt;
-            good[t] = format_rows(rows + a * bins_, b - a, bins_, *labels_, sparse_, first_file && a == 0, parts_[t]);
+            RawBuf& out = parts_[t];
+            // worst case per token: 8-byte label store + 11 digits + space
+            if (!out.reserve((b - a) * (bins_ * 20 + 1) + 16)) { good[t] = 0; return; }
+            char* p = out.data;
+            for (size_t r = a; r < b; r++) {
+                if (!(first_file && r == 0)) *p++ = '\n';
+                p = format_row(rows + r * bins_, bins_, *labels_, sparse_, false, p);
+            }
+            out.size = (size_t)(p - out.data);
         });
         first_ = false;
         for (char g : good) if (!g) { err.code = CFRK_ENOMEM; err.msg = "out of memory for the text of a row slice"; return false; }
@@ -536,34 +617,25 @@ public:
     // rows given as (key, count) pairs: the same "bin:count " tokens, non-zero bins only
     template <typename KeyT>
     bool write_pairs(const int64_t* row_begin, const int32_t* row_count, const KeyT* keys,
-                     const uint32_t* counts, size_t nrows, Err& err)
+                     const uint32_t* counts, size_t nrows, const int32_t* text_bytes, Err& err)
     {
         if (!nrows) return true;
+        if (mapped_ && text_bytes)
+            return write_mapped(nrows, text_bytes, [&](size_t r, char* p, bool) {
+                return format_pairs<KeyT>(keys + row_begin[r], counts + row_begin[r], row_count[r], p); }, err);
         const int nt = (int)std::min<size_t>((size_t)nt_, nrows);
         std::vector<char> good(nt, 1);
         const bool first_file = first_;
         pool_->run(nt, [&](int t) {
             const size_t a = nrows * t / nt, b = nrows * (t + 1) / nt;
-            const bool first = first_file && a == 0;
             size_t npairs = 0;
             for (size_t r = a; r < b; r++) npairs += (size_t)row_count[r];
             RawBuf& out = parts_[t];
             if (!out.reserve(npairs * 33 + (b - a) + 1)) { good[t] = 0; return; }   // 20 + 1 + 10 + 1 per token, '\n' per row
             char* p = out.data;
             for (size_t r = a; r < b; r++) {
-                if (!(first && r == a)) *p++ = '\n';
-                const KeyT* kk = keys + row_begin[r];
-                const uint32_t* cc = counts + row_begin[r];
-                for (int32_t i = 0; i < row_count[r]; i++) {
-                    char tmp[24];
-                    int l = 0;
-                    uint64_t u = (uint64_t)kk[i];
-                    do { tmp[l++] = (char)('0' + u % 10); u /= 10; } while (u);
-                    while (l) *p++ = tmp[--l];
-                    *p++ = ':';
-                    p = put_int(p, (int32_t)cc[i]);
-                    *p++ = ' ';
-                }
+                if (!(first_file && r == 0)) *p++ = '\n';
+                p = format_pairs<KeyT>(keys + row_begin[r], counts + row_begin[r], row_count[r], p);
             }
             out.size = (size_t)(p - out.data);
         });
@@ -574,6 +646,58 @@ public:
     ~CfrkWriter() { if (fd_ >= 0) ::close(fd_); }
 
 private:
+    // Rows whose text sizes are known: the file grows by exactly that much, the new piece is mapped and the pool
+    // threads format STRAIGHT INTO IT -- no private buffer, no copy, and the page allocation of the new pages runs on
+    // all threads, where pwrite()s into one file take turns on the inode lock (tools/host/pwrite_scaling.c: 2.1-2.6 GB/s
+    // into tmpfs whatever the thread count; the mapping scales with the threads).
+    template <typename RowFn>
+    bool write_mapped(size_t nrows, const int32_t* text_bytes, RowFn&& row_fn, Err& err)
+    {
+        row_off_.resize(nrows + 1);
+        int64_t o = 0;
+        for (size_t r = 0; r < nrows; r++) {
+            row_off_[r] = o;
+            if (text_bytes[r] < 0) { err.code = CFRK_EIO; err.msg = "internal: negative row text size"; return false; }
+            o += (int64_t)text_bytes[r] + ((first_ && r == 0) ? 0 : 1);
+        }
+        row_off_[nrows] = o;
+        const int64_t total = o;
+        const bool first_file = first_;
+        first_ = false;
+        if (total == 0) return true;
+        struct statvfs vfs;
+        if (fstatvfs(fd_, &vfs) == 0 && (uint64_t)vfs.f_bavail * vfs.f_frsize < (uint64_t)total) {
+            err.code = CFRK_EIO; err.msg = "no space left for the output"; return false;   // a mapped write would fault instead
+        }
+        if (ftruncate(fd_, off_ + (off_t)total) != 0) { err.code = CFRK_EIO; err.msg = std::string("cannot grow the output: ") + strerror(errno); return false; }
+        const off_t pg = (off_t)sysconf(_SC_PAGESIZE);
+        const off_t map_at = off_ & ~(pg - 1);
+        const size_t map_len = (size_t)(off_ + (off_t)total - map_at);
+        void* m = mmap(nullptr, map_len, PROT_READ | PROT_WRITE, MAP_SHARED, fd_, map_at);
+        if (m == MAP_FAILED) { err.code = CFRK_EIO; err.msg = std::string("cannot map the output: ") + strerror(errno); return false; }
+        char* base = static_cast<char*>(m) + (off_ - map_at);
+        // pieces of about equal text, cut at rows
+        const int nt = (int)std::min<size_t>((size_t)nt_, nrows);
+        std::vector<size_t> cut(nt + 1);
+        for (int t = 0; t <= nt; t++)
+            cut[t] = t == nt ? nrows : (size_t)(std::lower_bound(row_off_.begin(), row_off_.begin() + nrows, total * t / nt) - row_off_.begin());
+        std::vector<char> good(nt, 1);
+        pool_->run(nt, [&](int t) {
+            const size_t a = cut[t], b = cut[t + 1];
+            if (a >= b) return;
+            char* p = base + row_off_[a];
+            char* const end = base + row_off_[b];
+            for (size_t r = a; r < b; r++) {
+                if (!(first_file && r == 0)) *p++ = '\n';
+                p = row_fn(r, p, end - (p + text_bytes[r]) < 8);
+                if (p != base + row_off_[r + 1]) { good[t] = 0; return; }   // the GPU's size and the formatter disagree: stop
+            }
+        });
+        munmap(m, map_len);
+        off_ += (off_t)total;
+        for (char g : good) if (!g) { err.code = CFRK_EIO; err.msg = "internal: row text size mismatch"; return false; }
+        return true;
+    }
     // formatted parts -> file, in order.  Regular files: every part is written at its own offset
     // by its own pool thread (pwrite); pipes (the Swift stdout form): sequential write.
     bool flush_parts(int nparts, Err& err)
@@ -605,9 +729,10 @@ private:
         return ok;
     }
     std::vector<RawBuf> parts_;
+    std::vector<int64_t> row_off_;
     std::unique_ptr<ThreadPool> pool_;
     int fd_ = -1;
-    bool seekable_ = false;
+    bool seekable_ = false, mapped_ = false;
     off_t off_ = 0;
     size_t bins_ = 0;
     std::unique_ptr<BinLabels> labels_;
@@ -712,9 +837,69 @@ __global__ void row_compact_kernel(const int32_t* __restrict__ rows, int64_t nro
 }
 
 // ------------------------------------------------------------------------------------------
+// Bytes of the text of every row ("bin:count " tokens, format_row / format_pairs on the host), so that the writer
+// knows where every row goes in the file before a byte is formatted.  One warp per row.
+__device__ __forceinline__ int dec_digits(uint64_t v)
+{
+    int n = 1;
+    uint64_t p = 10;
+    while (v >= p && n < 20) { n++; p *= 10; }   // 20 digits: p would overflow, the loop has ended
+    return n;
+}
+__device__ __forceinline__ int dec_digits32(uint32_t v)
+{
+    return 1 + (v >= 10u) + (v >= 100u) + (v >= 1000u) + (v >= 10000u) + (v >= 100000u) + (v >= 1000000u) +
+           (v >= 10000000u) + (v >= 100000000u) + (v >= 1000000000u);
+}
+__global__ void row_text_bytes_kernel(const int32_t* __restrict__ rows, int64_t nrows, int bins, int sparse,
+                                      int32_t* __restrict__ text_bytes)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += warps) {
+        const int32_t* row = rows + r * bins;
+        int c = 0;
+        for (int b = lane; b < bins; b += 32) {
+            const int32_t v = row[b];
+            const int tok = dec_digits32((uint32_t)b) + 2 + (v < 0 ? 1 + dec_digits32((uint32_t)(-(int64_t)v)) : dec_digits32((uint32_t)v));
+            c += (sparse && v == 0) ? 0 : tok;
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        if (lane == 0) text_bytes[r] = c;
+    }
+}
+template <typename KeyT>
+__global__ void pairs_text_bytes_kernel(const int64_t* __restrict__ row_begin, const int32_t* __restrict__ row_count,
+                                        const KeyT* __restrict__ keys, const uint32_t* __restrict__ counts, int64_t nrows,
+                                        int32_t* __restrict__ text_bytes)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); r < nrows; r += warps) {
+        const int64_t at = row_begin[r];
+        const int n = row_count[r];
+        int c = 0;
+        for (int i = lane; i < n; i += 32) c += dec_digits((uint64_t)keys[at + i]) + 2 + dec_digits32(counts[at + i]);
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        if (lane == 0) text_bytes[r] = c;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // GPU side of one worker: device input buffer + row ring.
 struct Pipeline {
     static constexpr size_t kSlotBytes = (size_t)128 << 20;
+    static size_t slot_bytes_limit()      // CFRK_ROW_SLOT_BYTES: size of a row ring slot (measurements)
+    {
+        static const size_t v = [] {
+            const char* ev = getenv("CFRK_ROW_SLOT_BYTES");
+            const long long x = ev ? atoll(ev) : 0;
+            return x > 0 ? (size_t)x : kSlotBytes;
+        }();
+        return v;
+    }
     int device = 0;
     cudaStream_t compute = nullptr, copy = nullptr;
     cudaEvent_t done[2] = {}, drained[2] = {};
@@ -728,8 +913,8 @@ struct Pipeline {
     size_t n_headers = 0;
     int32_t* d_rows[2] = {}; int32_t* h_rows[2] = {}; size_t cap_rows = 0;
     // pooled scratch of the sparse outputs (device + pinned mirrors), grown on demand
-    void* d_pool[4] = {}; size_t cap_pool[4] = {};
-    void* h_pool[4] = {}; size_t cap_hpool[4] = {};
+    void* d_pool[5] = {}; size_t cap_pool[5] = {};     // [4]: text bytes of the rows
+    void* h_pool[5] = {}; size_t cap_hpool[5] = {};
     char* h_hdr = nullptr; size_t cap_hhdr = 0;     // pinned staging of the record table
     Sequencer* seq = nullptr;
     bool fastq = false;                              // 4-line FASTQ records (fasta_scan.cu launch_fastq_scan)
@@ -911,6 +1096,7 @@ struct Pipeline {
     bool count_scanned_sparse(const Span& sp, const RecordIndex& ri, size_t nrows, int k, CfrkWriter& w, Err& err)
     {
         const size_t nreads = ri.start.size();
+        const int32_t* tb = nullptr;     // text bytes per row, when the writer maps the file
         if (nrows > 0) {
             if (!unwrap_scanned(sp.n, nreads, err)) return false;   // k > 8 is exact mode only
             int64_t cap = 0;
@@ -931,13 +1117,24 @@ struct Pipeline {
             if (!host_pool(2, std::max<size_t>(used, 1) * 8, err) || !host_pool(3, std::max<size_t>(used, 1) * 4, err)) return false;
             RF_CU(cudaMemcpyAsync(h_pool[2], d_pool[2], used * 8, cudaMemcpyDeviceToHost, compute));
             RF_CU(cudaMemcpyAsync(h_pool[3], d_pool[3], used * 4, cudaMemcpyDeviceToHost, compute));
+            if (w.sized()) {
+                if (!dev_pool(4, nrows * 4, err) || !host_pool(4, nrows * 4, err)) return false;
+                const unsigned g = (unsigned)std::min<size_t>((nrows + 7) / 8, 148 * 8);
+                pairs_text_bytes_kernel<uint64_t><<<g, 256, 0, compute>>>(static_cast<int64_t*>(d_pool[0]), static_cast<int32_t*>(d_pool[1]),
+                                                                          static_cast<uint64_t*>(d_pool[2]), static_cast<uint32_t*>(d_pool[3]),
+                                                                          (int64_t)nrows, static_cast<int32_t*>(d_pool[4]));
+                cfrk::count_launch();
+                RF_CU(cudaGetLastError());
+                RF_CU(cudaMemcpyAsync(h_pool[4], d_pool[4], nrows * 4, cudaMemcpyDeviceToHost, compute));
+                tb = static_cast<int32_t*>(h_pool[4]);
+            }
             RF_CU(cudaStreamSynchronize(compute));
         }
         if (!seq->wait_turn(sp.index)) { err.code = CFRK_EIO; err.msg = "aborted"; return false; }
         bool ok = true;
         if (nrows > 0)
             ok = w.write_pairs<uint64_t>(static_cast<int64_t*>(h_pool[0]), static_cast<int32_t*>(h_pool[1]),
-                                         static_cast<uint64_t*>(h_pool[2]), static_cast<uint32_t*>(h_pool[3]), nrows, err);
+                                         static_cast<uint64_t*>(h_pool[2]), static_cast<uint32_t*>(h_pool[3]), nrows, tb, err);
         seq->end_turn(sp.index);
         return ok;
     }
@@ -960,7 +1157,7 @@ struct Pipeline {
         const size_t bins = (size_t)1 << (2 * k), row_bytes = bins * 4;
         const bool compact = sparse && k >= 5;   // (bin, count) pairs instead of dense rows over PCIe
         // ring slots: as large as the span needs, at most kSlotBytes
-        if (!reserve(0, 0, std::max(row_bytes, std::min(kSlotBytes, nrows * row_bytes)), err)) return false;
+        if (!reserve(0, 0, std::max(row_bytes, std::min(slot_bytes_limit(), nrows * row_bytes)), err)) return false;
         const size_t rpt = (size_t)cfrk::dense_reads_per_tile(k);
         size_t slice = std::max<size_t>(1, cap_rows / row_bytes);
         slice = std::max(rpt, slice / rpt * rpt);
@@ -976,6 +1173,8 @@ struct Pipeline {
             cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, (int64_t*)nullptr, (int64_t*)nullptr, (int64_t)slice + 1, compute);
             if (!dev_pool(0, 2 * slot_bytes, err) || !dev_pool(1, scan_bytes + 16, err) || !host_pool(0, 2 * slot_bytes, err)) return false;
         }
+        const bool sized = w.sized();
+        if (sized && (!dev_pool(4, 2 * slice * 4, err) || !host_pool(4, 2 * slice * 4, err))) return false;
         for (size_t s = 0; s <= nslices; s++) {
             if (s < nslices) {
                 const int slot = (int)(s & 1);
@@ -987,6 +1186,13 @@ struct Pipeline {
                                                    (int64_t)r0, (int64_t)r1, k, mode, chunk_size, index_base,
                                                    d_rows[slot], compute);
                 if (e != cudaSuccess) { err.code = CFRK_ECUDA; err.msg = std::string("dense_count_kernel: ") + cudaGetErrorString(e); return false; }
+                int32_t* d_tb = static_cast<int32_t*>(d_pool[4]) + (size_t)slot * slice;
+                int32_t* h_tb = static_cast<int32_t*>(h_pool[4]) + (size_t)slot * slice;
+                if (sized) {
+                    const unsigned g = (unsigned)std::min<size_t>((r1 - r0 + 7) / 8, 148 * 8);
+                    row_text_bytes_kernel<<<g, 256, 0, compute>>>(d_rows[slot], (int64_t)(r1 - r0), (int)bins, sparse ? 1 : 0, d_tb);
+                    cfrk::count_launch();
+                }
                 if (compact) {
                     char* db = static_cast<char*>(d_pool[0]) + (size_t)slot * slot_bytes;
                     char* hb = static_cast<char*>(h_pool[0]) + (size_t)slot * slot_bytes;
@@ -1011,11 +1217,13 @@ struct Pipeline {
                     if (used > pair_cap) { err.code = CFRK_ECUDA; err.msg = "sparse compaction overflow"; return false; }
                     RF_CU(cudaMemcpyAsync(hb + tab_bytes, ck, used * 4, cudaMemcpyDeviceToHost, copy));
                     RF_CU(cudaMemcpyAsync(hb + tab_bytes + pair_cap * 4, cc, used * 4, cudaMemcpyDeviceToHost, copy));
+                    if (sized) RF_CU(cudaMemcpyAsync(h_tb, d_tb, (r1 - r0) * 4, cudaMemcpyDeviceToHost, copy));
                     RF_CU(cudaEventRecord(drained[slot], copy));
                 } else {
                     RF_CU(cudaEventRecord(done[slot], compute));
                     RF_CU(cudaStreamWaitEvent(copy, done[slot], 0));
                     RF_CU(cudaMemcpyAsync(h_rows[slot], d_rows[slot], (r1 - r0) * row_bytes, cudaMemcpyDeviceToHost, copy));
+                    if (sized) RF_CU(cudaMemcpyAsync(h_tb, d_tb, (r1 - r0) * 4, cudaMemcpyDeviceToHost, copy));
                     RF_CU(cudaEventRecord(drained[slot], copy));
                 }
             }
@@ -1028,14 +1236,15 @@ struct Pipeline {
                     have_turn = true;
                 }
                 RF_CU(cudaEventSynchronize(drained[slot]));
+                const int32_t* tb = sized ? static_cast<int32_t*>(h_pool[4]) + (size_t)slot * slice : nullptr;
                 bool ok;
                 if (compact) {
                     char* hb = static_cast<char*>(h_pool[0]) + (size_t)slot * slot_bytes;
                     ok = w.write_pairs<uint32_t>(reinterpret_cast<int64_t*>(hb), reinterpret_cast<int32_t*>(hb + (slice + 1) * 8),
                                                  reinterpret_cast<uint32_t*>(hb + tab_bytes),
-                                                 reinterpret_cast<uint32_t*>(hb + tab_bytes + pair_cap * 4), r1 - r0, err);
+                                                 reinterpret_cast<uint32_t*>(hb + tab_bytes + pair_cap * 4), r1 - r0, tb, err);
                 } else {
-                    ok = w.write_rows(h_rows[slot], r1 - r0, err);
+                    ok = w.write_rows(h_rows[slot], r1 - r0, tb, err);
                 }
                 if (!ok) return false;
             }
@@ -1056,7 +1265,7 @@ struct Pipeline {
             if (done[i]) cudaEventDestroy(done[i]);
             if (drained[i]) cudaEventDestroy(drained[i]);
         }
-        for (int i = 0; i < 4; i++) {
+        for (int i = 0; i < 5; i++) {
             cudaFree(d_pool[i]);
             if (h_pool[i]) cudaFreeHost(h_pool[i]);
         }
@@ -1215,6 +1424,43 @@ extern "C" int cfrk_run_file_multi(const char* fasta_path, const char* out_path,
         }
         if (!ok) { err.code = CFRK_ECUDA; err.msg = "no such CUDA device (this library has no CPU fallback)"; }
         else run_file(fasta_path, out_path, cfg, err);
+    }
+    if (err.code != CFRK_OK) cfrk::set_last_error(err.msg);
+    return err.code;
+}
+
+// PrintFreq (src/main.cu:26-63) as a function: dense rows -> .cfrk text.  Host only (no CUDA call).
+extern "C" int cfrk_write_rows(const char* out_path, const int32_t* rows, int64_t n_rows, int k, int nt, int flags)
+{
+    Err err;
+    if (!out_path || (!rows && n_rows > 0)) { err.code = CFRK_EINVAL; err.msg = "null argument"; }
+    else if (k < 1 || k > CFRK_CLI_DENSE_MAX_K || n_rows < 0) { err.code = CFRK_EINVAL; err.msg = "k must be in 1..8, n_rows >= 0"; }
+    else {
+        CfrkWriter w;
+        const size_t bins = (size_t)1 << (2 * k);
+        // slices as the pipeline hands them over: at most kSlotBytes of rows each
+        const size_t slice = std::max<size_t>(1, Pipeline::slot_bytes_limit() / (bins * 4));
+        if (w.open(out_path, k, nt, flags & CFRK_RUN_SPARSE, err)) {
+            std::vector<int32_t> tb;
+            for (size_t r = 0; r < (size_t)n_rows && err.code == CFRK_OK; r += slice) {
+                const size_t n = std::min(slice, (size_t)n_rows - r);
+                const auto t0 = std::chrono::steady_clock::now();
+                if (w.sized()) {      // the pipeline gets these from row_text_bytes_kernel
+                    tb.resize(n);
+                    const int nth = (int)std::min<size_t>((size_t)w.threads(), n);
+                    w.pool().run(nth, [&](int t) {
+                        for (size_t i = n * t / nth; i < n * (t + 1) / nth; i++)
+                            tb[i] = row_text_bytes(rows + (r + i) * bins, bins, w.labels(), flags & CFRK_RUN_SPARSE);
+                    });
+                }
+                const auto t1 = std::chrono::steady_clock::now();
+                w.write_rows(rows + r * bins, n, w.sized() ? tb.data() : nullptr, err);
+                if (getenv("CFRK_TRACE"))
+                    fprintf(stderr, "[cfrk write_rows] %zu rows: text sizes %.1f ms, format + write %.1f ms\n", n,
+                            std::chrono::duration<double, std::milli>(t1 - t0).count(),
+                            std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count());
+            }
+        }
     }
     if (err.code != CFRK_OK) cfrk::set_last_error(err.msg);
     return err.code;

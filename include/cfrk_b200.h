@@ -231,6 +231,14 @@ int cfrk_run_file(const char *fasta_path, const char *out_path, int k, int nt,
 int cfrk_run_file_multi(const char *fasta_path, const char *out_path, int k, int nt,
                         int64_t chunk_size, int flags, const int *devices, int n_devices);
 
+/*
+ * PrintFreq (src/main.cu:26-63) as a function: n_rows dense rows of 4^k int32 bins -> .cfrk text
+ * ("bin:count " tokens, rows separated by '\n', no trailing newline; out_path is truncated as by
+ * fopen(.., "w")), formatted and written by nt host threads.  flags: CFRK_RUN_SPARSE skips zero bins.
+ * Host only.  k = 1..8.
+ */
+int cfrk_write_rows(const char *out_path, const int32_t *rows, int64_t n_rows, int k, int nt, int flags);
+
 #ifdef __cplusplus
 }
 #endif
