@@ -890,7 +890,7 @@ __global__ void pairs_text_bytes_kernel(const int64_t* __restrict__ row_begin, c
 // ------------------------------------------------------------------------------------------
 // GPU side of one worker: device input buffer + row ring.
 struct Pipeline {
-    static constexpr size_t kSlotBytes = (size_t)128 << 20;
+    static constexpr size_t kSlotBytes = (size_t)16 << 20;
     static size_t slot_bytes_limit()      // CFRK_ROW_SLOT_BYTES: size of a row ring slot (measurements)
     {
         static const size_t v = [] {
@@ -911,7 +911,7 @@ struct Pipeline {
     // what the count kernels read: the raw span or its unwrapped copy
     const char* cur_bases = nullptr; const int64_t* cur_start = nullptr; const int32_t* cur_length = nullptr;
     size_t n_headers = 0;
-    int32_t* d_rows[2] = {}; int32_t* h_rows[2] = {}; size_t cap_rows = 0;
+    int32_t* d_rows[2] = {}; int32_t* h_rows[2] = {}; size_t cap_rows = 0, cap_hrows = 0;
     // pooled scratch of the sparse outputs (device + pinned mirrors), grown on demand
     void* d_pool[5] = {}; size_t cap_pool[5] = {};     // [4]: text bytes of the rows
     void* h_pool[5] = {}; size_t cap_hpool[5] = {};
@@ -951,7 +951,7 @@ struct Pipeline {
         cap_hpool[i] = want;
         return true;
     }
-    bool reserve(size_t in_bytes, size_t nreads, size_t row_bytes, Err& err)
+    bool reserve(size_t in_bytes, size_t nreads, size_t row_bytes, Err& err, bool host_rows = true)
     {
         if (in_bytes && in_bytes + CFRK_PAD > cap_in) {
             cudaFree(d_in); d_in = nullptr;
@@ -968,16 +968,16 @@ struct Pipeline {
         }
         const size_t need = row_bytes;
         if (row_bytes && need > cap_rows) {
-            for (int i = 0; i < 2; i++) {
-                cudaFree(d_rows[i]); if (h_rows[i]) cudaFreeHost(h_rows[i]);
-                d_rows[i] = nullptr; h_rows[i] = nullptr;
-            }
+            for (int i = 0; i < 2; i++) { cudaFree(d_rows[i]); d_rows[i] = nullptr; }
             cap_rows = 0;
-            for (int i = 0; i < 2; i++) {
-                RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_rows[i]), need));
-                RF_CU(cudaMallocHost(reinterpret_cast<void**>(&h_rows[i]), need));
-            }
+            for (int i = 0; i < 2; i++) RF_CU(cudaMalloc(reinterpret_cast<void**>(&d_rows[i]), need));
             cap_rows = need;
+        }
+        if (row_bytes && host_rows && need > cap_hrows) {      // compacted rows never reach the host as rows
+            for (int i = 0; i < 2; i++) { if (h_rows[i]) cudaFreeHost(h_rows[i]); h_rows[i] = nullptr; }
+            cap_hrows = 0;
+            for (int i = 0; i < 2; i++) RF_CU(cudaMallocHost(reinterpret_cast<void**>(&h_rows[i]), need));
+            cap_hrows = need;
         }
         return true;
     }
@@ -1156,10 +1156,13 @@ struct Pipeline {
         if (nrows == 0) return true;
         const size_t bins = (size_t)1 << (2 * k), row_bytes = bins * 4;
         const bool compact = sparse && k >= 5;   // (bin, count) pairs instead of dense rows over PCIe
-        // ring slots: as large as the span needs, at most kSlotBytes
-        if (!reserve(0, 0, std::max(row_bytes, std::min(slot_bytes_limit(), nrows * row_bytes)), err)) return false;
+        // ring slots: as large as the span needs, at most kSlotBytes -- pinned host memory is what makes large slots
+        // expensive; compacted rows stay on the device, and their slices end with a host round trip (the number of
+        // pairs): large device slots, no host rows
+        const size_t slot_limit = compact ? std::max(slot_bytes_limit(), (size_t)128 << 20) : slot_bytes_limit();
+        if (!reserve(0, 0, std::max(row_bytes, std::min(slot_limit, nrows * row_bytes)), err, !compact)) return false;
         const size_t rpt = (size_t)cfrk::dense_reads_per_tile(k);
-        size_t slice = std::max<size_t>(1, cap_rows / row_bytes);
+        size_t slice = std::max<size_t>(1, (compact ? cap_rows : std::min(cap_rows, cap_hrows)) / row_bytes);
         slice = std::max(rpt, slice / rpt * rpt);
         slice = std::min(slice, (nrows + rpt - 1) / rpt * rpt);
         const size_t nslices = (nrows + slice - 1) / slice;
@@ -1295,9 +1298,10 @@ bool run_pass(Source& src, size_t file_off, int64_t first_read, bool rows, const
               PassResult& res, Err& err)
 {
     if (!src.restart(file_off, err)) return false;
-    // 64 MiB streaming window; small inputs get small pinned buffers: pinning costs ~0.35 ms/MiB and
-    // test-sized inputs should start instantly
-    size_t window = (size_t)64 << 20;
+    // 16 MiB streaming window (measured on 2 M x 150 bp, k = 4, all rows: 64 MiB windows + 128 MiB row slots 1033 ms,
+    // 32 + 32: 769 ms, 16 + 16: 506 ms -- pinning costs 0.35-0.7 ms/MiB and the first span's rows wait for it);
+    // small inputs get small pinned buffers: test-sized inputs should start instantly
+    size_t window = (size_t)16 << 20;
     if (const char* ev = getenv("CFRK_WINDOW_BYTES")) window = std::max<size_t>(4096, (size_t)atoll(ev));   // tests: many spans from small files
     const size_t left = src.size_hint() > file_off ? src.size_hint() - file_off : 0;
     if (left < window) window = std::max<size_t>((size_t)1 << 16, (left + 4095) & ~(size_t)4095);
@@ -1305,11 +1309,13 @@ bool run_pass(Source& src, size_t file_off, int64_t first_read, bool rows, const
     const size_t spans_guess = left / window + 1;
     const int nslots = (int)std::min<size_t>((size_t)nworkers + 1, spans_guess + 1);
     SpanReader rd;
-    if (!rd.open(&src, window, std::max(2, nslots), err)) return false;
-    tr.mark("reader open (pinned buffers, window)", (size_t)nslots, window);
     Sequencer seq;
     seq.reset(first_read);
-    rd.start(file_off);
+    // the workers start first: their streams, device buffers and pinned row ring are set up while the reader pins its
+    // buffers and reads the first window
+    std::mutex go_mu;
+    std::condition_variable go_cv;
+    int go = 0;     // 1: the reader runs, 2: it could not be opened
 
     std::mutex res_mu;
     Err first_err;
@@ -1324,11 +1330,40 @@ bool run_pass(Source& src, size_t file_off, int64_t first_read, bool rows, const
     };
     const int nthreads = (int)std::min<size_t>((size_t)nworkers, std::max<size_t>(1, spans_guess));
     std::vector<std::thread> th;
+    // a worker that runs out of spans keeps its buffers until all are done: freeing device and pinned memory takes
+    // the driver's locks for tens of milliseconds and stalls the worker that still has the last span
+    // (measured, k = 6 --sparse: 760 ms for the last span instead of 35)
+    std::mutex fin_mu;
+    std::condition_variable fin_cv;
+    int finished = 0;
+    struct Finish {
+        std::mutex& mu; std::condition_variable& cv; int& n; int all;
+        ~Finish()
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            n++;
+            cv.notify_all();
+            cv.wait(lk, [&] { return n >= all; });
+        }
+    };
     for (int t = 0; t < nthreads; t++) {
         th.emplace_back([&, t] {
             Err e;
             Pipeline gpu;
-            if (!gpu.init(cfg.devices[(size_t)t % cfg.devices.size()], &seq, e)) { fail(e); return; }
+            Finish fin{fin_mu, fin_cv, finished, nthreads};     // destroyed before gpu: waits for the other workers
+            bool ready = gpu.init(cfg.devices[(size_t)t % cfg.devices.size()], &seq, e);
+            if (ready && left >= ((size_t)1 << 20)) {
+                const size_t row_bytes = rows && cfg.k <= CFRK_CLI_DENSE_MAX_K ? (size_t)4 << (2 * cfg.k) : 0;
+                const bool compact = (cfg.flags & CFRK_RUN_SPARSE) && cfg.k >= 5;      // count_rows_inner sizes those itself
+                ready = gpu.reserve(window + window / 8, window / 64 + 64,
+                                    row_bytes && !compact ? std::max(row_bytes, Pipeline::slot_bytes_limit()) : 0, e);
+            }
+            {
+                std::unique_lock<std::mutex> lk(go_mu);
+                go_cv.wait(lk, [&] { return go != 0; });
+                if (go == 2) return;
+            }
+            if (!ready) { fail(e); return; }
             gpu.fastq = src.is_fastq();
             RecordIndex ri;
             for (;;) {
@@ -1369,7 +1404,18 @@ bool run_pass(Source& src, size_t file_off, int64_t first_read, bool rows, const
             }
         });
     }
+    const bool opened = rd.open(&src, window, std::max(2, nslots), err);
+    if (opened) {
+        tr.mark("reader open (pinned buffers, window)", (size_t)nslots, window);
+        rd.start(file_off);
+    }
+    {
+        std::lock_guard<std::mutex> lk(go_mu);
+        go = opened ? 1 : 2;
+    }
+    go_cv.notify_all();
     for (auto& x : th) x.join();
+    if (!opened) return false;
     rd.stop();
     if (failed.load()) { err = first_err; return false; }
     if (rd.error().code != CFRK_OK) { err = rd.error(); return false; }

@@ -83,8 +83,7 @@ def test_rows_with_every_digit_count(tmp_path, k, writer):
 
 
 def test_many_slices(tmp_path, monkeypatch):
-    """several slices per call (CFRK_ROW_SLOT_BYTES is read once per process: the rows here exceed the default 128 MiB
-    slot at k = 8 only, so use k = 7 rows and enough of them for two slices of 128 MiB / 64 KiB = 2048 rows)"""
+    """several slices per call: k = 7 rows are 64 KiB, a 16 MiB row slot holds 256 of them -> 10 slices"""
     rng = np.random.default_rng(3)
     rows = (rng.random((2500, 4 ** 7)) < 0.01).astype(np.int32) * rng.integers(1, 30, size=(2500, 4 ** 7)).astype(np.int32)
     for sparse in (False, True):
