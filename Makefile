@@ -9,7 +9,7 @@ OBJ     := build/obj
 LIB     := cfrk_b200/lib/libcfrk_b200.so
 CLI     := bin/cfrk
 
-CU_SRCS  := $(CSRC)/kernels.cu $(CSRC)/dense_lane.cu $(CSRC)/row_pairs.cu $(CSRC)/sparse.cu $(CSRC)/hist_split.cu $(CSRC)/fasta_scan.cu $(CSRC)/api.cu $(CSRC)/compat_shim.cu $(CSRC)/runfile.cu
+CU_SRCS  := $(CSRC)/kernels.cu $(CSRC)/dense_lane.cu $(CSRC)/row_pairs.cu $(CSRC)/sparse.cu $(CSRC)/hist_split.cu $(CSRC)/hist_reduce.cu $(CSRC)/fasta_scan.cu $(CSRC)/api.cu $(CSRC)/compat_shim.cu $(CSRC)/runfile.cu
 CU_OBJS  := $(patsubst $(CSRC)/%.cu,$(OBJ)/%.o,$(CU_SRCS))
 HDRS     := $(wildcard $(CSRC)/*.h $(CSRC)/*.cuh) include/cfrk_b200.h
 

@@ -754,7 +754,21 @@ def run_ours(args):
         k5 = 12
         n5 = split_even(args.c5_reads, world, rank)
         f5, s5, l5 = make_reads_device(torch, n5, L, 46 + rank, 0.0, "ascii", dev)
-        hist = torch.zeros(4 ** k5, dtype=torch.int32, device=dev)
+        # N > 1: the table lives in memory the peers can address and is summed in place by cfrk_hist_allreduce_device
+        # (one kernel per GPU over NVLink peer memory, hist_reduce.cu); NCCL only if that cannot be set up
+        reducer, reduce_how = None, "none (1 GPU)"
+        if world > 1:
+            try:
+                from cfrk_b200.sharding import HistReducer
+                reducer = HistReducer(4 ** k5, dev)
+                reduce_how = f"cfrk_hist_allreduce_device ({reducer.mode})"
+            except Exception as e:  # noqa: BLE001
+                reducer, reduce_how = None, f"NCCL all-reduce (peer memory unavailable: {type(e).__name__})"
+            flag = torch.tensor([1 if reducer is not None else 0], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)     # all ranks or none
+            if int(flag) == 0 and reducer is not None:
+                reducer, reduce_how = None, "NCCL all-reduce (peer memory unavailable on a peer)"
+        hist = reducer.table if reducer is not None else torch.zeros(4 ** k5, dtype=torch.int32, device=dev)
         W5, K5 = 3, 10
         evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(K5)]
 
@@ -766,8 +780,10 @@ def run_ours(args):
                                   fmt=cf.FMT_ASCII, stream=stream)
             if ev:
                 ev[1].record()
-            if world > 1:
-                dist.all_reduce(hist, op=dist.ReduceOp.SUM)   # NCCL over NVLink: the path's one exchange step
+            if reducer is not None:
+                reducer.allreduce(stream)                     # the path's one exchange step
+            elif world > 1:
+                dist.all_reduce(hist, op=dist.ReduceOp.SUM)
             if ev:
                 ev[2].record()
         for _ in range(W5):
@@ -785,14 +801,31 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms5, cnt5, red5 = (float(x) for x in t)
         windows = args.c5_reads * (L - k5 + 1)
+        nccl5 = None
+        if world > 1:        # the library collective on the same table, for the record (outside the timed steps)
+            tmp = hist.clone()
+            for _ in range(3):
+                dist.all_reduce(tmp)
+            barrier()
+            n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0.record()
+            for _ in range(K5):
+                dist.all_reduce(tmp)
+            n1.record()
+            torch.cuda.synchronize()
+            tn5 = torch.tensor([n0.elapsed_time(n1) / K5], dtype=torch.float64, device=dev)
+            dist.all_reduce(tn5, op=dist.ReduceOp.MAX)
+            nccl5 = round(float(tn5), 3)
+            del tmp
+        status5 = reducer.status() if reducer is not None else 0
         configs["C5_global_hist_k12"] = {
             "config": "C5: 1 Gbase (6 666 667 x 150 bp) whole-dataset histogram, k = 12, reads split over the ranks, "
-                      "NCCL all-reduce of the 64 MiB table", "k": k5, "reads_all_ranks": args.c5_reads, "scaling": "strong",
+                      "64 MiB table summed over the ranks in place", "reduce": reduce_how, "nccl_allreduce_ms": nccl5, "k": k5, "reads_all_ranks": args.c5_reads, "scaling": "strong",
             "ms_per_step": round(ms5, 3), "count_ms": round(cnt5, 3), "allreduce_ms": round(red5, 3),
             "gbases_s": round(args.c5_reads * L / ms5 / 1e6, 1), "red_global_per_s_per_gpu_G": round(windows / world / cnt5 / 1e6, 1),
             "alg_bytes": int(args.c5_reads * (L + 8) + 4 ** k5 * 4),
-            "check": {"sum_eq_windows": int(hist.sum(dtype=torch.int64)) == windows}}
-        del f5, s5, l5, hist
+            "check": {"sum_eq_windows": int(hist.sum(dtype=torch.int64)) == windows, "all_peers_met": status5 == 0}}
+        del f5, s5, l5, hist, reducer
         torch.cuda.empty_cache()
 
     if rank != 0:

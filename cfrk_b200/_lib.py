@@ -11,7 +11,7 @@ SYMBOLS = [
     "cfrk_count_dense_host", "cfrk_set_host_threads", "cfrk_count_dense_device", "cfrk_count_dense_packed_device",
     "cfrk_dense_reads_per_tile",
     "cfrk_encode_2bit_device", "cfrk_global_hist_device", "cfrk_count_sparse_device", "cfrk_count_sparse_packed_device", "cfrk_scan_fasta_device",
-    "cfrk_run_file", "cfrk_run_file_multi", "cfrk_write_rows",
+    "cfrk_run_file", "cfrk_run_file_multi", "cfrk_write_rows", "cfrk_hist_allreduce_device",
 ]
 
 _lib = None
@@ -48,6 +48,7 @@ def load():
                                                   C.POINTER(C.c_int64), vp]
     L.cfrk_scan_fasta_device.argtypes = [vp, i64, i32, vp, vp, vp, i64, C.POINTER(C.c_int64), vp]
     L.cfrk_run_file.argtypes = [C.c_char_p, C.c_char_p, i32, i32, i64, i32, i32]
+    L.cfrk_hist_allreduce_device.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), i32, i32, i64, C.c_uint32, vp, vp]
     L.cfrk_write_rows.argtypes = [C.c_char_p, C.c_void_p, i64, i32, i32, i32]
     L.cfrk_run_file_multi.argtypes = [C.c_char_p, C.c_char_p, i32, i32, i64, i32, C.POINTER(C.c_int), i32]
     _lib = L

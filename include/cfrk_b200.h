@@ -160,6 +160,25 @@ int cfrk_global_hist_device(const void *d_bases, int fmt, const int64_t *d_start
                             uint32_t *d_hist, void *stream);
 
 /*
+ * The exchange step of the whole-dataset histogram on the GPUs of ONE box (north_star config 5; the reference has
+ * no multi-GPU reduction -- its devCount pthreads share one GPU, src/main.cu:208-230): every rank's table
+ * becomes the element-wise sum of all tables, in place, by one kernel per GPU over NVLink peer memory (two shots:
+ * rank r sums slice r of every table, then writes it into every table).  To be called by every rank with the same
+ * epoch (1, 2, 3, ... per call), on the stream that produced its table.
+ *   peer_tables[i]  address of rank i's 4^k uint32 table as THIS rank addresses it (own table included) --
+ *                   symmetric / peer-mapped allocations made by the host side (torch symmetric memory, cuMem + IPC)
+ *   peer_flags[i]   the same for a CFRK_HIST_REDUCE_FLAG_BYTES buffer per rank, zeroed once before the first call;
+ *                   word CFRK_HIST_REDUCE_STATUS_WORD of the own buffer is non-zero if a peer did not show up
+ *                   within ~2 s (tables then undefined)
+ *   multicast_table NULL, or the multicast address of the tables (NVLS: the switch adds; sums must stay < 2^32)
+ */
+#define CFRK_HIST_REDUCE_MAX_RANKS   8
+#define CFRK_HIST_REDUCE_FLAG_BYTES  65536
+#define CFRK_HIST_REDUCE_STATUS_WORD 8192
+int cfrk_hist_allreduce_device(void *const *peer_tables, void *const *peer_flags, int rank, int world,
+                               int64_t n_bins, uint32_t epoch, void *multicast_table, void *stream);
+
+/*
  * Sparse per-read counts, exact semantics, k = 1..31 (BASELINE configs 3 and 4; no reference
  * counterpart: its dense rows end at k = 8 with the default chunk).
  * Row r = the sorted distinct k-mers of read r and their multiplicities, stored at
