@@ -174,6 +174,36 @@ __device__ __forceinline__ void count_planes(uint32_t codes, uint32_t pcodes, ui
     }
 }
 
+// Two blocks at once: the masks of a block use the even bits only (one per base), so block B's go to the odd bits
+// and every POPC counts 32 bases: per 32 bases 16 (k = 2) / 4 (k = 1) LOP3 + POPC + add instead of twice that.
+template <int K>
+__device__ __forceinline__ void count_planes2(uint32_t codesA, uint32_t pcodesA, uint32_t goodA, uint32_t codesB,
+                                              uint32_t pcodesB, uint32_t goodB, uint32_t (&cnt)[1 << (2 * K)])
+{
+    static_assert(K == 1 || K == 2, "bit-plane counting is for 4 and 16 bins");
+    // planes of the window's LAST base: low / high code bit of base j at bit 2(15-j) (A) and 2(15-j)+1 (B)
+    const uint32_t lo = (codesA & kEven) + 2u * (codesB & kEven);
+    const uint32_t hi = ((codesA >> 1) & kEven) + 2u * ((codesB >> 1) & kEven);
+    const uint32_t good = goodA + 2u * goodB;
+    if (K == 1) {
+        cnt[0] += __popc(~lo & ~hi & good);
+        cnt[1] += __popc(lo & ~hi & good);
+        cnt[2] += __popc(~lo & hi & good);
+        cnt[3] += __popc(lo & hi & good);
+    } else {
+        // ... and of its FIRST base (base j-1 brought under base j's bit pair)
+        const uint32_t c1A = __funnelshift_r(codesA, pcodesA, 2), c1B = __funnelshift_r(codesB, pcodesB, 2);
+        const uint32_t lo1 = (c1A & kEven) + 2u * (c1B & kEven);
+        const uint32_t hi1 = ((c1A >> 1) & kEven) + 2u * ((c1B >> 1) & kEven);
+        const uint32_t m[4] = {~lo1 & ~hi1 & good, lo1 & ~hi1 & good, ~lo1 & hi1 & good, lo1 & hi1 & good};
+        const uint32_t s2[4] = {~lo & ~hi, lo & ~hi, ~lo & hi, lo & hi};
+#pragma unroll
+        for (int a = 0; a < 4; a++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) cnt[4 * a + c] += __popc(m[a] & s2[c]);
+    }
+}
+
 // k-mer windows of one block into a shared-memory row aligned to its own size (cf. emit_item)
 template <int K>
 __device__ __forceinline__ void count_row(uint32_t codes, uint32_t pcodes, uint32_t good, uint32_t row_saddr)
@@ -201,8 +231,13 @@ __device__ __forceinline__ void lane_block(bool live, const uint4 raw, int t0, i
 {
     uint32_t valid = 0, cmask = 0;
     codes = 0;
+    // packed words: a block without N (validity 0xFFFF: nearly all) needs no bit spreading -- a warp-uniform branch,
+    // 2 instructions instead of 14
+    bool all_valid = false;
+    if (FMT == FMT_PACKED) all_valid = !__any_sync(kFull, live && raw.y != 0xFFFFu);
     if (live) {
-        encode16_s<FMT>(raw, codes, valid);
+        if (FMT == FMT_PACKED && all_valid) { codes = raw.x; valid = kEven; }
+        else encode16_s<FMT>(raw, codes, valid);
         if (t0 >= K - 1 && t0 + 16 <= tend) {
             cmask = kEven;                                                  // a block inside the read: every window end counts
         } else {
@@ -398,6 +433,23 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dense_lane_kernel(const Dens
             uint32_t carry_c = 0, carry_v = 0;
             int nbad = 0;
             uint4 raw_next = make_uint4(0u, 0u, 0u, 0u);
+            if constexpr (PLANES && SPLIT == 1) {
+                // a lane per read, two blocks per step (count_planes2); the next two are on their way from shared memory
+                const int steps = (rounds + 1) >> 1;
+                uint4 raw_next2 = make_uint4(0u, 0u, 0u, 0u);
+                if (0 < nblk) raw_next = fetch_block<FMT, true>(bases, sg, blk0);
+                if (1 < nblk) raw_next2 = fetch_block<FMT, true>(bases, sg, blk0 + 1);
+                for (int i = 0; i < steps; i++) {
+                    const int b = 2 * i;
+                    const uint4 rawA = raw_next, rawB = raw_next2;
+                    if (b + 2 < nblk) raw_next = fetch_block<FMT, true>(bases, sg, blk0 + b + 2);
+                    if (b + 3 < nblk) raw_next2 = fetch_block<FMT, true>(bases, sg, blk0 + b + 3);
+                    uint32_t cA, pA, gA, cB, pB, gB;
+                    lane_block<K, FMT, 1>(b < nblk, rawA, b * 16 - off, tend, a.mode, carry_c, carry_v, cA, pA, gA, nbad);
+                    lane_block<K, FMT, 1>(b + 1 < nblk, rawB, b * 16 + 16 - off, tend, a.mode, carry_c, carry_v, cB, pB, gB, nbad);
+                    count_planes2<K>(cA, pA, gA, cB, pB, gB, cnt);
+                }
+            } else {
             if (g < nblk) raw_next = fetch_block<FMT, true>(bases, sg, blk0 + g);
             for (int i = 0; i < rounds; i++) {
                 const int b = i * SPLIT + g;
@@ -409,6 +461,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dense_lane_kernel(const Dens
                 lane_block<K, FMT, SPLIT>(live, raw, b * 16 - off, tend, a.mode, carry_c, carry_v, codes, pcodes, good, nbad);
                 if constexpr (PLANES) count_planes<K>(codes, pcodes, good, cnt);
                 else count_row<K>(codes, pcodes, good, row_saddr);
+            }
             }
             if (compat) {
 #pragma unroll
