@@ -592,9 +592,11 @@ public:
     bool write_rows(const int32_t* rows, size_t nrows, const int32_t* text_bytes, Err& err)
     {
         if (!nrows) return true;
-        if (mapped_ && text_bytes)
-            return write_mapped(nrows, text_bytes, [&](size_t r, char* p, bool exact) {
+        if (mapped_ && text_bytes) {
+            const int m = write_mapped(nrows, text_bytes, [&](size_t r, char* p, bool exact) {
                 return format_row(rows + r * bins_, bins_, *labels_, sparse_, exact, p); }, err);
+            if (m >= 0) return m != 0;
+        }
         const int nt = (int)std::min<size_t>((size_t)nt_, nrows);
         std::vector<char> good(nt, 1);
         const bool first_file = first_;
@@ -620,9 +622,11 @@ public:
                      const uint32_t* counts, size_t nrows, const int32_t* text_bytes, Err& err)
     {
         if (!nrows) return true;
-        if (mapped_ && text_bytes)
-            return write_mapped(nrows, text_bytes, [&](size_t r, char* p, bool) {
+        if (mapped_ && text_bytes) {
+            const int m = write_mapped(nrows, text_bytes, [&](size_t r, char* p, bool) {
                 return format_pairs<KeyT>(keys + row_begin[r], counts + row_begin[r], row_count[r], p); }, err);
+            if (m >= 0) return m != 0;
+        }
         const int nt = (int)std::min<size_t>((size_t)nt_, nrows);
         std::vector<char> good(nt, 1);
         const bool first_file = first_;
@@ -650,31 +654,36 @@ private:
     // threads format STRAIGHT INTO IT -- no private buffer, no copy, and the page allocation of the new pages runs on
     // all threads, where pwrite()s into one file take turns on the inode lock (tools/host/pwrite_scaling.c: 2.1-2.6 GB/s
     // into tmpfs whatever the thread count; the mapping scales with the threads).
+    // 1: written, 0: failed (err), -1: this file cannot be mapped -- the caller (and every later slice) takes the buffers
     template <typename RowFn>
-    bool write_mapped(size_t nrows, const int32_t* text_bytes, RowFn&& row_fn, Err& err)
+    int write_mapped(size_t nrows, const int32_t* text_bytes, RowFn&& row_fn, Err& err)
     {
         row_off_.resize(nrows + 1);
         int64_t o = 0;
         for (size_t r = 0; r < nrows; r++) {
             row_off_[r] = o;
-            if (text_bytes[r] < 0) { err.code = CFRK_EIO; err.msg = "internal: negative row text size"; return false; }
+            if (text_bytes[r] < 0) { err.code = CFRK_EIO; err.msg = "internal: negative row text size"; return 0; }
             o += (int64_t)text_bytes[r] + ((first_ && r == 0) ? 0 : 1);
         }
         row_off_[nrows] = o;
         const int64_t total = o;
         const bool first_file = first_;
-        first_ = false;
-        if (total == 0) return true;
+        if (total == 0) { first_ = false; return 1; }
         struct statvfs vfs;
         if (fstatvfs(fd_, &vfs) == 0 && (uint64_t)vfs.f_bavail * vfs.f_frsize < (uint64_t)total) {
-            err.code = CFRK_EIO; err.msg = "no space left for the output"; return false;   // a mapped write would fault instead
+            err.code = CFRK_EIO; err.msg = "no space left for the output"; return 0;   // a mapped write would fault instead
         }
-        if (ftruncate(fd_, off_ + (off_t)total) != 0) { err.code = CFRK_EIO; err.msg = std::string("cannot grow the output: ") + strerror(errno); return false; }
+        if (ftruncate(fd_, off_ + (off_t)total) != 0) { err.code = CFRK_EIO; err.msg = std::string("cannot grow the output: ") + strerror(errno); return 0; }
         const off_t pg = (off_t)sysconf(_SC_PAGESIZE);
         const off_t map_at = off_ & ~(pg - 1);
         const size_t map_len = (size_t)(off_ + (off_t)total - map_at);
         void* m = mmap(nullptr, map_len, PROT_READ | PROT_WRITE, MAP_SHARED, fd_, map_at);
-        if (m == MAP_FAILED) { err.code = CFRK_EIO; err.msg = std::string("cannot map the output: ") + strerror(errno); return false; }
+        if (m == MAP_FAILED) {          // a file system without shared writable mappings: back to buffers + pwrite
+            if (ftruncate(fd_, off_) != 0) { err.code = CFRK_EIO; err.msg = std::string("cannot shrink the output: ") + strerror(errno); return 0; }
+            mapped_ = false;
+            return -1;
+        }
+        first_ = false;
         char* base = static_cast<char*>(m) + (off_ - map_at);
         // pieces of about equal text, cut at rows
         const int nt = (int)std::min<size_t>((size_t)nt_, nrows);
@@ -695,8 +704,8 @@ private:
         });
         munmap(m, map_len);
         off_ += (off_t)total;
-        for (char g : good) if (!g) { err.code = CFRK_EIO; err.msg = "internal: row text size mismatch"; return false; }
-        return true;
+        for (char g : good) if (!g) { err.code = CFRK_EIO; err.msg = "internal: row text size mismatch"; return 0; }
+        return 1;
     }
     // formatted parts -> file, in order.  Regular files: every part is written at its own offset
     // by its own pool thread (pwrite); pipes (the Swift stdout form): sequential write.
