@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dense_lane_kernel(const Dens
             uint4 raw_next = make_uint4(0u, 0u, 0u, 0u);
             if constexpr (PLANES && SPLIT == 1) {
                 // a lane per read, two blocks per step (count_planes2); the next two are on their way from shared memory
-                const int steps = (rounds + 1) >> 1;
+                const int steps = rounds >> 1;          // an odd last block (11 blocks for most 150-bp tiles) goes alone
                 uint4 raw_next2 = make_uint4(0u, 0u, 0u, 0u);
                 if (0 < nblk) raw_next = fetch_block<FMT, true>(bases, sg, blk0);
                 if (1 < nblk) raw_next2 = fetch_block<FMT, true>(bases, sg, blk0 + 1);
@@ -448,6 +448,12 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) dense_lane_kernel(const Dens
                     lane_block<K, FMT, 1>(b < nblk, rawA, b * 16 - off, tend, a.mode, carry_c, carry_v, cA, pA, gA, nbad);
                     lane_block<K, FMT, 1>(b + 1 < nblk, rawB, b * 16 + 16 - off, tend, a.mode, carry_c, carry_v, cB, pB, gB, nbad);
                     count_planes2<K>(cA, pA, gA, cB, pB, gB, cnt);
+                }
+                if (rounds & 1) {
+                    const int b = 2 * steps;
+                    uint32_t codes, pcodes, good;
+                    lane_block<K, FMT, 1>(b < nblk, raw_next, b * 16 - off, tend, a.mode, carry_c, carry_v, codes, pcodes, good, nbad);
+                    count_planes<K>(codes, pcodes, good, cnt);
                 }
             } else {
             if (g < nblk) raw_next = fetch_block<FMT, true>(bases, sg, blk0 + g);

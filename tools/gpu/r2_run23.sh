@@ -7,7 +7,7 @@ python - <<PY
 import json
 d=json.loads(open("$O/r2_b23.json").read().strip().splitlines()[-1])
 print("value", d["value"], "min_frac", d.get("min_frac"))
-for k,v in sorted(d["per_k"].items()): print(k, v.get("gbases_s"), v.get("frac_of_peak"))
+for v in d["per_k"]: print(v.get("k"), v.get("gbases_s"), v.get("frac_of_peak"))
 print(d.get("checks"))
 print({k: (v.get("gbases_s"), v.get("check")) for k,v in d.get("configs",{}).items()})
 PY
