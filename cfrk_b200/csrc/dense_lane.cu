@@ -248,6 +248,19 @@ __device__ __forceinline__ void lane_block(bool live, const uint4 raw, int t0, i
     // 2 instructions instead of 14
     bool all_valid = false;
     if (FMT == FMT_PACKED) all_valid = !__any_sync(kFull, live && raw.y != 0xFFFFu);
+    if (W == 1) {
+        // a lane per read: when this block lies inside its read in EVERY lane, without N here or in the block before
+        // (8 of the 10-11 blocks of a 150-bp tile), all 16 window ends count and nothing else is to be found out
+        uint32_t c = raw.x, v = kEven;
+        if (FMT != FMT_PACKED) encode16_s<FMT>(raw, c, v);
+        const bool inside = live && t0 >= K - 1 && t0 + 16 <= tend && carry_v == kEven &&
+                            (FMT == FMT_PACKED ? raw.y == 0xFFFFu : v == kEven);
+        if (__all_sync(kFull, inside)) {
+            codes = c; pcodes = carry_c; good = kEven;
+            carry_c = c;
+            return;
+        }
+    }
     if (live) {
         if (FMT == FMT_PACKED && all_valid) { codes = raw.x; valid = kEven; }
         else encode16_s<FMT>(raw, codes, valid);
