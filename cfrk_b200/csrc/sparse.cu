@@ -459,6 +459,31 @@ __device__ __forceinline__ void sort_lane(KeyT (&k)[E])
 #undef CFRK_CE
 }
 
+// After the cross-lane stages of a merge level a lane holds the right E keys as a BITONIC sequence (any rotation of
+// an ascending one: the 74 / 112 reachable 0-1 patterns, tools/host/lane_merge_search.py), so a merger does instead of
+// the full network: 18 comparators for 9 keys (sort the columns, then the rows, of a 3 x 3 grid), 25 for 11.
+template <typename KeyT, int E>
+__device__ __forceinline__ void merge_lane(KeyT (&k)[E])
+{
+    static_assert(E == 9 || E == 11, "mergers for 9 and 11 keys per lane");
+#define CFRK_CE(i, j) { const KeyT a_ = k[i], b_ = k[j]; k[i] = a_ < b_ ? a_ : b_; k[j] = a_ < b_ ? b_ : a_; }
+    if constexpr (E == 9) {
+        CFRK_CE(0, 3) CFRK_CE(1, 4) CFRK_CE(5, 8)
+        CFRK_CE(0, 6) CFRK_CE(1, 7) CFRK_CE(2, 8)
+        CFRK_CE(3, 6) CFRK_CE(2, 5) CFRK_CE(4, 7)
+        CFRK_CE(0, 1) CFRK_CE(3, 4) CFRK_CE(6, 7)
+        CFRK_CE(0, 2) CFRK_CE(3, 5) CFRK_CE(6, 8)
+        CFRK_CE(1, 2) CFRK_CE(4, 5) CFRK_CE(7, 8)
+    } else {
+        CFRK_CE(0, 4) CFRK_CE(5, 10) CFRK_CE(1, 6) CFRK_CE(3, 9) CFRK_CE(2, 7)
+        CFRK_CE(1, 3) CFRK_CE(6, 9) CFRK_CE(0, 8) CFRK_CE(2, 5) CFRK_CE(7, 10)
+        CFRK_CE(4, 8) CFRK_CE(3, 5) CFRK_CE(6, 7) CFRK_CE(0, 1)
+        CFRK_CE(8, 9) CFRK_CE(0, 2)
+        CFRK_CE(1, 2) CFRK_CE(2, 3) CFRK_CE(3, 4) CFRK_CE(4, 5) CFRK_CE(5, 6) CFRK_CE(6, 7) CFRK_CE(7, 8) CFRK_CE(8, 10) CFRK_CE(9, 10)
+    }
+#undef CFRK_CE
+}
+
 // 16 lanes x E keys, blocked layout (lane hl holds elements E*hl .. E*hl+E-1), ascending; both halves of
 // the warp at once (lane masks < 16 never cross the halves)
 template <typename KeyT, int E = kHalfE>
@@ -485,7 +510,7 @@ __device__ __forceinline__ void half_sort(KeyT (&key)[E])
                 key[e] = keep_minmax<KeyT>(key[e], other, upper);
             }
         }
-        sort_lane<KeyT, E>(key);
+        merge_lane<KeyT, E>(key);
     }
 }
 
