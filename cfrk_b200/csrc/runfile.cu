@@ -670,7 +670,7 @@ private:
         const bool first_file = first_;
         if (total == 0) { first_ = false; return 1; }
         struct statvfs vfs;
-        if (fstatvfs(fd_, &vfs) == 0 && (uint64_t)vfs.f_bavail * vfs.f_frsize < (uint64_t)total) {
+        if (fstatvfs(fd_, &vfs) == 0 && vfs.f_blocks > 0 && (uint64_t)vfs.f_bavail * vfs.f_frsize < (uint64_t)total) {
             err.code = CFRK_EIO; err.msg = "no space left for the output"; return 0;   // a mapped write would fault instead
         }
         if (ftruncate(fd_, off_ + (off_t)total) != 0) { err.code = CFRK_EIO; err.msg = std::string("cannot grow the output: ") + strerror(errno); return 0; }
