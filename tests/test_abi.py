@@ -74,6 +74,24 @@ def test_housekeeping_entry_points_need_no_gpu():
     assert L.cfrk_run_file_multi(b"/nonexistent", b"/tmp/x", 40, 1, 8192, 0, devs, 2) == -1      # k out of range
 
 
+def test_hist_allreduce_argument_checks_need_no_gpu():
+    """cfrk_hist_allreduce_device: bad arguments are refused before any CUDA call; one rank is a no-op"""
+    L = cf.lib()
+    one = (ctypes.c_void_p * 1)(0x1000)
+    two = (ctypes.c_void_p * 2)(0x1000, 0x2000)
+    odd = (ctypes.c_void_p * 2)(0x1000, 0x2004)
+    nul = (ctypes.c_void_p * 2)(0x1000, None)
+    assert L.cfrk_hist_allreduce_device(one, one, 0, 1, 16, 1, None, None) == 0          # world 1: nothing to do
+    assert L.cfrk_hist_allreduce_device(None, two, 0, 2, 16, 1, None, None) == -1
+    assert L.cfrk_hist_allreduce_device(two, two, 2, 2, 16, 1, None, None) == -1         # rank out of range
+    assert L.cfrk_hist_allreduce_device(two, two, 0, 9, 16, 1, None, None) == -1         # more than 8 ranks
+    assert L.cfrk_hist_allreduce_device(two, two, 0, 2, 6, 1, None, None) == -1          # not a multiple of 4 bins
+    assert L.cfrk_hist_allreduce_device(two, two, 0, 2, 16, 0, None, None) == -1         # epochs start at 1
+    assert L.cfrk_hist_allreduce_device(odd, two, 0, 2, 16, 1, None, None) == -1         # misaligned table
+    assert L.cfrk_hist_allreduce_device(nul, two, 0, 2, 16, 1, None, None) == -1
+    assert b"" != L.cfrk_last_error()
+
+
 @pytest.mark.skipif(cf.device_count() > 0, reason="a GPU is present")
 def test_fails_loudly_without_gpu(tmp_path):
     with pytest.raises(cf.CfrkError) as e:
